@@ -1,0 +1,509 @@
+// capi.cu -- the extern "C" boundary declared in include/drrt_gpu.h.
+// Host entry points stage caller buffers through device scratch owned by the
+// handle, on the handle's stream, and return after the results are on the host.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "store.cuh"
+
+namespace drrt {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+static cudaStream_t pick(Store *S, void *stream) {
+  return stream ? (cudaStream_t)stream : S->stream;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+#define ENTER(h)                                                         \
+  if (!(h)) return drrt::set_error(DRRT_ERR_INVALID, "null handle");      \
+  drrt::Store *S = reinterpret_cast<drrt::Store *>(h);                    \
+  std::lock_guard<std::mutex> lock__(S->mu);                              \
+  drrt::DeviceGuard guard__(S->device);                                   \
+  if (!guard__.ok) return drrt::set_error(DRRT_ERR_CUDA, "cudaSetDevice failed")
+
+static int upload(const void *src, void *dst, size_t bytes, cudaStream_t st) {
+  if (!bytes) return DRRT_OK;
+  DRRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+  return DRRT_OK;
+}
+static int download(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return DRRT_OK;
+  DRRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+  return DRRT_OK;
+}
+
+__global__ void counts_from_offsets(const int64_t *off, int64_t nq, int32_t *counts) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < nq) counts[i] = (int32_t)(off[i + 1] - off[i]);
+}
+
+static int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist) {
+  if (nq < 0 || k < 1 || (nq > 0 && (!q || !ids)))
+    return set_error(DRRT_ERR_INVALID, "knn: arguments");
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
+  DRRT_CHECK(S->i_stage.reserve(nq * k + 1, st));
+  DRRT_CHECK(S->d_stage.reserve(nq * k + 1, st));
+  DRRT_CHECK(upload(q, S->q_stage.p, 3 * nq * sizeof(double), st));
+  DRRT_CHECK(knn_batch_dev(S, nq, S->q_stage.p, k, S->i_stage.p, S->d_stage.p, st));
+  DRRT_CHECK(download(ids, S->i_stage.p, nq * k * sizeof(int32_t), st));
+  if (dist) DRRT_CHECK(download(dist, S->d_stage.p, nq * k * sizeof(double), st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+template <typename T>
+static int put(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t st) {
+  DRRT_CHECK(b.reserve(v.size() + 1, st));
+  return upload(v.data(), b.p, v.size() * sizeof(T), st);
+}
+
+static int edge_host(Store *S, int64_t n, const double *start, const double *end,
+                     const int32_t *sid, const int32_t *eid, int edge_kind, double robot_radius,
+                     double r_min, int in_warmup, uint8_t *verdict, double *length) {
+  if (n < 0 || (n > 0 && !verdict)) return set_error(DRRT_ERR_INVALID, "edgecheck: arguments");
+  bool by_id = sid && eid;
+  if (n > 0 && !by_id && !(start && end)) return set_error(DRRT_ERR_INVALID, "edgecheck: endpoints");
+  if (n == 0) return DRRT_OK;
+  cudaStream_t st = S->stream;
+  const double *sd = nullptr, *ed = nullptr;
+  const int32_t *si = nullptr, *ei = nullptr;
+  if (by_id) {
+    for (int64_t i = 0; i < n; i++)
+      if (sid[i] < 0 || sid[i] >= S->n || eid[i] < 0 || eid[i] >= S->n)
+        return set_error(DRRT_ERR_INVALID, "edgecheck: node id out of range at edge %lld", (long long)i);
+    DRRT_CHECK(S->i_stage.reserve(n, st));
+    DRRT_CHECK(S->i_stage2.reserve(n, st));
+    DRRT_CHECK(upload(sid, S->i_stage.p, n * sizeof(int32_t), st));
+    DRRT_CHECK(upload(eid, S->i_stage2.p, n * sizeof(int32_t), st));
+    si = S->i_stage.p; ei = S->i_stage2.p;
+  } else {
+    DRRT_CHECK(S->d_stage.reserve(3 * n, st));
+    DRRT_CHECK(S->d_stage2.reserve(3 * n, st));
+    DRRT_CHECK(upload(start, S->d_stage.p, 3 * n * sizeof(double), st));
+    DRRT_CHECK(upload(end, S->d_stage2.p, 3 * n * sizeof(double), st));
+    sd = S->d_stage.p; ed = S->d_stage2.p;
+  }
+  DRRT_CHECK(S->b_stage.reserve(n, st));
+  if (length) DRRT_CHECK(S->d_stage3.reserve(n, st));
+  // in_warmup_time_ (obstacle.cpp:883): no obstacle is consulted, lengths still computed
+  bool saved = S->has_obstacles;
+  if (in_warmup) S->has_obstacles = false;
+  int rc = edgecheck_batch_dev(S, n, sd, ed, si, ei, edge_kind, robot_radius, r_min, S->b_stage.p,
+                               length ? S->d_stage3.p : nullptr, st);
+  S->has_obstacles = saved;
+  DRRT_CHECK(rc);
+  DRRT_CHECK(download(verdict, S->b_stage.p, n, st));
+  if (length) DRRT_CHECK(download(length, S->d_stage3.p, n * sizeof(double), st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+}  // namespace drrt
+
+using namespace drrt;
+
+extern "C" {
+
+const char *drrt_last_error(void) { return g_last_error.c_str(); }
+int drrt_abi_version(void) { return DRRT_ABI_VERSION; }
+int64_t drrt_kernel_launch_count(void) { return g_launches.load(); }
+
+int drrt_store_create(int device, int dims, int n_wraps, const int *wrap_dims,
+                      const double *wrap_points, int metric, int64_t capacity_hint,
+                      drrt_store **out) {
+  if (!out) return set_error(DRRT_ERR_INVALID, "create: out == NULL");
+  *out = nullptr;
+  if (dims != 3) return set_error(DRRT_ERR_UNSUPPORTED, "create: dims must be 3 (x, y, theta)");
+  if (metric != DRRT_METRIC_R2S1_WRAP && metric != DRRT_METRIC_EUCLID)
+    return set_error(DRRT_ERR_INVALID, "create: unknown metric %d", metric);
+  if (n_wraps < 0 || n_wraps > 1)
+    return set_error(DRRT_ERR_UNSUPPORTED, "create: at most one wrapped dimension");
+  if (n_wraps == 1) {
+    if (!wrap_dims || !wrap_points) return set_error(DRRT_ERR_INVALID, "create: wrap arrays");
+    if (wrap_dims[0] != 2)
+      return set_error(DRRT_ERR_UNSUPPORTED, "create: only dimension 2 (theta) may wrap");
+    if (!(wrap_points[0] > 0.0)) return set_error(DRRT_ERR_INVALID, "create: wrap point <= 0");
+    if (metric == DRRT_METRIC_R2S1_WRAP && wrap_points[0] != DRRT_TWO_PI)
+      return set_error(DRRT_ERR_UNSUPPORTED,
+                       "create: the R2S1 metric wraps at 2.0*3.1415926536; wrap point differs");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_error(DRRT_ERR_NO_DEVICE, "create: no CUDA device (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return set_error(DRRT_ERR_INVALID, "create: device %d", device);
+  cudaDeviceProp prop;
+  DRRT_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_error(DRRT_ERR_NO_DEVICE, "create: device %d is sm_%d%d; built for sm_100a only",
+                     device, prop.major, prop.minor);
+  DeviceGuard guard(device);
+  if (!guard.ok) return set_error(DRRT_ERR_CUDA, "create: cudaSetDevice");
+  Store *S = new (std::nothrow) Store();
+  if (!S) return set_error(DRRT_ERR_NOMEM, "create: host allocation");
+  S->device = device;
+  S->metric = metric;
+  S->n_wraps = n_wraps;
+  S->wrap_point = n_wraps ? wrap_points[0] : 0.0;
+  S->period = (metric == DRRT_METRIC_R2S1_WRAP) ? DRRT_TWO_PI : (n_wraps ? wrap_points[0] : 0.0);
+  cudaError_t e = cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&S->d_pending, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&S->d_ticket, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&S->d_bounds, 6 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost(&S->h_pending, 64);
+  if (e == cudaSuccess) e = cudaMallocHost(&S->h_bounds, 6 * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost(&S->h_scalar, 8 * sizeof(int64_t));
+  if (e != cudaSuccess) {
+    delete S;
+    return set_error(DRRT_ERR_CUDA, "create: %s", cudaGetErrorString(e));
+  }
+  if (capacity_hint > 0) {
+    int rc = store_reserve_nodes(S, capacity_hint);
+    if (rc != DRRT_OK) { delete S; return rc; }
+  }
+  *out = reinterpret_cast<drrt_store *>(S);
+  return DRRT_OK;
+}
+
+int drrt_store_destroy(drrt_store *h) {
+  if (!h) return DRRT_OK;
+  Store *S = reinterpret_cast<Store *>(h);
+  {
+    DeviceGuard guard(S->device);
+    cudaStreamSynchronize(S->stream);
+    S->x.release(); S->y.release(); S->th.release(); S->gate.release();
+    S->parent.release(); S->left.release(); S->right.release(); S->split.release();
+    S->ins_cur.release(); S->ins_split.release(); S->ins_gate.release(); S->stage_pos.release();
+    S->rec.release(); S->cell_start.release(); S->cell_of.release(); S->rank_in_cell.release();
+    S->scan_tmp.release();
+    S->r_offsets.release(); S->r_ids.release(); S->r_dist.release(); S->r_desc.release();
+    S->q_stage.release(); S->rad_stage.release();
+    S->i_stage.release(); S->i_stage2.release(); S->d_stage.release(); S->d_stage2.release();
+    S->d_stage3.release(); S->b_stage.release();
+    S->o_kind.release(); S->o_voff.release(); S->oa_kind.release(); S->oa_voff.release();
+    S->oa_live.release(); S->o_ox.release(); S->o_oy.release(); S->o_rad.release();
+    S->o_vx.release(); S->o_vy.release(); S->oa_ox.release(); S->oa_oy.release();
+    S->oa_rad.release(); S->oa_vx.release(); S->oa_vy.release();
+    if (S->d_pending) cudaFree(S->d_pending);
+    if (S->d_ticket) cudaFree(S->d_ticket);
+    if (S->d_bounds) cudaFree(S->d_bounds);
+    if (S->h_pending) cudaFreeHost(S->h_pending);
+    if (S->h_bounds) cudaFreeHost(S->h_bounds);
+    if (S->h_scalar) cudaFreeHost(S->h_scalar);
+    if (S->stream) cudaStreamDestroy(S->stream);
+  }
+  delete S;
+  return DRRT_OK;
+}
+
+int drrt_store_size(drrt_store *h, int64_t *n) {
+  ENTER(h);
+  if (!n) return set_error(DRRT_ERR_INVALID, "size: n == NULL");
+  *n = S->n;
+  return DRRT_OK;
+}
+
+void *drrt_store_stream(drrt_store *h) {
+  return h ? (void *)reinterpret_cast<Store *>(h)->stream : nullptr;
+}
+
+int drrt_store_insert(drrt_store *h, int64_t n, const double *pos, int32_t *first_id) {
+  ENTER(h);
+  if (n < 0 || (n > 0 && !pos)) return set_error(DRRT_ERR_INVALID, "insert: arguments");
+  for (int64_t i = 0; i < 3 * n; i++)
+    if (!(pos[i] - pos[i] == 0.0))
+      return set_error(DRRT_ERR_UNSUPPORTED, "insert: non-finite coordinate at %lld", (long long)i);
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(S->stage_pos.reserve(3 * n, st));
+  DRRT_CHECK(upload(pos, S->stage_pos.p, 3 * n * sizeof(double), st));
+  DRRT_CHECK(store_insert_dev(S, n, S->stage_pos.p, st, first_id));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+int drrt_store_insert_dev(drrt_store *h, int64_t n, const double *pos_dev, void *stream,
+                          int32_t *first_id) {
+  ENTER(h);
+  if (n < 0 || (n > 0 && !pos_dev)) return set_error(DRRT_ERR_INVALID, "insert: arguments");
+  return store_insert_dev(S, n, pos_dev, pick(S, stream), first_id);
+}
+
+int drrt_store_structure(drrt_store *h, int64_t first, int64_t n, int32_t *parent, int32_t *left,
+                         int32_t *right, int32_t *split) {
+  ENTER(h);
+  if (first < 0 || n < 0 || first + n > S->n) return set_error(DRRT_ERR_INVALID, "structure: range");
+  cudaStream_t st = S->stream;
+  std::vector<uint8_t> sp;
+  if (parent) DRRT_CHECK(download(parent, S->parent.p + first, n * sizeof(int32_t), st));
+  if (left) DRRT_CHECK(download(left, S->left.p + first, n * sizeof(int32_t), st));
+  if (right) DRRT_CHECK(download(right, S->right.p + first, n * sizeof(int32_t), st));
+  if (split) {
+    sp.resize(n);
+    DRRT_CHECK(download(sp.data(), S->split.p + first, n, st));
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  for (int64_t i = 0; i < n; i++) {
+    if (left && left[i] == 0x7fffffff) left[i] = -1;
+    if (right && right[i] == 0x7fffffff) right[i] = -1;
+    if (split) split[i] = sp[i];
+  }
+  return DRRT_OK;
+}
+
+int drrt_store_positions(drrt_store *h, int64_t first, int64_t n, double *pos) {
+  ENTER(h);
+  if (first < 0 || n < 0 || first + n > S->n || (n > 0 && !pos))
+    return set_error(DRRT_ERR_INVALID, "positions: range");
+  cudaStream_t st = S->stream;
+  std::vector<double> tmp(3 * (size_t)n);
+  DRRT_CHECK(download(tmp.data(), S->x.p + first, n * sizeof(double), st));
+  DRRT_CHECK(download(tmp.data() + n, S->y.p + first, n * sizeof(double), st));
+  DRRT_CHECK(download(tmp.data() + 2 * n, S->th.p + first, n * sizeof(double), st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  for (int64_t i = 0; i < n; i++) {
+    pos[3 * i] = tmp[i];
+    pos[3 * i + 1] = tmp[n + i];
+    pos[3 * i + 2] = tmp[2 * n + i];
+  }
+  return DRRT_OK;
+}
+
+// ---- range ----------------------------------------------------------------
+
+int drrt_range_batch(drrt_store *h, int64_t nq, const double *q, const double *radius,
+                     double radius_all, int32_t *counts, int64_t *total) {
+  ENTER(h);
+  if (nq < 0 || (nq > 0 && (!q || !counts))) return set_error(DRRT_ERR_INVALID, "range: arguments");
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
+  DRRT_CHECK(upload(q, S->q_stage.p, 3 * nq * sizeof(double), st));
+  const double *rad_dev = nullptr;
+  if (radius) {
+    DRRT_CHECK(S->rad_stage.reserve(nq + 1, st));
+    DRRT_CHECK(upload(radius, S->rad_stage.p, nq * sizeof(double), st));
+    rad_dev = S->rad_stage.p;
+  }
+  drrt_range_result res{};
+  DRRT_CHECK(range_batch_dev(S, nq, S->q_stage.p, rad_dev, radius_all, st, &res));
+  if (nq > 0) {
+    DRRT_CHECK(S->i_stage.reserve(nq, st));
+    counts_from_offsets<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(res.offsets_dev, nq,
+                                                                      S->i_stage.p);
+    DRRT_LAUNCHED();
+    DRRT_CHECK(download(counts, S->i_stage.p, nq * sizeof(int32_t), st));
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  if (total) *total = res.total;
+  return DRRT_OK;
+}
+
+int drrt_range_fetch(drrt_store *h, int32_t *ids, double *dist) {
+  ENTER(h);
+  if (S->last_nq < 0) return set_error(DRRT_ERR_STATE, "fetch: no range batch on this handle");
+  cudaStream_t st = S->stream;
+  if (S->last_total > 0) {
+    if (ids) DRRT_CHECK(download(ids, S->r_ids.p, S->last_total * sizeof(int32_t), st));
+    if (dist) DRRT_CHECK(download(dist, S->r_dist.p, S->last_total * sizeof(double), st));
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+int drrt_range_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, const double *radius_dev,
+                         double radius_all, void *stream, drrt_range_result *out) {
+  ENTER(h);
+  if (nq < 0 || (nq > 0 && !q_dev)) return set_error(DRRT_ERR_INVALID, "range: arguments");
+  return range_batch_dev(S, nq, q_dev, radius_dev, radius_all, pick(S, stream), out);
+}
+
+// ---- nearest / knn --------------------------------------------------------
+
+int drrt_nearest_batch(drrt_store *h, int64_t nq, const double *q, int32_t *ids, double *dist) {
+  ENTER(h);
+  return knn_host(S, nq, q, 1, ids, dist);
+}
+int drrt_nearest_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, int32_t *ids_dev,
+                           double *dist_dev, void *stream) {
+  ENTER(h);
+  if (!q_dev || !ids_dev || !dist_dev) return set_error(DRRT_ERR_INVALID, "nearest: arguments");
+  return knn_batch_dev(S, nq, q_dev, 1, ids_dev, dist_dev, pick(S, stream));
+}
+int drrt_knn_batch(drrt_store *h, int64_t nq, const double *q, int k, int32_t *ids, double *dist) {
+  ENTER(h);
+  return knn_host(S, nq, q, k, ids, dist);
+}
+int drrt_knn_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
+                       double *dist_dev, void *stream) {
+  ENTER(h);
+  if (!q_dev || !ids_dev || !dist_dev) return set_error(DRRT_ERR_INVALID, "knn: arguments");
+  return knn_batch_dev(S, nq, q_dev, k, ids_dev, dist_dev, pick(S, stream));
+}
+
+// ---- obstacles ------------------------------------------------------------
+
+int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const uint8_t *used,
+                       const double *life_span, const double *origin_xy, const double *radius,
+                       const int32_t *vert_off, const double *verts_xy) {
+  ENTER(h);
+  if (n_obs < 0) return set_error(DRRT_ERR_INVALID, "obstacles: n_obs < 0");
+  if (n_obs > 0 && (!kind || !used || !life_span || !origin_xy || !radius || !vert_off))
+    return set_error(DRRT_ERR_INVALID, "obstacles: null array");
+  for (int i = 0; i < n_obs; i++) {
+    if (kind[i] == 6 || kind[i] == 7)
+      return set_error(DRRT_ERR_UNSUPPORTED,
+                       "obstacles: kind %d (time-parametrised) needs a time dimension", kind[i]);
+    if (vert_off[i + 1] < vert_off[i]) return set_error(DRRT_ERR_INVALID, "obstacles: vert_off");
+  }
+  const int nv_all = n_obs ? vert_off[n_obs] : 0;
+  if (nv_all > 0 && !verts_xy) return set_error(DRRT_ERR_INVALID, "obstacles: verts");
+  std::vector<int32_t> k_all(kind, kind + n_obs), vo_all(n_obs + 1, 0), k_act, vo_act(1, 0);
+  std::vector<uint8_t> live(n_obs);
+  std::vector<double> ox(n_obs), oy(n_obs), rad(radius, radius + n_obs), vx(nv_all), vy(nv_all);
+  std::vector<double> aox, aoy, arad, avx, avy;
+  for (int i = 0; i <= n_obs; i++) vo_all[i] = n_obs ? vert_off[i] : 0;
+  for (int v = 0; v < nv_all; v++) { vx[v] = verts_xy[2 * v]; vy[v] = verts_xy[2 * v + 1]; }
+  for (int i = 0; i < n_obs; i++) {
+    ox[i] = origin_xy[2 * i];
+    oy[i] = origin_xy[2 * i + 1];
+    live[i] = (used[i] && !(life_span[i] <= 0)) ? 1 : 0;  // obstacle.cpp:761
+    // only a live ball or polygon can ever answer true (obstacle.cpp:781-804)
+    if (live[i] && (kind[i] == 1 || kind[i] == 3)) {
+      k_act.push_back(kind[i]);
+      aox.push_back(ox[i]); aoy.push_back(oy[i]); arad.push_back(rad[i]);
+      for (int v = vert_off[i]; v < vert_off[i + 1]; v++) { avx.push_back(vx[v]); avy.push_back(vy[v]); }
+      vo_act.push_back((int32_t)avx.size());
+    }
+  }
+  cudaStream_t st = S->stream;
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  DRRT_CHECK(put(S->o_kind, k_act, st)); DRRT_CHECK(put(S->o_voff, vo_act, st));
+  DRRT_CHECK(put(S->o_ox, aox, st)); DRRT_CHECK(put(S->o_oy, aoy, st));
+  DRRT_CHECK(put(S->o_rad, arad, st)); DRRT_CHECK(put(S->o_vx, avx, st));
+  DRRT_CHECK(put(S->o_vy, avy, st));
+  DRRT_CHECK(put(S->oa_kind, k_all, st)); DRRT_CHECK(put(S->oa_voff, vo_all, st));
+  DRRT_CHECK(put(S->oa_live, live, st));
+  DRRT_CHECK(put(S->oa_ox, ox, st)); DRRT_CHECK(put(S->oa_oy, oy, st));
+  DRRT_CHECK(put(S->oa_rad, rad, st)); DRRT_CHECK(put(S->oa_vx, vx, st));
+  DRRT_CHECK(put(S->oa_vy, vy, st));
+  DRRT_CUDA(cudaStreamSynchronize(st));  // host vectors die at return
+  ObstacleTable &T = S->obs;
+  T.n_active = (int32_t)k_act.size();
+  T.n_active_verts = (int32_t)avx.size();
+  T.kind = S->o_kind.p; T.ox = S->o_ox.p; T.oy = S->o_oy.p; T.rad = S->o_rad.p;
+  T.vert_off = S->o_voff.p; T.vx = S->o_vx.p; T.vy = S->o_vy.p;
+  T.n_all = n_obs;
+  T.a_kind = S->oa_kind.p; T.a_live = S->oa_live.p; T.a_ox = S->oa_ox.p; T.a_oy = S->oa_oy.p;
+  T.a_rad = S->oa_rad.p; T.a_vert_off = S->oa_voff.p; T.a_vx = S->oa_vx.p; T.a_vy = S->oa_vy.p;
+  S->has_obstacles = true;
+  return DRRT_OK;
+}
+
+// ---- edge checks ----------------------------------------------------------
+
+int drrt_edgecheck_batch(drrt_store *h, int64_t n, const double *start, const double *end,
+                         int edge_kind, double robot_radius, double r_min, int in_warmup,
+                         uint8_t *verdict, double *length) {
+  ENTER(h);
+  return edge_host(S, n, start, end, nullptr, nullptr, edge_kind, robot_radius, r_min, in_warmup,
+                   verdict, length);
+}
+
+int drrt_edgecheck_ids_batch(drrt_store *h, int64_t n, const int32_t *start_id,
+                             const int32_t *end_id, int edge_kind, double robot_radius,
+                             double r_min, int in_warmup, uint8_t *verdict, double *length) {
+  ENTER(h);
+  if (n > 0 && (!start_id || !end_id)) return set_error(DRRT_ERR_INVALID, "edgecheck: ids");
+  return edge_host(S, n, nullptr, nullptr, start_id, end_id, edge_kind, robot_radius, r_min,
+                   in_warmup, verdict, length);
+}
+
+int drrt_edgecheck_batch_dev(drrt_store *h, int64_t n, const double *start_dev,
+                             const double *end_dev, const int32_t *start_id_dev,
+                             const int32_t *end_id_dev, int edge_kind, double robot_radius,
+                             double r_min, uint8_t *verdict_dev, double *length_dev, void *stream) {
+  ENTER(h);
+  return edgecheck_batch_dev(S, n, start_dev, end_dev, start_id_dev, end_id_dev, edge_kind,
+                             robot_radius, r_min, verdict_dev, length_dev, pick(S, stream));
+}
+
+int drrt_dubins_trajectory_batch(drrt_store *h, int64_t n, const double *start, const double *end,
+                                 double r_min, double *xy, int32_t *npts, char *type,
+                                 double *length) {
+  ENTER(h);
+  if (n < 0 || (n > 0 && (!start || !end || !xy || !npts)))
+    return set_error(DRRT_ERR_INVALID, "trajectory: arguments");
+  if (n == 0) return DRRT_OK;
+  cudaStream_t st = S->stream;
+  const size_t per = (size_t)DRRT_TRAJ_MAX * 2;
+  DRRT_CHECK(S->d_stage.reserve(3 * n, st));
+  DRRT_CHECK(S->d_stage2.reserve(3 * n, st));
+  DRRT_CHECK(S->d_stage3.reserve(n * per + n, st));
+  DRRT_CHECK(S->i_stage.reserve(n, st));
+  DRRT_CHECK(S->b_stage.reserve(4 * n, st));
+  DRRT_CHECK(upload(start, S->d_stage.p, 3 * n * sizeof(double), st));
+  DRRT_CHECK(upload(end, S->d_stage2.p, 3 * n * sizeof(double), st));
+  double *len_dev = S->d_stage3.p + n * per;
+  DRRT_CHECK(trajectory_batch_dev(S, n, S->d_stage.p, S->d_stage2.p, r_min, S->d_stage3.p,
+                                  S->i_stage.p, (char *)S->b_stage.p, len_dev, st));
+  DRRT_CHECK(download(xy, S->d_stage3.p, n * per * sizeof(double), st));
+  DRRT_CHECK(download(npts, S->i_stage.p, n * sizeof(int32_t), st));
+  if (type) DRRT_CHECK(download(type, S->b_stage.p, 4 * n, st));
+  if (length) DRRT_CHECK(download(length, len_dev, n * sizeof(double), st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+int drrt_pointcheck_batch(drrt_store *h, int64_t n, const double *pts, double robot_radius,
+                          double collision_distance, uint8_t *verdict) {
+  ENTER(h);
+  if (n < 0 || (n > 0 && (!pts || !verdict))) return set_error(DRRT_ERR_INVALID, "pointcheck: arguments");
+  if (n == 0) return DRRT_OK;
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(S->d_stage.reserve(3 * n, st));
+  DRRT_CHECK(S->b_stage.reserve(n, st));
+  DRRT_CHECK(upload(pts, S->d_stage.p, 3 * n * sizeof(double), st));
+  DRRT_CHECK(pointcheck_batch_dev(S, n, S->d_stage.p, robot_radius, collision_distance,
+                                  S->b_stage.p, st));
+  DRRT_CHECK(download(verdict, S->b_stage.p, n, st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+int drrt_pointcheck_batch_dev(drrt_store *h, int64_t n, const double *pts_dev, double robot_radius,
+                              double collision_distance, uint8_t *verdict_dev, void *stream) {
+  ENTER(h);
+  return pointcheck_batch_dev(S, n, pts_dev, robot_radius, collision_distance, verdict_dev,
+                              pick(S, stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// geom.cuh -- device restatements of the reference's 2-D geometry helpers
+// (src/distancefunctions.cpp) and of the Dubins candidate solve
+// (DubinsEdge::CalculateTrajectory, src/dubinsedge.cpp:172-449), in the
+// reference's floating-point operation order.  No FMA contraction
+// (-fmad=false); sin/cos/atan2/acos are CUDA's double-precision routines,
+// which differ from glibc by at most a few ulp (DESIGN.md "Trig parity").
+#pragma once
+
+#include "common.cuh"
+
+namespace drrt {
+
+// DistanceSqrdPointToSegment  distancefunctions.cpp:50-74
+__device__ __forceinline__ double dist_sqrd_point_segment(double px, double py, double sx,
+                                                          double sy, double ex, double ey) {
+  double vx = px - sx, vy = py - sy;
+  double ux = ex - sx, uy = ey - sy;
+  double determinate = vx * ux + vy * uy;
+  if (determinate <= 0) return vx * vx + vy * vy;
+  double len = ux * ux + uy * uy;
+  if (determinate >= len) return (ex - px) * (ex - px) + (ey - py) * (ey - py);
+  double c = ux * vy - uy * vx;
+  return c * c / len;
+}
+
+// SegmentDistSqrd  distancefunctions.cpp:94-164
+__device__ __forceinline__ double segment_dist_sqrd(double pax, double pay, double pbx, double pby,
+                                                    double qax, double qay, double qbx, double qby) {
+  bool possible = true;
+  double m, diffA, diffB;
+  if (fabs(pbx - pax) < 0.000001) {
+    if ((qax >= pax && qbx >= pax) || (qax <= pax && qbx <= pax)) possible = false;
+  } else {
+    m = (pby - pay) / (pbx - pax);
+    diffA = (m * (qax - pax) + pay) - qay;
+    diffB = (m * (qbx - pax) + pay) - qby;
+    if ((diffA > 0.0 && diffB > 0.0) || (diffA < 0.0 && diffB < 0.0)) possible = false;
+  }
+  if (possible) {
+    if (fabs(qbx - qax) < 0.000001) {
+      if ((pax >= qax && pbx >= qax) || (pax <= qax && pbx <= qax)) possible = false;
+    } else {
+      m = (qby - qay) / (qbx - qax);
+      diffA = (m * (pax - qax) + qay) - pay;
+      diffB = (m * (pbx - qax) + qay) - pby;
+      if ((diffA > 0.0 && diffB > 0.0) || (diffA < 0.0 && diffB < 0.0)) possible = false;
+    }
+  }
+  if (possible) return 0.0;
+  double d0 = dist_sqrd_point_segment(pax, pay, qax, qay, qbx, qby);
+  double d1 = dist_sqrd_point_segment(pbx, pby, qax, qay, qbx, qby);
+  double d2 = dist_sqrd_point_segment(qax, qay, pax, pay, pbx, pby);
+  double d3 = dist_sqrd_point_segment(qbx, qby, pax, pay, pbx, pby);
+  double mn = d0;
+  if (d1 < mn) mn = d1;
+  if (d2 < mn) mn = d2;
+  if (d3 < mn) mn = d3;
+  return mn;
+}
+
+// RightTurnDist / LeftTurnDist  distancefunctions.cpp:24-46
+__device__ __forceinline__ double right_turn_dist(double ax, double ay, double bx, double by,
+                                                  double cx, double cy, double r) {
+  double theta = atan2(ay - cy, ax - cx) - atan2(by - cy, bx - cx);
+  if (theta < 0) theta += 2 * 3.1415926536;
+  return theta * r;
+}
+__device__ __forceinline__ double left_turn_dist(double ax, double ay, double bx, double by,
+                                                 double cx, double cy, double r) {
+  double theta = atan2(by - cy, bx - cx) - atan2(ay - cy, ax - cx);
+  if (theta < 0) theta += 2 * 3.1415926536;
+  return theta * r;
+}
+
+// PointInPolygon  distancefunctions.cpp:166-205
+__device__ __forceinline__ bool point_in_polygon(double px, double py, const double *vx,
+                                                 const double *vy, int nv) {
+  if (nv < 2) return false;
+  int crossings = 0;
+  double sx = vx[nv - 1], sy = vy[nv - 1];
+  for (int i = 0; i < nv; i++) {
+    double ex = vx[i], ey = vy[i];
+    if ((sy > py && ey < py) || (sy < py && ey > py)) {
+      if (sx > px && ex > px) {
+        crossings++;
+      } else if (sx < px && ex < px) {
+      } else {
+        double mx = (sx < ex) ? ex : sx;
+        double t = 2 * mx;
+        double x = (-((sx * ey - sy * ex) * (px - t)) + ((sx - ex) * (px * py - py * t))) /
+                   ((sy - ey) * (px - t));
+        if (x > px) crossings++;
+      }
+    }
+    sx = ex;
+    sy = ey;
+  }
+  return (crossings % 2) == 1;
+}
+
+// DistToPolygonSqrd  distancefunctions.cpp:77-92
+__device__ __forceinline__ double dist_to_polygon_sqrd(double px, double py, const double *vx,
+                                                       const double *vy, int nv) {
+  double mn = DRRT_INF;
+  double sx = vx[nv - 1], sy = vy[nv - 1];
+  for (int i = 0; i < nv; i++) {
+    double ex = vx[i], ey = vy[i];
+    double d = dist_sqrd_point_segment(px, py, sx, sy, ex, ey);
+    if (d < mn) mn = d;
+    sx = ex;
+    sy = ey;
+  }
+  return mn;
+}
+
+// ---------------------------------------------------------------------------
+// Dubins word solved by CalculateTrajectory.  Each of the (up to) three parts
+// is an arc (centre, start/end angle as atan2 gives them, turn direction) or
+// the straight piece (two points).
+enum { TRAJ_XXX = 0, TRAJ_RSL, TRAJ_RSR, TRAJ_RLR, TRAJ_LSR, TRAJ_LSL, TRAJ_LRL, TRAJ_0S0 };
+enum { PART_NONE = 0, PART_ARC_R = 1, PART_ARC_L = 2, PART_LINE = 3 };
+
+struct DubinsPart {
+  int kind;
+  double cx, cy;  // arc centre            | line: first point
+  double a, b;    // arc phi_start/phi_end | line: second point
+};
+
+struct DubinsPath {
+  int type;
+  double dist;  // edge->dist_ (dubinsedge.cpp:808; INF when no candidate exists)
+  DubinsPart part[3];
+};
+
+__device__ __forceinline__ double len2(double dx, double dy) { return sqrt(dx * dx + dy * dy); }
+
+__device__ __forceinline__ void arc_part(DubinsPart &P, int kind, double cx, double cy, double fx,
+                                         double fy, double tx, double ty) {
+  P.kind = kind;
+  P.cx = cx;
+  P.cy = cy;
+  P.a = atan2(fy - cy, fx - cx);
+  P.b = atan2(ty - cy, tx - cx);
+}
+
+// edge_dist = Edge::NewEdge's dist_ (dubinsedge.cpp:19), read by the "0s0" test
+__device__ void dubins_solve(double sx, double sy, double st, double ex, double ey, double et,
+                             double r_min, double edge_dist, DubinsPath &out) {
+  // :183-202 turn-circle centres
+  double sn, cs;
+  sincos(st - (DRRT_PI / 2.0), &sn, &cs);
+  const double ircx = sx + r_min * cs, ircy = sy + r_min * sn;
+  sincos(st + (DRRT_PI / 2.0), &sn, &cs);
+  const double ilcx = sx + r_min * cs, ilcy = sy + r_min * sn;
+  sincos(et - (DRRT_PI / 2.0), &sn, &cs);
+  const double grcx = ex + r_min * cs, grcy = ey + r_min * sn;
+  sincos(et + (DRRT_PI / 2.0), &sn, &cs);
+  const double glcx = ex + r_min * cs, glcy = ey + r_min * sn;
+
+  double best = DRRT_INF;
+  int type = TRAJ_XXX;
+  double D, R, sq, a, b, d0, d1, v0, v1, first, second, third, len;
+
+  // rsl :216-254
+  double rsl_x0 = 0, rsl_x1 = 0, rsl_y0 = 0, rsl_y1 = 0;
+  d0 = glcx - ircx; d1 = glcy - ircy;
+  D = sqrt(d0 * d0 + d1 * d1);
+  v0 = d0 / D; v1 = d1 / D;
+  R = -2.0 * r_min / D;
+  if (!(fabs(R) > 1.0)) {
+    sq = sqrt(1.0 - R * R);
+    a = r_min * (R * v0 + v1 * sq);
+    b = r_min * (R * v1 - v0 * sq);
+    rsl_x0 = ircx - a; rsl_x1 = glcx + a;
+    rsl_y0 = ircy - b; rsl_y1 = glcy + b;
+    first = right_turn_dist(sx, sy, rsl_x0, rsl_y0, ircx, ircy, r_min);
+    second = len2(rsl_x1 - rsl_x0, rsl_y1 - rsl_y0);
+    third = left_turn_dist(rsl_x1, rsl_y1, ex, ey, glcx, glcy, r_min);
+    len = first + second + third;
+    if (best > len) { best = len; type = TRAJ_RSL; }
+  }
+
+  // rsr :257-290
+  d0 = grcx - ircx; d1 = grcy - ircy;
+  D = sqrt(d0 * d0 + d1 * d1);
+  v0 = d0 / D; v1 = d1 / D;
+  const double rsr_x0 = -r_min * v1 + ircx, rsr_x1 = -r_min * v1 + grcx;
+  const double rsr_y0 = r_min * v0 + ircy, rsr_y1 = r_min * v0 + grcy;
+  first = right_turn_dist(sx, sy, rsr_x0, rsr_y0, ircx, ircy, r_min);
+  second = len2(rsr_x1 - rsr_x0, rsr_y1 - rsr_y0);
+  third = right_turn_dist(rsr_x1, rsr_y1, ex, ey, grcx, grcy, r_min);
+  len = first + second + third;
+  if (best > len) { best = len; type = TRAJ_RSR; }
+
+  // rlr :293-328 (D, v of rsr)
+  double rlr_rlx = 0, rlr_rly = 0, rlr_lrx = 0, rlr_lry = 0, rlr_cx = 0, rlr_cy = 0;
+  if (D < 4.0 * r_min) {
+    double theta = -acos(D / (4 * r_min)) + atan2(v1, v0);
+    sincos(theta, &sn, &cs);
+    rlr_cx = ircx + 2 * r_min * cs;
+    rlr_cy = ircy + 2 * r_min * sn;
+    rlr_rlx = (rlr_cx + ircx) / 2.0; rlr_rly = (rlr_cy + ircy) / 2.0;
+    rlr_lrx = (rlr_cx + grcx) / 2.0; rlr_lry = (rlr_cy + grcy) / 2.0;
+    first = right_turn_dist(sx, sy, rlr_rlx, rlr_rly, ircx, ircy, r_min);
+    second = left_turn_dist(rlr_rlx, rlr_rly, rlr_lrx, rlr_lry, rlr_cx, rlr_cy, r_min);
+    third = right_turn_dist(rlr_lrx, rlr_lry, ex, ey, grcx, grcy, r_min);
+    len = first + second + third;
+    if (best > len) { best = len; type = TRAJ_RLR; }
+  }
+
+  // lsr :331-369
+  double lsr_x0 = 0, lsr_x1 = 0, lsr_y0 = 0, lsr_y1 = 0;
+  d0 = grcx - ilcx; d1 = grcy - ilcy;
+  D = sqrt(d0 * d0 + d1 * d1);
+  v0 = d0 / D; v1 = d1 / D;
+  R = 2.0 * r_min / D;
+  if (!(fabs(R) > 1.0)) {
+    sq = sqrt(1.0 - R * R);
+    a = R * v0 + v1 * sq;
+    b = R * v1 - v0 * sq;
+    lsr_x0 = ilcx + a * r_min; lsr_x1 = grcx - a * r_min;
+    lsr_y0 = ilcy + b * r_min; lsr_y1 = grcy - b * r_min;
+    first = left_turn_dist(sx, sy, lsr_x0, lsr_y0, ilcx, ilcy, r_min);
+    second = len2(lsr_x1 - lsr_x0, lsr_y1 - lsr_y0);
+    third = right_turn_dist(lsr_x1, lsr_y1, ex, ey, grcx, grcy, r_min);
+    len = first + second + third;
+    if (best > len) { best = len; type = TRAJ_LSR; }
+  }
+
+  // lsl :372-405
+  d0 = glcx - ilcx; d1 = glcy - ilcy;
+  D = sqrt(d0 * d0 + d1 * d1);
+  v0 = d0 / D; v1 = d1 / D;
+  const double lsl_x0 = r_min * v1 + ilcx, lsl_x1 = r_min * v1 + glcx;
+  const double lsl_y0 = -r_min * v0 + ilcy, lsl_y1 = -r_min * v0 + glcy;
+  first = left_turn_dist(sx, sy, lsl_x0, lsl_y0, ilcx, ilcy, r_min);
+  second = len2(lsl_x1 - lsl_x0, lsl_y1 - lsl_y0);
+  third = left_turn_dist(lsl_x1, lsl_y1, ex, ey, glcx, glcy, r_min);
+  len = first + second + third;
+  if (best > len) { best = len; type = TRAJ_LSL; }
+
+  // lrl :408-443 (D, v of lsl; arc lengths R,L,R as the reference writes them)
+  double lrl_rlx = 0, lrl_rly = 0, lrl_lrx = 0, lrl_lry = 0, lrl_cx = 0, lrl_cy = 0;
+  if (D < 4.0 * r_min) {
+    double theta = -acos(D / (4 * r_min)) + atan2(v1, v0);
+    sincos(theta, &sn, &cs);
+    lrl_cx = ilcx + 2 * r_min * cs;
+    lrl_cy = ilcy + 2 * r_min * sn;
+    lrl_lrx = (lrl_cx + ilcx) / 2.0; lrl_lry = (lrl_cy + ilcy) / 2.0;
+    lrl_rlx = (lrl_cx + glcx) / 2.0; lrl_rly = (lrl_cy + glcy) / 2.0;
+    first = right_turn_dist(sx, sy, lrl_lrx, lrl_lry, ilcx, ilcy, r_min);
+    second = left_turn_dist(lrl_lrx, lrl_lry, lrl_rlx, lrl_rly, lrl_cx, lrl_cy, r_min);
+    third = right_turn_dist(lrl_rlx, lrl_rly, ex, ey, glcx, glcy, r_min);
+    len = first + second + third;
+    if (best > len) { best = len; type = TRAJ_LRL; }
+  }
+
+  if (edge_dist <= 2.0 && st == et) type = TRAJ_0S0;  // :445-449
+
+  out.type = type;
+  out.dist = best;
+  DubinsPart &P0 = out.part[0], &P1 = out.part[1], &P2 = out.part[2];
+  P0.kind = P1.kind = P2.kind = PART_NONE;
+  switch (type) {  // :467-723
+    case TRAJ_RSL:
+      arc_part(P0, PART_ARC_R, ircx, ircy, sx, sy, rsl_x0, rsl_y0);
+      P1.kind = PART_LINE; P1.cx = rsl_x0; P1.cy = rsl_y0; P1.a = rsl_x1; P1.b = rsl_y1;
+      arc_part(P2, PART_ARC_L, glcx, glcy, rsl_x1, rsl_y1, ex, ey);
+      break;
+    case TRAJ_RSR:
+      arc_part(P0, PART_ARC_R, ircx, ircy, sx, sy, rsr_x0, rsr_y0);
+      P1.kind = PART_LINE; P1.cx = rsr_x0; P1.cy = rsr_y0; P1.a = rsr_x1; P1.b = rsr_y1;
+      arc_part(P2, PART_ARC_R, grcx, grcy, rsr_x1, rsr_y1, ex, ey);
+      break;
+    case TRAJ_RLR:
+      arc_part(P0, PART_ARC_R, ircx, ircy, sx, sy, rlr_rlx, rlr_rly);
+      arc_part(P1, PART_ARC_L, rlr_cx, rlr_cy, rlr_rlx, rlr_rly, rlr_lrx, rlr_lry);
+      arc_part(P2, PART_ARC_R, grcx, grcy, rlr_lrx, rlr_lry, ex, ey);
+      break;
+    case TRAJ_LSR:
+      arc_part(P0, PART_ARC_L, ilcx, ilcy, sx, sy, lsr_x0, lsr_y0);
+      P1.kind = PART_LINE; P1.cx = lsr_x0; P1.cy = lsr_y0; P1.a = lsr_x1; P1.b = lsr_y1;
+      arc_part(P2, PART_ARC_R, grcx, grcy, lsr_x1, lsr_y1, ex, ey);
+      break;
+    case TRAJ_LSL:
+      arc_part(P0, PART_ARC_L, ilcx, ilcy, sx, sy, lsl_x0, lsl_y0);
+      P1.kind = PART_LINE; P1.cx = lsl_x0; P1.cy = lsl_y0; P1.a = lsl_x1; P1.b = lsl_y1;
+      arc_part(P2, PART_ARC_L, glcx, glcy, lsl_x1, lsl_y1, ex, ey);
+      break;
+    case TRAJ_LRL:
+      arc_part(P0, PART_ARC_L, ilcx, ilcy, sx, sy, lrl_lrx, lrl_lry);
+      arc_part(P1, PART_ARC_R, lrl_cx, lrl_cy, lrl_lrx, lrl_lry, lrl_rlx, lrl_rly);
+      arc_part(P2, PART_ARC_L, glcx, glcy, lrl_rlx, lrl_rly, ex, ey);
+      break;
+    case TRAJ_0S0:
+      P1.kind = PART_LINE; P1.cx = sx; P1.cy = sy; P1.a = ex; P1.b = ey;
+      break;
+    default:
+      break;
+  }
+}
+
+// Walks the polyline of a solved path point by point, in the order
+// CalculateTrajectory stores it (:484-502 and siblings; :577-583).
+struct PolylineWalker {
+  const DubinsPath *path;
+  double r_min;
+  int part;       // current part, 3 = done
+  int i, n;       // index / count within the part
+  double val, phi_end;
+  bool ended, equal;
+
+  __device__ __forceinline__ void begin_part() {
+    while (part < 3) {
+      const DubinsPart &P = path->part[part];
+      if (P.kind == PART_LINE) { n = 2; i = 0; return; }
+      if (P.kind == PART_ARC_R || P.kind == PART_ARC_L) {
+        double pe = P.b;
+        if (P.kind == PART_ARC_R) { if (pe > P.a) pe -= 2.0 * DRRT_PI; }
+        else { if (pe < P.a) pe += 2.0 * DRRT_PI; }
+        phi_end = pe;
+        n = (int)(ceil(fabs(pe - P.a) / 0.1) + 1);
+        if (n > DRRT_TRAJ_MAX) n = DRRT_TRAJ_MAX;
+        equal = (pe == P.a);
+        val = P.a;
+        ended = false;
+        i = 0;
+        if (n > 0) return;
+      }
+      part++;
+    }
+  }
+  __device__ __forceinline__ void start(const DubinsPath *p, double r) {
+    path = p; r_min = r; part = 0; i = 0; n = 0;
+    begin_part();
+  }
+  __device__ __forceinline__ bool next(double *x, double *y) {
+    if (part >= 3) return false;
+    const DubinsPart &P = path->part[part];
+    if (P.kind == PART_LINE) {
+      if (i == 0) { *x = P.cx; *y = P.cy; } else { *x = P.a; *y = P.b; }
+    } else {
+      double phi;
+      if (equal) {
+        phi = (i == 0) ? P.a : 0.0;
+      } else if (!ended) {
+        bool in = (P.kind == PART_ARC_R) ? (val >= phi_end) : (val <= phi_end);
+        if (in) { phi = val; if (P.kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
+        else { phi = phi_end; ended = true; }
+      } else {
+        phi = 0.0;  // entries the reference's loop never reaches stay Zero()
+      }
+      double sn, cs;
+      sincos(phi, &sn, &cs);
+      *x = P.cx + r_min * cs;
+      *y = P.cy + r_min * sn;
+    }
+    i++;
+    if (i >= n) { part++; begin_part(); }
+    return true;
+  }
+};
+
+}  // namespace drrt

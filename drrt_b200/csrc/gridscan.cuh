@@ -1,0 +1,199 @@
+// gridscan.cuh -- candidate enumeration over the cell-sorted node records,
+// shared by the range (K2) and k-nearest (K3) kernels.
+//
+// A query of radius r selects the (x,y) columns whose footprint comes within r
+// and, inside each column, one or two contiguous runs of records (theta is the
+// fastest cell index; the second run is the periodic wrap).  A warp flattens
+// the runs of 32 columns so every lane always has a candidate to evaluate.
+#pragma once
+
+#include "store.cuh"
+
+namespace drrt {
+
+static constexpr int RUNS_PER_BATCH = 64;  // 32 columns x (run + wrapped run)
+
+struct GridView {
+  const NodeRec *rec;
+  const int32_t *cell_start;
+  GridParams gp;
+  int64_t n_indexed, n;
+  const double *x, *y, *th, *gate;
+  int has_wrap;
+  double wrap_point;
+};
+
+inline GridView make_view(const Store *S) {
+  GridView V{};
+  V.rec = S->rec.p; V.cell_start = S->cell_start.p; V.gp = S->gp;
+  V.n_indexed = S->n_indexed; V.n = S->n;
+  V.x = S->x.p; V.y = S->y.p; V.th = S->th.p; V.gate = S->gate.p;
+  V.has_wrap = S->n_wraps > 0; V.wrap_point = S->wrap_point;
+  return V;
+}
+
+struct Query {
+  double x, y, t, r, s_hi;
+  double gt;
+  bool has_ghost;
+  int ix0, ix1, iy0, iy1;
+  int ta0, ta1, tb0, tb1;  // theta cell runs (b empty when tb0 > tb1)
+  double rr;
+};
+
+__device__ __forceinline__ int cell_floor(double v, double v0, double inv_h) {
+  double f = floor((v - v0) * inv_h);
+  if (f < -1.0e9) return -1000000000;
+  if (f > 1.0e9) return 1000000000;
+  return (int)f;
+}
+
+// Fills the probe (ghost) and the candidate cell ranges of a query of radius r:
+// every node n with metric(p,n) <= r for a probe p lies in the selected cells.
+template <int METRIC>
+__device__ __forceinline__ void setup_query(const GridView &A, double qx, double qy, double qt,
+                                            double r, Query &Q) {
+  Q.x = qx;
+  Q.y = qy;
+  Q.t = qt;
+  Q.r = r;
+  Q.s_hi = Q.r * Q.r * (1.0 + 1e-12) + 1e-300;
+  Q.has_ghost = false;
+  Q.gt = 0.0;
+  if (A.has_wrap) Q.has_ghost = ghost_of<METRIC>(Q.x, Q.y, Q.t, A.wrap_point, Q.r, &Q.gt);
+  const GridParams &g = A.gp;
+  double rr = fabs(Q.r) * (1.0 + 1e-9) + 1e-12;
+  Q.rr = rr;
+  int a = cell_floor(Q.x - rr, g.x0, g.inv_hx), b = cell_floor(Q.x + rr, g.x0, g.inv_hx);
+  Q.ix0 = max(a, 0); Q.ix1 = min(b, g.nx - 1);
+  if (b < 0) { Q.ix0 = Q.ix1 = 0; }
+  if (a > g.nx - 1) { Q.ix0 = Q.ix1 = g.nx - 1; }
+  a = cell_floor(Q.y - rr, g.y0, g.inv_hy); b = cell_floor(Q.y + rr, g.y0, g.inv_hy);
+  Q.iy0 = max(a, 0); Q.iy1 = min(b, g.ny - 1);
+  if (b < 0) { Q.iy0 = Q.iy1 = 0; }
+  if (a > g.ny - 1) { Q.iy0 = Q.iy1 = g.ny - 1; }
+  // theta cells
+  double slack = 1e-6 / g.inv_ht;
+  Q.tb0 = 1; Q.tb1 = 0;
+  if (g.periodic) {
+    double k = theta_key(Q.t, g.period);
+    if (!(2.0 * (rr + slack) < g.period * (1.0 - 1e-9)) || !(k == k)) {
+      Q.ta0 = 0; Q.ta1 = g.nt - 1;
+    } else {
+      int lo = cell_floor(k - rr - slack, g.t0, g.inv_ht);
+      int hi = cell_floor(k + rr + slack, g.t0, g.inv_ht);
+      if (hi - lo + 1 >= g.nt) {
+        Q.ta0 = 0; Q.ta1 = g.nt - 1;
+      } else {
+        Q.ta0 = max(lo, 0); Q.ta1 = min(hi, g.nt - 1);
+        if (lo < 0) { Q.tb0 = lo + g.nt; Q.tb1 = g.nt - 1; }
+        else if (hi > g.nt - 1) { Q.tb0 = 0; Q.tb1 = hi - g.nt; }
+        if (Q.tb0 <= Q.tb1 && Q.tb0 <= Q.ta1 && Q.ta0 <= Q.tb1) {  // overlap: merge
+          Q.ta0 = 0; Q.ta1 = g.nt - 1; Q.tb0 = 1; Q.tb1 = 0;
+        }
+      }
+    }
+  } else {
+    int lo = cell_floor(Q.t - rr - slack, g.t0, g.inv_ht);
+    int hi = cell_floor(Q.t + rr + slack, g.t0, g.inv_ht);
+    Q.ta0 = max(lo, 0); Q.ta1 = min(hi, g.nt - 1);
+    if (hi < 0) { Q.ta0 = Q.ta1 = 0; }
+    if (lo > g.nt - 1) { Q.ta0 = Q.ta1 = g.nt - 1; }
+    if (!(Q.t == Q.t)) { Q.ta0 = 0; Q.ta1 = g.nt - 1; }
+  }
+}
+
+
+// whether the selected cells cover the whole index
+__device__ __forceinline__ bool covers_all(const GridView &A, const Query &Q) {
+  const GridParams &g = A.gp;
+  return Q.ix0 == 0 && Q.ix1 == g.nx - 1 && Q.iy0 == 0 && Q.iy1 == g.ny - 1 && Q.ta0 == 0 &&
+         Q.ta1 == g.nt - 1;
+}
+
+// One warp visits column batches first, first+stride, ... of query Q and calls
+// f(valid, x, y, theta, id) once per candidate slot with all 32 lanes converged
+// (valid == false on padding lanes).
+template <class F>
+__device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, int first,
+                                             int stride, int *run_start, int *run_pref,
+                                             int lane, F f) {
+  const GridParams &g = A.gp;
+  const int ncy = Q.iy1 - Q.iy0 + 1;
+  const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
+  const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
+  for (int cb = first * 32; cb < ncol; cb += stride * 32) {
+    int col = cb + lane;
+    int s0 = 0, l0 = 0, s1 = 0, l1 = 0;
+    if (col < ncol) {
+      int ix = Q.ix0 + col / ncy, iy = Q.iy0 + col % ncy;
+      // closest approach of the column's footprint (edge columns are open-ended)
+      double xlo = g.x0 + ((double)ix - 1e-6) / g.inv_hx, xhi = g.x0 + ((double)ix + 1.000001) / g.inv_hx;
+      double ylo = g.y0 + ((double)iy - 1e-6) / g.inv_hy, yhi = g.y0 + ((double)iy + 1.000001) / g.inv_hy;
+      double dx = 0.0, dy = 0.0;
+      if (ix > 0 && Q.x < xlo) dx = xlo - Q.x;
+      if (ix < g.nx - 1 && Q.x > xhi) dx = Q.x - xhi;
+      if (iy > 0 && Q.y < ylo) dy = ylo - Q.y;
+      if (iy < g.ny - 1 && Q.y > yhi) dy = Q.y - yhi;
+      if (!(dx * dx + dy * dy > cull)) {
+        int cbase = (ix * g.ny + iy) * g.nt;
+        s0 = A.cell_start[cbase + Q.ta0];
+        l0 = A.cell_start[cbase + Q.ta1 + 1] - s0;
+        if (Q.tb0 <= Q.tb1) {
+          s1 = A.cell_start[cbase + Q.tb0];
+          l1 = A.cell_start[cbase + Q.tb1 + 1] - s1;
+        }
+      }
+    }
+    // exclusive scan of run lengths, two runs per lane
+    int tot = l0 + l1, inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    int excl = inc - tot;
+    int total = __shfl_sync(0xffffffffu, inc, 31);
+    __syncwarp();
+    run_start[2 * lane] = s0;
+    run_start[2 * lane + 1] = s1;
+    run_pref[2 * lane] = excl;
+    run_pref[2 * lane + 1] = excl + l0;
+    if (lane == 31) run_pref[RUNS_PER_BATCH] = total;
+    __syncwarp();
+    for (int i = lane; i < ((total + 31) & ~31); i += 32) {
+      bool valid = i < total;
+      double nx = 0.0, ny = 0.0, nt = 0.0;
+      int32_t id = 0;
+      if (valid) {
+        // largest run index j with run_pref[j] <= i
+        int lo = 0, hi = RUNS_PER_BATCH;
+#pragma unroll
+        for (int step = 0; step < 6; step++) {
+          int mid = (lo + hi) >> 1;
+          if (run_pref[mid] <= i) lo = mid; else hi = mid;
+        }
+        const NodeRec *r = A.rec + (run_start[lo] + (i - run_pref[lo]));
+        double2 xy = *reinterpret_cast<const double2 *>(&r->x);
+        double2 ti = *reinterpret_cast<const double2 *>(&r->th);
+        nx = xy.x; ny = xy.y; nt = ti.x;
+        id = (int32_t)(__double_as_longlong(ti.y) & 0xffffffffll);
+      }
+      f(valid, nx, ny, nt, id);
+    }
+  }
+}
+
+// nodes inserted after the last index build: straight from the SoA store
+template <class F>
+__device__ __forceinline__ void scan_tail(const GridView &A, int first, int stride, int lane, F f) {
+  for (int64_t b = A.n_indexed + (int64_t)first * 32; b < A.n; b += (int64_t)stride * 32) {
+    int64_t i = b + lane;
+    bool valid = i < A.n;
+    double nx = 0.0, ny = 0.0, nt = 0.0;
+    if (valid) { nx = A.x[i]; ny = A.y[i]; nt = A.th[i]; }
+    f(valid, nx, ny, nt, (int32_t)i);
+  }
+}
+
+}  // namespace drrt

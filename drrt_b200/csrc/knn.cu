@@ -1,0 +1,162 @@
+// knn.cu -- K3: batched nearest / k-nearest.
+//
+// KDTree::KDFindNearest (src/kdtree.cpp:264-307) returns the node of smallest
+// metric distance; KDTree::KDFindKNearest (:630-666) has no caller and does
+// not terminate as written, so it is built by intent: the k
+// smallest metric(q, n), ties by smaller id, ascending (dist, id).
+//
+// One warp per query.  The warp keeps its k best (dist, id) pairs sorted in
+// shared memory, scans the cells of a ball whose radius starts at the size
+// expected to hold ~2k nodes and doubles until the k-th best distance is
+// inside the scanned ball (nodes outside it are provably farther), and merges
+// candidates that beat the current k-th with ballot + warp-cooperative insert.
+#include <math.h>
+
+#include <algorithm>
+
+#include "gridscan.cuh"
+
+namespace drrt {
+
+static constexpr int KNN_WARPS = 8;
+static constexpr int KNN_KMAX = 128;
+
+struct KnnArgs {
+  GridView V;
+  const double *q;
+  int64_t nq;
+  int k;
+  double r0;
+  int32_t *ids;
+  double *dist;
+};
+
+struct TopK {
+  double *d;   // shared, k entries ascending
+  int32_t *id;
+  int k;
+  int count;        // warp-uniform
+  double worst_d;   // warp-uniform (count == k), else +inf
+  int32_t worst_id;
+};
+
+__device__ __forceinline__ bool pair_less(double d0, int32_t i0, double d1, int32_t i1) {
+  return d0 < d1 || (d0 == d1 && i0 < i1);
+}
+
+// all lanes call with the same (d, id)
+__device__ __forceinline__ void topk_insert(TopK &T, double d, int32_t id, int lane) {
+  // position = number of kept pairs smaller than (d,id)
+  int pos = 0;
+  for (int b = 0; b < T.count; b += 32) {
+    int i = b + lane;
+    bool less = i < T.count && pair_less(T.d[i], T.id[i], d, id);
+    pos += __popc(__ballot_sync(0xffffffffu, less));
+  }
+  int last = (T.count < T.k) ? T.count : T.k - 1;  // slot that receives the shifted tail
+  // shift [pos, last) right by one, highest first
+  for (int b = ((last - 1) / 32) * 32; b >= 0 && last > pos; b -= 32) {
+    int i = b + lane;
+    double td = 0.0;
+    int32_t ti = 0;
+    bool mv = i >= pos && i < last;
+    if (mv) { td = T.d[i]; ti = T.id[i]; }
+    __syncwarp();
+    if (mv) { T.d[i + 1] = td; T.id[i + 1] = ti; }
+    __syncwarp();
+  }
+  if (lane == 0) { T.d[pos] = d; T.id[pos] = id; }
+  __syncwarp();
+  if (T.count < T.k) T.count++;
+  if (T.count == T.k) { T.worst_d = T.d[T.k - 1]; T.worst_id = T.id[T.k - 1]; }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_kernel(KnnArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_runs[KNN_WARPS][RUNS_PER_BATCH];
+  __shared__ int s_pref[KNN_WARPS][RUNS_PER_BATCH + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t qi = (int64_t)blockIdx.x * KNN_WARPS + w;
+  if (qi >= A.nq) return;
+  const GridView &V = A.V;
+  TopK T;
+  T.k = A.k;
+  T.d = reinterpret_cast<double *>(smem_raw) + (size_t)w * A.k;
+  T.id = reinterpret_cast<int32_t *>(smem_raw + sizeof(double) * KNN_WARPS * A.k) + (size_t)w * A.k;
+  const double qx = A.q[3 * qi], qy = A.q[3 * qi + 1], qt = A.q[3 * qi + 2];
+
+  auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
+    bool cand = false;
+    double d = 0.0;
+    if (valid) {
+      double s = metric_sum<METRIC>(qx, qy, qt, nx, ny, nt);
+      d = sqrt(s);
+      cand = (T.count < T.k) || pair_less(d, id, T.worst_d, T.worst_id);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, cand);
+    while (m) {
+      int src = __ffs(m) - 1;
+      m &= m - 1;
+      double cd = __shfl_sync(0xffffffffu, d, src);
+      int32_t ci = __shfl_sync(0xffffffffu, id, src);
+      if ((T.count < T.k) || pair_less(cd, ci, T.worst_d, T.worst_id)) topk_insert(T, cd, ci, lane);
+    }
+  };
+
+  double r = A.r0;
+  for (;;) {
+    T.count = 0;
+    T.worst_d = 1.0e308;
+    T.worst_id = 0x7fffffff;
+    Query Q;
+    bool all = true;
+    if (V.n_indexed > 0) {
+      setup_query<METRIC>(V, qx, qy, qt, r, Q);
+      Q.has_ghost = false;
+      all = covers_all(V, Q);
+      scan_columns(V, Q, 0, 1, s_runs[w], s_pref[w], lane, visit);
+    }
+    scan_tail(V, 0, 1, lane, visit);
+    // every unscanned node is farther than r
+    if (all || (T.count == T.k && T.worst_d <= r)) break;
+    r *= 2.0;
+  }
+  __syncwarp();
+  for (int i = lane; i < A.k; i += 32) {
+    bool have = i < T.count;
+    A.ids[qi * A.k + i] = have ? T.id[i] : -1;
+    A.dist[qi * A.k + i] = have ? T.d[i] : DRRT_INF;
+  }
+}
+
+int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
+                  double *dist_dev, cudaStream_t st) {
+  if (nq < 0 || k < 1) return set_error(DRRT_ERR_INVALID, "knn: bad nq/k");
+  if (k > KNN_KMAX) return set_error(DRRT_ERR_UNSUPPORTED, "knn: k > %d", KNN_KMAX);
+  if (nq == 0) return DRRT_OK;
+  DRRT_CHECK(ensure_index(S, nq, st));
+  KnnArgs A{};
+  A.V = make_view(S);
+  A.q = q_dev; A.nq = nq; A.k = k; A.ids = ids_dev; A.dist = dist_dev;
+  A.r0 = 1.0;
+  if (S->n_indexed > 0) {
+    const GridParams &g = S->gp;
+    double vol = (g.nx / g.inv_hx) * (g.ny / g.inv_hy) * (g.nt / g.inv_ht);
+    double want = 2.0 * k + 8.0;
+    A.r0 = cbrt(want * vol / ((double)S->n_indexed * 4.18879));
+    if (!(A.r0 > 0.0) || !std::isfinite(A.r0)) A.r0 = 1.0;
+  }
+  size_t smem = (size_t)KNN_WARPS * k * (sizeof(double) + sizeof(int32_t));
+  unsigned nb = (unsigned)((nq + KNN_WARPS - 1) / KNN_WARPS);
+  if (S->metric == DRRT_METRIC_EUCLID)
+    knn_kernel<DRRT_METRIC_EUCLID><<<nb, KNN_WARPS * 32, smem, st>>>(A);
+  else
+    knn_kernel<DRRT_METRIC_R2S1_WRAP><<<nb, KNN_WARPS * 32, smem, st>>>(A);
+  DRRT_LAUNCHED();
+  DRRT_CUDA(cudaGetLastError());
+  return DRRT_OK;
+}
+
+}  // namespace drrt

@@ -1,0 +1,147 @@
+// store.cuh -- the GPU-resident node store behind drrt_store.
+//
+// Device twin of KDTree + KDTreeNode (include/DRRT/kdtree.h:13-181,
+// include/DRRT/kdtreenode.h:14-154): only position_ and the KD links go to the
+// device; the RRTx graph state stays with the host planner.
+//
+// HBM layout (N nodes, id = insertion order):
+//   x[N] y[N] th[N]            f64 SoA, 24 B/node       (id order)
+//   parent[N] left[N] right[N] i32, split[N] u8         insertion-ordered KD tree
+//   gate[N]                    f64: smallest theta among the theta-split
+//                              ancestors that hold the node in their LEFT
+//                              subtree (and the node itself once it has a
+//                              right child): decides whether the reference's
+//                              signed-hyperplane walk ever evaluates the node
+//   rec[N_indexed]             32-B NodeRec sorted by grid cell (the scan target)
+//   cell_start[ncell+1]        i32
+// Nodes inserted after the last index build form a short unsorted tail that
+// queries scan directly; the index is rebuilt when the tail is long enough to
+// matter (ensure_index).
+#pragma once
+
+#include "common.cuh"
+
+namespace drrt {
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  int reserve(size_t n, cudaStream_t s, bool keep = false, size_t keep_n = 0);
+  void release();
+};
+
+struct Store {
+  int device = 0;
+  int metric = 0;
+  int n_wraps = 0;
+  double wrap_point = 0.0;
+  double period = 0.0;  // theta key period (0: none)
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+
+  int64_t n = 0;
+  DevBuf<double> x, y, th, gate;
+  DevBuf<int32_t> parent, left, right;
+  DevBuf<uint8_t> split;
+
+  // insert scratch
+  DevBuf<int32_t> ins_cur;
+  DevBuf<uint8_t> ins_split;
+  DevBuf<double> ins_gate;
+  DevBuf<double> stage_pos;  // n x 3 upload staging (device)
+  int32_t *d_pending = nullptr;
+  int32_t *h_pending = nullptr;  // pinned
+
+  // grid index
+  int64_t n_indexed = 0;
+  GridParams gp{};
+  int64_t ncell = 0;
+  DevBuf<NodeRec> rec;
+  DevBuf<int32_t> cell_start, cell_of, rank_in_cell, scan_tmp;
+  double *d_bounds = nullptr;  // 6 doubles: minx maxx miny maxy mint maxt (ordered-int encoded)
+  double *h_bounds = nullptr;  // pinned
+
+  // range results
+  DevBuf<int64_t> r_offsets;  // nq+1
+  DevBuf<int32_t> r_ids;
+  DevBuf<double> r_dist;
+  DevBuf<unsigned long long> r_desc;  // look-back descriptors
+  DevBuf<double> q_stage, rad_stage;
+  int32_t *d_ticket = nullptr;
+  int64_t last_nq = -1, last_total = 0;
+  int64_t *h_scalar = nullptr;  // pinned scratch (8 x i64)
+
+  // generic staging for host entry points
+  DevBuf<int32_t> i_stage, i_stage2;
+  DevBuf<double> d_stage, d_stage2, d_stage3;
+  DevBuf<uint8_t> b_stage;
+
+  // obstacles
+  ObstacleTable obs{};
+  DevBuf<int32_t> o_kind, o_voff, oa_kind, oa_voff;
+  DevBuf<uint8_t> oa_live;
+  DevBuf<double> o_ox, o_oy, o_rad, o_vx, o_vy, oa_ox, oa_oy, oa_rad, oa_vx, oa_vy;
+  bool has_obstacles = false;
+};
+
+// store.cu
+int store_reserve_nodes(Store *S, int64_t need);
+int store_insert_dev(Store *S, int64_t n, const double *pos_dev, cudaStream_t st,
+                     int32_t *first_id);
+int ensure_index(Store *S, int64_t nq, cudaStream_t st);
+int rebuild_index(Store *S, cudaStream_t st);
+
+// scan.cu
+int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, DevBuf<int32_t> &tmp,
+                       cudaStream_t st);
+
+// range.cu
+int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *radius_dev,
+                    double radius_all, cudaStream_t st, drrt_range_result *out);
+// knn.cu
+int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
+                  double *dist_dev, cudaStream_t st);
+// edgecheck.cu
+int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const double *end_dev,
+                        const int32_t *sid_dev, const int32_t *eid_dev, int edge_kind,
+                        double robot_radius, double r_min, uint8_t *verdict_dev,
+                        double *length_dev, cudaStream_t st);
+int trajectory_batch_dev(Store *S, int64_t n, const double *start_dev, const double *end_dev,
+                         double r_min, double *xy_dev, int32_t *npts_dev, char *type_dev,
+                         double *length_dev, cudaStream_t st);
+int pointcheck_batch_dev(Store *S, int64_t n, const double *pts_dev, double robot_radius,
+                         double collision_distance, uint8_t *verdict_dev, cudaStream_t st);
+
+template <typename T>
+int DevBuf<T>::reserve(size_t n, cudaStream_t s, bool keep, size_t keep_n) {
+  if (n <= cap) return DRRT_OK;
+  size_t ncap = cap ? cap : 256;
+  while (ncap < n) ncap = ncap + ncap / 2 + 256;
+  T *np = nullptr;
+  cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+  if (e != cudaSuccess)
+    return set_error(DRRT_ERR_NOMEM, "cudaMalloc(%zu B): %s", ncap * sizeof(T),
+                     cudaGetErrorString(e));
+  if (p) {
+    if (keep && keep_n) {
+      e = cudaMemcpyAsync(np, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return set_error(DRRT_ERR_CUDA, "grow copy: %s", cudaGetErrorString(e));
+    }
+    // the old block may still be read by work queued on s
+    cudaStreamSynchronize(s);
+    cudaFree(p);
+  }
+  p = np;
+  cap = ncap;
+  return DRRT_OK;
+}
+
+template <typename T>
+void DevBuf<T>::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+}  // namespace drrt

@@ -1,0 +1,247 @@
+"""Host-side mirror of the reference's KDTree interface, batched.
+
+Names and argument meaning follow include/DRRT/kdtree.h:13-181; every method
+takes a BATCH of query points (rows) where the reference takes one, and forwards
+to the C ABI (include/drrt_gpu.h).  Results come back as numpy arrays; the
+`*_dev` variants take and return torch CUDA tensors and leave everything on the
+device.  There is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import (EDGE_DUBINS, EDGE_STRAIGHT, METRIC_EUCLID, METRIC_R2S1_WRAP, PI, c_dp, c_i64p,
+                   c_ip, c_u8p, check)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(ty)
+
+
+def _dev_ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _torch_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class KDTree:
+    """KDTree(int d, VectorXi wraps, VectorXd wrapPoints) kdtree.h:33-36 with
+    SetDistanceFunction (:47-49) folded into `metric`."""
+
+    def __init__(self, dims=3, wraps=(2,), wrap_points=(2.0 * PI,), metric=METRIC_R2S1_WRAP,
+                 device=0, capacity=0):
+        self._lib = capi.load()
+        self.dimensions_ = dims
+        self.metric = metric
+        self.device = device
+        w = np.asarray(wraps, dtype=np.int32).reshape(-1)
+        wp = np.asarray(wrap_points, dtype=np.float64).reshape(-1)
+        self.num_wraps_ = len(w)
+        h = C.c_void_p()
+        check(self._lib.drrt_store_create(device, dims, len(w), w.ctypes.data_as(C.POINTER(C.c_int)),
+                                          _ptr(wp, c_dp), metric, int(capacity), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.drrt_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- KDTree::tree_size_ kdtree.h:23
+    @property
+    def tree_size_(self):
+        n = C.c_int64()
+        check(self._lib.drrt_store_size(self._h, C.byref(n)))
+        return n.value
+
+    # -- KDTree::KDInsert kdtree.cpp:87-136 (rows inserted in order)
+    def KDInsert(self, positions):
+        pos = _f64(positions, (-1, 3))
+        first = C.c_int32()
+        check(self._lib.drrt_store_insert(self._h, pos.shape[0], _ptr(pos, c_dp), C.byref(first)))
+        return first.value
+
+    def KDInsert_dev(self, positions):
+        """positions: torch.float64 CUDA tensor (n,3) on this store's device."""
+        assert positions.is_cuda and positions.dtype.is_floating_point and positions.is_contiguous()
+        first = C.c_int32()
+        check(self._lib.drrt_store_insert_dev(self._h, positions.shape[0], _dev_ptr(positions),
+                                              _torch_stream(), C.byref(first)))
+        return first.value
+
+    def structure(self, first=0, n=None):
+        """kd_parent_/kd_child_L_/kd_child_R_/kd_split_ (kdtreenode.h:17-20,29), -1 = none."""
+        n = self.tree_size_ - first if n is None else n
+        arrs = [np.empty(n, dtype=np.int32) for _ in range(4)]
+        check(self._lib.drrt_store_structure(self._h, first, n, *[_ptr(a, c_ip) for a in arrs]))
+        return dict(parent=arrs[0], left=arrs[1], right=arrs[2], split=arrs[3])
+
+    def positions(self, first=0, n=None):
+        n = self.tree_size_ - first if n is None else n
+        pos = np.empty((n, 3), dtype=np.float64)
+        check(self._lib.drrt_store_positions(self._h, first, n, _ptr(pos, c_dp)))
+        return pos
+
+    # -- KDTree::KDFindWithinRange kdtree.cpp:794-820
+    def KDFindWithinRange(self, range_, query_points):
+        """-> (offsets int64[nq+1], ids int32[total], dists f64[total]); each row
+        sorted by node id.  range_: scalar or per-query array."""
+        q = _f64(query_points, (-1, 3))
+        nq = q.shape[0]
+        rad = None
+        r_all = 0.0
+        if np.ndim(range_) == 0:
+            r_all = float(range_)
+        else:
+            rad = _f64(range_, (nq,))
+        counts = np.zeros(nq, dtype=np.int32)
+        total = C.c_int64()
+        check(self._lib.drrt_range_batch(self._h, nq, _ptr(q, c_dp),
+                                         _ptr(rad, c_dp) if rad is not None else None, r_all,
+                                         _ptr(counts, c_ip), C.byref(total)))
+        ids = np.empty(total.value, dtype=np.int32)
+        dist = np.empty(total.value, dtype=np.float64)
+        check(self._lib.drrt_range_fetch(self._h, _ptr(ids, c_ip), _ptr(dist, c_dp)))
+        off = np.zeros(nq + 1, dtype=np.int64)
+        np.cumsum(counts, out=off[1:])
+        return off, ids, dist
+
+    # KDFindMoreWithinRange kdtree.cpp:822-851 is the same search; the caller's
+    # list de-duplication (AddToRangeList :670-682) is the caller's to do.
+    KDFindMoreWithinRange = KDFindWithinRange
+
+    def KDFindWithinRange_dev(self, range_, query_points):
+        """torch in / torch views out (valid until the next range call)."""
+        import torch
+        q = query_points
+        assert q.is_cuda and q.dtype == torch.float64 and q.is_contiguous()
+        rad_t = None
+        r_all = 0.0
+        if torch.is_tensor(range_):
+            rad_t = range_
+        else:
+            r_all = float(range_)
+        res = capi.RangeResult()
+        check(self._lib.drrt_range_batch_dev(self._h, q.shape[0], _dev_ptr(q), _dev_ptr(rad_t),
+                                             r_all, _torch_stream(), C.byref(res)))
+        return res
+
+    # -- KDTree::KDFindNearest kdtree.cpp:264-307
+    def KDFindNearest(self, query_points):
+        q = _f64(query_points, (-1, 3))
+        nq = q.shape[0]
+        ids = np.empty(nq, dtype=np.int32)
+        dist = np.empty(nq, dtype=np.float64)
+        check(self._lib.drrt_nearest_batch(self._h, nq, _ptr(q, c_dp), _ptr(ids, c_ip),
+                                           _ptr(dist, c_dp)))
+        return ids, dist
+
+    # -- KDTree::KDFindKNearest kdtree.cpp:630-666 (by intent)
+    def KDFindKNearest(self, k, query_points):
+        q = _f64(query_points, (-1, 3))
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int32)
+        dist = np.empty((nq, k), dtype=np.float64)
+        check(self._lib.drrt_knn_batch(self._h, nq, _ptr(q, c_dp), int(k), _ptr(ids, c_ip),
+                                       _ptr(dist, c_dp)))
+        return ids, dist
+
+    def KDFindKNearest_dev(self, k, q, ids_out, dist_out):
+        check(self._lib.drrt_knn_batch_dev(self._h, q.shape[0], _dev_ptr(q), int(k),
+                                           _dev_ptr(ids_out), _dev_ptr(dist_out), _torch_stream()))
+
+    # ---- ConfigSpace::obstacles_ + the edge / node checks (obstacle.h:252-282) ----
+    def SetObstacles(self, kind, used, life_span, origin, radius, vert_off, verts):
+        kind = np.ascontiguousarray(kind, dtype=np.int32)
+        used = np.ascontiguousarray(used, dtype=np.uint8)
+        life = _f64(life_span)
+        origin = _f64(origin, (-1, 2))
+        radius = _f64(radius)
+        voff = np.ascontiguousarray(vert_off, dtype=np.int32)
+        verts = _f64(verts, (-1, 2))
+        check(self._lib.drrt_obstacles_set(self._h, len(kind), _ptr(kind, c_ip), _ptr(used, c_u8p),
+                                           _ptr(life, c_dp), _ptr(origin, c_dp), _ptr(radius, c_dp),
+                                           _ptr(voff, c_ip), _ptr(verts, c_dp)))
+
+    # -- ExplicitEdgeCheck(C, edge) obstacle.cpp:879-923
+    def ExplicitEdgeCheck(self, start, end, robot_radius=0.5, r_min=1.0, edge_kind=EDGE_DUBINS,
+                          in_warmup=False, want_length=True):
+        s = _f64(start, (-1, 3))
+        e = _f64(end, (-1, 3))
+        n = s.shape[0]
+        verdict = np.zeros(n, dtype=np.uint8)
+        length = np.zeros(n, dtype=np.float64) if want_length else None
+        check(self._lib.drrt_edgecheck_batch(self._h, n, _ptr(s, c_dp), _ptr(e, c_dp), edge_kind,
+                                             float(robot_radius), float(r_min), int(in_warmup),
+                                             _ptr(verdict, c_u8p),
+                                             _ptr(length, c_dp) if want_length else None))
+        return (verdict, length) if want_length else verdict
+
+    def ExplicitEdgeCheckIds(self, start_ids, end_ids, robot_radius=0.5, r_min=1.0,
+                             edge_kind=EDGE_DUBINS, in_warmup=False):
+        si = np.ascontiguousarray(start_ids, dtype=np.int32)
+        ei = np.ascontiguousarray(end_ids, dtype=np.int32)
+        n = si.shape[0]
+        verdict = np.zeros(n, dtype=np.uint8)
+        length = np.zeros(n, dtype=np.float64)
+        check(self._lib.drrt_edgecheck_ids_batch(self._h, n, _ptr(si, c_ip), _ptr(ei, c_ip),
+                                                 edge_kind, float(robot_radius), float(r_min),
+                                                 int(in_warmup), _ptr(verdict, c_u8p),
+                                                 _ptr(length, c_dp)))
+        return verdict, length
+
+    def ExplicitEdgeCheck_dev(self, verdict_out, start=None, end=None, start_ids=None,
+                              end_ids=None, robot_radius=0.5, r_min=1.0, edge_kind=EDGE_DUBINS,
+                              length_out=None):
+        n = verdict_out.shape[0]
+        check(self._lib.drrt_edgecheck_batch_dev(self._h, n, _dev_ptr(start), _dev_ptr(end),
+                                                 _dev_ptr(start_ids), _dev_ptr(end_ids), edge_kind,
+                                                 float(robot_radius), float(r_min),
+                                                 _dev_ptr(verdict_out), _dev_ptr(length_out),
+                                                 _torch_stream()))
+
+    # -- LineCheck obstacle.cpp:1092-1143
+    def LineCheck(self, node1, node2, robot_radius=0.5):
+        return self.ExplicitEdgeCheck(node1, node2, robot_radius=robot_radius,
+                                      edge_kind=EDGE_STRAIGHT, want_length=False)
+
+    # -- DubinsEdge::CalculateTrajectory dubinsedge.cpp:172-830
+    def CalculateTrajectory(self, start, end, r_min=1.0):
+        s = _f64(start, (-1, 3))
+        e = _f64(end, (-1, 3))
+        n = s.shape[0]
+        xy = np.zeros((n, capi.TRAJ_MAX, 2), dtype=np.float64)
+        npts = np.zeros(n, dtype=np.int32)
+        types = C.create_string_buffer(4 * n)
+        length = np.zeros(n, dtype=np.float64)
+        check(self._lib.drrt_dubins_trajectory_batch(self._h, n, _ptr(s, c_dp), _ptr(e, c_dp),
+                                                     float(r_min), _ptr(xy, c_dp), _ptr(npts, c_ip),
+                                                     types, _ptr(length, c_dp)))
+        names = [types.raw[4 * i:4 * i + 3].decode() for i in range(n)]
+        return xy, npts, names, length
+
+    # -- ExplicitNodeCheck obstacle.cpp:1087-1090
+    def ExplicitNodeCheck(self, points, robot_radius=0.5, collision_distance=0.1):
+        p = _f64(points, (-1, 3))
+        verdict = np.zeros(p.shape[0], dtype=np.uint8)
+        check(self._lib.drrt_pointcheck_batch(self._h, p.shape[0], _ptr(p, c_dp),
+                                              float(robot_radius), float(collision_distance),
+                                              _ptr(verdict, c_u8p)))
+        return verdict

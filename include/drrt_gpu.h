@@ -1,0 +1,196 @@
+/* drrt_gpu.h -- C ABI of drrt_b200 (libdrrt_b200.so).
+ *
+ * The drop-in boundary for the data-parallel hot path of cosa0481/DRRT:
+ * batched KD-tree neighbourhood queries and batched edge collision checks.
+ * The reference has no FFI / plugin API; the boundary is the
+ * set of C++ methods cited beside each entry point below (paths relative to
+ * the reference root).  drrt_b200/shim/ re-implements those method signatures
+ * on top of this header; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every call returns an int status
+ *    (DRRT_OK == 0) and never throws or exits (the reference prints to stdout
+ *    and returns bool; fatal states call exit(-1)).
+ *  - node ids are dense insertion indices (id 0 == KDTree::root).
+ *  - `*_dev` entry points take DEVICE pointers and a cudaStream_t (as void*;
+ *    NULL = the store's own stream); the others take caller-owned HOST
+ *    pointers (pinned memory preferred) and include the copies.
+ *  - there is no CPU fallback: without a usable sm_100 device every call
+ *    fails with DRRT_ERR_NO_DEVICE / DRRT_ERR_CUDA.
+ *  - one store may be entered from several host threads (the reference takes
+ *    KDTree::tree_mutex_ around every tree call and cspace_mutex_ inside the
+ *    edge check); calls on one handle are serialised internally.
+ */
+#ifndef DRRT_GPU_H
+#define DRRT_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRRT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DRRT_API __attribute__((visibility("default")))
+#else
+#define DRRT_API
+#endif
+
+enum {
+  DRRT_OK = 0,
+  DRRT_ERR_INVALID = 1,     /* bad argument */
+  DRRT_ERR_UNSUPPORTED = 2, /* configuration the device path does not cover */
+  DRRT_ERR_CUDA = 3,        /* a CUDA call failed; see drrt_last_error() */
+  DRRT_ERR_NOMEM = 4,
+  DRRT_ERR_NO_DEVICE = 5,
+  DRRT_ERR_STATE = 6        /* call order (e.g. fetch without a batch) */
+};
+
+/* the reference passes a host function pointer (include/DRRT/kdtree.h:21,47-49);
+ * a device cannot call it, so the two metrics in the tree are enumerated */
+enum {
+  DRRT_METRIC_R2S1_WRAP = 0, /* distance_function  src/smalltest.cpp:167-175 */
+  DRRT_METRIC_EUCLID = 1     /* DistFunc           src/thetastar.cpp:10-15   */
+};
+
+enum {
+  DRRT_EDGE_DUBINS = 0,  /* DubinsEdge::CalculateTrajectory + ExplicitEdgeCheck */
+  DRRT_EDGE_STRAIGHT = 1 /* LineCheck  src/obstacle.cpp:1092-1143               */
+};
+
+typedef struct drrt_store drrt_store;
+
+DRRT_API const char *drrt_last_error(void);
+DRRT_API int drrt_abi_version(void);
+/* number of kernels this library has launched in this process (all handles) */
+DRRT_API int64_t drrt_kernel_launch_count(void);
+
+/* ---- node store + index ------------------------------------------------ */
+
+/* KDTree::KDTree(int d, VectorXi wraps, VectorXd wrapPoints)
+ * include/DRRT/kdtree.h:33-36 + SetDistanceFunction :47-49.
+ * Supported: dims == 3; n_wraps == 0, or n_wraps == 1 with wrap_dims[0] == 2
+ * (and, for DRRT_METRIC_R2S1_WRAP, wrap_points[0] == 2.0*3.1415926536). */
+DRRT_API int drrt_store_create(int device, int dims, int n_wraps, const int *wrap_dims,
+                      const double *wrap_points, int metric,
+                      int64_t capacity_hint, drrt_store **out);
+DRRT_API int drrt_store_destroy(drrt_store *h);
+DRRT_API int drrt_store_size(drrt_store *h, int64_t *n); /* KDTree::tree_size_ kdtree.h:23 */
+DRRT_API void *drrt_store_stream(drrt_store *h);        /* cudaStream_t of the handle */
+
+/* KDTree::KDInsert  src/kdtree.cpp:87-136, n nodes in order (pos = n x 3 f64,
+ * row-major).  first_id receives the id of pos[0]. Builds the same
+ * insertion-ordered KD tree (parent / children / split) on the device. */
+DRRT_API int drrt_store_insert(drrt_store *h, int64_t n, const double *pos,
+                      int32_t *first_id);
+DRRT_API int drrt_store_insert_dev(drrt_store *h, int64_t n, const double *pos_dev,
+                          void *stream, int32_t *first_id);
+
+/* KDTreeNode::kd_parent_/kd_child_L_/kd_child_R_/kd_split_
+ * include/DRRT/kdtreenode.h:17-20,29 for ids [first, first+n): -1 = none.
+ * (drrt.cpp:849 and KDTree::GetNodeAt kdtree.cpp:56-85 read them.) */
+DRRT_API int drrt_store_structure(drrt_store *h, int64_t first, int64_t n,
+                         int32_t *parent, int32_t *left, int32_t *right,
+                         int32_t *split);
+DRRT_API int drrt_store_positions(drrt_store *h, int64_t first, int64_t n, double *pos);
+
+/* ---- range ball ---------------------------------------------------------
+ * KDTree::KDFindWithinRange src/kdtree.cpp:794-820 (and the identical
+ * KDFindMoreWithinRange :822-851), ghost loop src/ghostpoint.cpp:15-75.
+ * radius: per-query array (nq) or NULL to use radius_all.
+ * Result: CSR over queries; each row sorted by node id; dist = the key the
+ * reference stores in the JList node (metric to the probe that found it).
+ * Two-call sizing: batch -> counts[nq] and *total; fetch -> ids/dist[total]
+ * laid out by the exclusive prefix sum of counts. */
+DRRT_API int drrt_range_batch(drrt_store *h, int64_t nq, const double *q,
+                     const double *radius, double radius_all, int32_t *counts,
+                     int64_t *total);
+DRRT_API int drrt_range_fetch(drrt_store *h, int32_t *ids, double *dist);
+
+/* device-resident variant: queries/radii on the device; results stay in
+ * library-owned device buffers valid until the next range call on h.
+ * offsets_dev has nq+1 int64 entries. */
+typedef struct {
+  int64_t nq;
+  int64_t total;
+  const int64_t *offsets_dev;
+  const int32_t *ids_dev;
+  const double *dist_dev;
+} drrt_range_result;
+DRRT_API int drrt_range_batch_dev(drrt_store *h, int64_t nq, const double *q_dev,
+                         const double *radius_dev, double radius_all,
+                         void *stream, drrt_range_result *out);
+
+/* ---- nearest / k-nearest -------------------------------------------------
+ * KDTree::KDFindNearest src/kdtree.cpp:264-307: id and distance of the
+ * nearest node (ties: smaller id).
+ * KDTree::KDFindKNearest src/kdtree.cpp:630-666 (dead and broken upstream,
+ * SURVEY F7): by intent, the k smallest metric(q,n), ties by smaller id,
+ * ascending (dist,id); rows padded with id -1 when the store has < k nodes. */
+DRRT_API int drrt_nearest_batch(drrt_store *h, int64_t nq, const double *q,
+                       int32_t *ids, double *dist);
+DRRT_API int drrt_nearest_batch_dev(drrt_store *h, int64_t nq, const double *q_dev,
+                           int32_t *ids_dev, double *dist_dev, void *stream);
+DRRT_API int drrt_knn_batch(drrt_store *h, int64_t nq, const double *q, int k,
+                   int32_t *ids, double *dist);
+DRRT_API int drrt_knn_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, int k,
+                       int32_t *ids_dev, double *dist_dev, void *stream);
+
+/* ---- obstacles + edge checks --------------------------------------------
+ * Flat copy of ConfigSpace::obstacles_ (List of Obstacle,
+ * include/DRRT/obstacle.h:16-211) with the fields the analytic checker reads:
+ * kind_, obstacle_used_, life_span_, origin_(0..1), radius_,
+ * shape_.GetPolygon() rows -- all in the WORLD frame.
+ * Kinds 6/7 (time-parametrised) -> DRRT_ERR_UNSUPPORTED. */
+DRRT_API int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind,
+                       const uint8_t *used, const double *life_span,
+                       const double *origin_xy, const double *radius,
+                       const int32_t *vert_off, const double *verts_xy);
+
+/* ExplicitEdgeCheck(C, edge) src/obstacle.cpp:879-923 over
+ * Edge::NewEdge + DubinsEdge::CalculateTrajectory src/dubinsedge.cpp:12-21,
+ * 172-830 + DubinsEdge::ExplicitEdgeCheck :850-898 with the analytic
+ * ExplicitEdgeCheck2D src/obstacle.cpp:756-804 per polyline segment
+ * (edge_kind DRRT_EDGE_STRAIGHT: the LineCheck polyline instead).
+ * start/end: n x 3 f64 poses.  verdict[i] = 1 when edge i collides.
+ * length (optional): edge->dist_ after CalculateTrajectory.
+ * in_warmup != 0 reproduces ConfigSpace::in_warmup_time_ (:883): all free. */
+DRRT_API int drrt_edgecheck_batch(drrt_store *h, int64_t n, const double *start,
+                         const double *end, int edge_kind, double robot_radius,
+                         double r_min, int in_warmup, uint8_t *verdict,
+                         double *length);
+/* same, endpoints named by node id in the store (8 B per edge on the wire) */
+DRRT_API int drrt_edgecheck_ids_batch(drrt_store *h, int64_t n, const int32_t *start_id,
+                             const int32_t *end_id, int edge_kind,
+                             double robot_radius, double r_min, int in_warmup,
+                             uint8_t *verdict, double *length);
+DRRT_API int drrt_edgecheck_batch_dev(drrt_store *h, int64_t n, const double *start_dev,
+                             const double *end_dev, const int32_t *start_id_dev,
+                             const int32_t *end_id_dev, int edge_kind,
+                             double robot_radius, double r_min,
+                             uint8_t *verdict_dev, double *length_dev,
+                             void *stream);
+
+/* DubinsEdge::CalculateTrajectory polyline (edge->trajectory_, read by
+ * src/moverobot.cpp:107,158): up to DRRT_TRAJ_MAX (x,y) points per edge.
+ * xy: n x DRRT_TRAJ_MAX x 2 f64; npts: n; type: n x 4 chars ("rsl\0"...) */
+#define DRRT_TRAJ_MAX 200
+DRRT_API int drrt_dubins_trajectory_batch(drrt_store *h, int64_t n, const double *start,
+                                 const double *end, double r_min, double *xy,
+                                 int32_t *npts, char *type, double *length);
+
+/* ExplicitNodeCheck -> ExplicitPointCheck src/obstacle.cpp:1062-1090
+ * (QuickCheck2D :925-965, ExplicitPointCheck2D :984-1060): 1 = in collision */
+DRRT_API int drrt_pointcheck_batch(drrt_store *h, int64_t n, const double *pts,
+                          double robot_radius, double collision_distance,
+                          uint8_t *verdict);
+DRRT_API int drrt_pointcheck_batch_dev(drrt_store *h, int64_t n, const double *pts_dev,
+                              double robot_radius, double collision_distance,
+                              uint8_t *verdict_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRRT_GPU_H */

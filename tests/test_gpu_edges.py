@@ -1,0 +1,142 @@
+"""Edge-check parity (drrt_edgecheck_batch through the C ABI) against the
+oracle's restatement of CalculateTrajectory + ExplicitEdgeCheck +
+ExplicitEdgeCheck2D.  Bar (north star): verdicts identical except edges within
+1e-6 of an obstacle boundary; lengths within 1e-9 relative (CUDA vs glibc
+atan2/acos differ by a few ulp)."""
+import numpy as np
+import pytest
+
+from drrt_b200 import synth
+
+pytestmark = pytest.mark.gpu
+BAND = 1e-6
+
+
+def _obs(drrt, po, o):
+    t = drrt.KDTree()
+    t.SetObstacles(**o)
+    ro = po.RefObstacles(**o)
+    return t, ro
+
+
+def _compare(t, ro, s, e, kind=0, radius=0.5, r_min=1.0):
+    v, ln = t.ExplicitEdgeCheck(s, e, robot_radius=radius, r_min=r_min, edge_kind=kind)
+    rv, rln, clr = ro.edge_check_batch(s, e, edge_kind=kind, robot_radius=radius, r_min=r_min,
+                                       want_clearance=True)
+    diff = np.nonzero(v != rv)[0]
+    assert (clr[diff] < BAND).all(), "verdicts differ outside the 1e-6 boundary band: %s" % diff[:10]
+    assert len(diff) <= max(2, len(v) // 100000)
+    ok = rln < 1e11
+    assert np.allclose(ln[ok], rln[ok], rtol=1e-9, atol=1e-9)
+    assert (ln[~ok] > 1e11).all()
+    return v, rv
+
+
+def test_dubins_edges_random(drrt, po):
+    o = synth.obstacles()
+    t, ro = _obs(drrt, po, o)
+    s, e = synth.random_edges(200_000, 81, max_len=0.66)
+    v, rv = _compare(t, ro, s, e)
+    assert 0.02 < v.mean() < 0.9
+    s, e = synth.random_edges(60_000, 82, max_len=5.0)
+    _compare(t, ro, s, e)
+
+
+def test_straight_edges_linecheck(drrt, po):
+    o = synth.obstacles()
+    t, ro = _obs(drrt, po, o)
+    s, e = synth.random_edges(100_000, 83, max_len=3.0)
+    _compare(t, ro, s, e, kind=1)
+
+
+def test_trajectories_match(drrt, po):
+    t = drrt.KDTree()
+    s, e = synth.random_edges(3000, 84, max_len=3.0)
+    xy, npts, names, length = t.CalculateTrajectory(s, e)
+    bad = 0
+    for i in range(len(s)):
+        ref = po.dubins_trajectory(s[i], e[i])
+        if names[i] != ref["type"] or npts[i] != len(ref["xy"]):
+            bad += 1          # an ulp in atan2 moved ceil(|dphi|/0.1) or a near-tie between words
+            continue
+        assert np.allclose(xy[i, :npts[i]], ref["xy"], rtol=0, atol=1e-9)
+        assert abs(length[i] - ref["dist"]) <= 1e-9 * max(1.0, ref["dist"])
+    assert bad <= 3
+
+
+def test_edge_known_answers(drrt, po):
+    # square obstacle [10,20]^2, kind 3
+    sq = dict(kind=[3], used=[1], life_span=[1e12], origin=[[15.0, 15.0]], radius=[7.0710678118654755],
+              vert_off=[0, 4], verts=[[10, 10], [20, 10], [20, 20], [10, 20]])
+    t, ro = _obs(drrt, po, sq)
+    th = 0.0
+    s = np.array([[14.0, 15.0, th], [5.0, 15.0, th], [0.0, 0.0, th], [9.4, 12.0, 1.5707963]])
+    e = np.array([[15.5, 15.0, th], [12.0, 15.0, th], [1.5, 0.0, th], [9.4, 13.5, 1.5707963]])
+    # (4) a short straight ("0s0") edge strictly inside the polygon is free (no containment test)
+    # crossing the boundary collides; far away is free; passing 0.6 from the wall is free
+    v = t.ExplicitEdgeCheck(s, e, want_length=False)
+    rv, _ = ro.edge_check_batch(s, e)
+    assert list(v) == list(rv)
+    assert v[0] == 0 and v[2] == 0
+    # (6) unused obstacle / expired obstacle never collide
+    for used, life in ((0, 1e12), (1, 0.0)):
+        sq2 = dict(sq, used=[used], life_span=[life])
+        t.SetObstacles(**sq2)
+        assert not t.ExplicitEdgeCheck(s, e, want_length=False).any()
+    # (7) kind 1 ball inside the bounding reach collides, kind 2 never
+    t.SetObstacles(**dict(sq, kind=[1]))
+    v1 = t.ExplicitEdgeCheck(s, e, want_length=False)
+    r1, _ = po.RefObstacles(**dict(sq, kind=[1])).edge_check_batch(s, e)
+    assert list(v1) == list(r1) and v1[0] == 1
+    t.SetObstacles(**dict(sq, kind=[2]))
+    assert not t.ExplicitEdgeCheck(s, e, want_length=False).any()
+    # (8) in_warmup_time_: every edge is free
+    t.SetObstacles(**sq)
+    assert not t.ExplicitEdgeCheck(s, e, in_warmup=True, want_length=False).any()
+    # kinds 6/7 are refused loudly
+    with pytest.raises(drrt.DrrtError):
+        t.SetObstacles(**dict(sq, kind=[6]))
+
+
+def test_edge_ids_variant_matches_pose_variant(drrt, po):
+    o = synth.obstacles()
+    t, ro = _obs(drrt, po, o)
+    pos = synth.box_points(50_000, 85)
+    t.KDInsert(pos)
+    rng = np.random.default_rng(86)
+    a = rng.integers(0, len(pos), 30_000).astype(np.int32)
+    off, ids, _ = t.KDFindWithinRange(1.0, pos[a[:2000]])
+    b = np.repeat(a[:2000], np.diff(off)).astype(np.int32)
+    v1, l1 = t.ExplicitEdgeCheckIds(b, ids)
+    v2, l2 = t.ExplicitEdgeCheck(pos[b], pos[ids])
+    assert np.array_equal(v1, v2) and np.array_equal(l1, l2)
+
+
+def test_node_check(drrt, po):
+    o = synth.obstacles()
+    o["kind"][:20] = 1
+    o["kind"][20:30] = 2
+    o["kind"][30:40] = 5
+    t, ro = _obs(drrt, po, o)
+    pts = synth.box_points(200_000, 87)
+    v = t.ExplicitNodeCheck(pts, robot_radius=0.5, collision_distance=0.1)
+    rv = ro.point_check_batch(pts, robot_radius=0.5, collision_distance=0.1)
+    assert np.array_equal(v, rv)
+    assert 0.05 < v.mean() < 0.95
+
+
+def test_edge_round_trip_properties_full_size(drrt, po):
+    # size-independent properties on a large batch: no obstacles -> all free;
+    # verdicts are independent of batch order; lengths >= straight-line distance
+    o = synth.obstacles()
+    t, ro = _obs(drrt, po, o)
+    s, e = synth.random_edges(2_000_000, 88, max_len=0.66)
+    v, ln = t.ExplicitEdgeCheck(s, e)
+    perm = np.random.default_rng(89).permutation(len(s))
+    v2, ln2 = t.ExplicitEdgeCheck(s[perm], e[perm])
+    assert np.array_equal(v[perm], v2) and np.array_equal(ln[perm], ln2)
+    d = np.hypot(e[:, 0] - s[:, 0], e[:, 1] - s[:, 1])
+    assert (ln >= d * (1 - 1e-12)).all()
+    t.SetObstacles(kind=[], used=[], life_span=[], origin=np.zeros((0, 2)), radius=[],
+                   vert_off=[0], verts=np.zeros((0, 2)))
+    assert not t.ExplicitEdgeCheck(s[:100000], e[:100000], want_length=False).any()

@@ -1,0 +1,155 @@
+"""Parity of the CUDA range-ball path (drrt_range_batch, through the C ABI)
+against the CPU oracle's restatement of KDTree::KDFindWithinRange
+(src/kdtree.cpp:794-820).  Bar: neighbour id sets bit-exact (rows sorted by
+id); distances within 1e-5 relative (north star) -- in fact compared exactly.
+"""
+import numpy as np
+import pytest
+
+from drrt_b200 import synth
+
+pytestmark = pytest.mark.gpu
+W = synth.TWO_PI
+
+
+def _check(tree, ref, q, r, exact_dist=True):
+    off, ids, dist = tree.KDFindWithinRange(r, q)
+    roff, rids, rdist = ref.range_batch(q, r)
+    assert np.array_equal(off, roff), "hit counts differ"
+    assert np.array_equal(ids, rids), "neighbour ids differ"
+    if exact_dist:
+        assert np.array_equal(dist, rdist)
+    else:
+        assert np.allclose(dist, rdist, rtol=1e-5, atol=0)
+    return off
+
+
+def _pair(drrt, po, pos, metric=0, wraps=(2,), wrap_points=(W,)):
+    t = drrt.KDTree(wraps=wraps, wrap_points=wrap_points, metric=metric)
+    t.KDInsert(pos)
+    r = po.RefTree(wraps=wraps, wrap_points=wrap_points, metric=metric)
+    r.insert(pos)
+    return t, r
+
+
+def test_range_small_tree_no_index(drrt, po):
+    pos = synth.box_points(500, 11)
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(300, 12)
+    _check(t, r, q, 6.0)
+    _check(t, r, q, 0.5)
+
+
+def test_range_indexed_sparse_and_dense(drrt, po):
+    pos = synth.box_points(200_000, 21)
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(2000, 22)
+    off = _check(t, r, q, 1.1)          # warp-per-query mode
+    assert off[-1] > 0
+    _check(t, r, q[:300], 4.0)          # CTA-per-query mode (~2000 hits each)
+    _check(t, r, q[:40], 9.0)           # staging overflow path
+
+
+def test_range_per_query_radius(drrt, po):
+    pos = synth.box_points(100_000, 31)
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(1500, 32)
+    rad = np.random.default_rng(33).uniform(0.0, 2.5, len(q))
+    rad[:5] = 0.0
+    _check(t, r, q, rad)
+
+
+def test_range_ghost_wraparound(drrt, po):
+    # queries hugging theta = 0 and theta = 2*pi' must see neighbours across the seam
+    pos = synth.box_points(150_000, 41)
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(3000, 42)
+    q[:1000, 2] = np.random.default_rng(43).uniform(0.0, 0.3, 1000)
+    q[1000:2000, 2] = W - np.random.default_rng(44).uniform(0.0, 0.3, 1000)
+    off = _check(t, r, q, 1.3)
+    # the seam matters: dropping the wrap changes the answer
+    t2 = drrt.KDTree(wraps=(), wrap_points=())
+    t2.KDInsert(pos)
+    off2, _, _ = t2.KDFindWithinRange(1.3, q)
+    assert off2[-1] <= off[-1]
+
+
+def test_range_known_answers(drrt, po):
+    # SURVEY 8c hand-derived cases
+    t = drrt.KDTree()
+    t.KDInsert(np.array([[10.0, 10.0, 1.0]]))
+    # (1) root at distance exactly r is admitted (kdtree.cpp:802 `<=`)
+    off, ids, dist = t.KDFindWithinRange(2.0, np.array([[12.0, 10.0, 1.0]]))
+    assert list(ids) == [0] and dist[0] == 2.0
+    # the same geometry for a non-root node is a miss (:733 `<`)
+    t.KDInsert(np.array([[20.0, 10.0, 1.0]]))
+    off, ids, _ = t.KDFindWithinRange(2.0, np.array([[22.0, 10.0, 1.0]]))
+    assert len(ids) == 0
+    # (2) q theta 0.05 vs node theta 2*pi'-0.05: d = 0.1 through the wrap
+    t.KDInsert(np.array([[30.0, 30.0, W - 0.05]]))
+    off, ids, dist = t.KDFindWithinRange(0.2, np.array([[30.0, 30.0, 0.05]]))
+    assert list(ids) == [2] and abs(dist[0] - 0.1) < 1e-12
+
+
+def test_range_negative_theta_and_out_of_box(drrt, po):
+    # start/goal poses of smalltest.cpp have theta = -3*pi/4 (smalltest.cpp:190-196)
+    rng = np.random.default_rng(51)
+    pos = synth.box_points(60_000, 52)
+    pos[0] = [0.0, 0.0, -3 * synth.PI / 4]
+    pos[1] = [49.0, 49.0, -3 * synth.PI / 4]
+    pos[100:200, 2] -= W          # negative headings
+    pos[200:300, 2] += W          # headings above the wrap point
+    pos[300:320, 0] += 80.0       # far outside the bulk
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(1500, 53)
+    q[:50] = pos[:50]
+    q[50:100, 2] = -rng.uniform(0, 3, 50)
+    q[100:150, 2] = W + rng.uniform(0, 3, 50)
+    q[150:160, 0] = 120.0
+    _check(t, r, q, 1.5)
+    _check(t, r, q[:200], 5.0)
+
+
+def test_range_euclid_metric_thetastar_grid(drrt, po):
+    # Theta*'s private tree: 50x50 unit grid, Euclidean metric, theta wraps,
+    # range 2 (thetastar.cpp:50-52, 80-110, 152): distances land exactly on r
+    xs, ys = np.meshgrid(np.arange(50.0), np.arange(50.0), indexing="ij")
+    pos = np.stack([xs.ravel(), ys.ravel(), np.zeros(2500)], 1)
+    t, r = _pair(drrt, po, pos, metric=1)
+    _check(t, r, pos[::7], 2.0)
+    _check(t, r, pos[::7] + [0.25, 0.5, 0.0], 2.0)
+
+
+def test_range_after_incremental_inserts(drrt, po):
+    # the index is rebuilt lazily; nodes in the unsorted tail must still be found
+    pos = synth.box_points(30_000, 61)
+    t = drrt.KDTree()
+    r = po.RefTree()
+    q = synth.box_points(64, 62)
+    done = 0
+    for chunk in (1, 1, 2, 5, 100, 3000, 1, 1, 7, 20_000, 1, 3, 2000, 4890):
+        t.KDInsert(pos[done:done + chunk])
+        r.insert(pos[done:done + chunk])
+        done += chunk
+        _check(t, r, q[:8], 3.0)
+    assert done == 30_000
+    _check(t, r, q, 2.0)
+
+
+def test_range_empty_inputs(drrt, po):
+    t = drrt.KDTree()
+    off, ids, dist = t.KDFindWithinRange(1.0, np.zeros((3, 3)))
+    assert list(off) == [0, 0, 0, 0] and len(ids) == 0
+    t.KDInsert(synth.box_points(10, 1))
+    off, ids, dist = t.KDFindWithinRange(1.0, np.zeros((0, 3)))
+    assert list(off) == [0]
+
+
+def test_range_config2_sample(drrt, po):
+    # BASELINE config 2 at full node count, on a query sample the oracle finishes in seconds
+    pos = synth.nodes()
+    t, r = _pair(drrt, po, pos)
+    q = synth.queries()[:512]
+    for gamma in (synth.GAMMA_SPARSE, synth.GAMMA_REF):
+        rad = synth.shrinking_radius(len(pos), gamma)
+        _check(t, r, q if gamma == synth.GAMMA_SPARSE else q[:96], rad)
