@@ -127,7 +127,7 @@ def test_range_after_incremental_inserts(drrt, po):
     r = po.RefTree()
     q = synth.box_points(64, 62)
     done = 0
-    for chunk in (1, 1, 2, 5, 100, 3000, 1, 1, 7, 20_000, 1, 3, 2000, 4890):
+    for chunk in (1, 1, 2, 5, 100, 3000, 1, 1, 7, 20_000, 1, 3, 2000, 4878):
         t.KDInsert(pos[done:done + chunk])
         r.insert(pos[done:done + chunk])
         done += chunk
