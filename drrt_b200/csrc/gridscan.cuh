@@ -111,6 +111,33 @@ __device__ __forceinline__ bool covers_all(const GridView &A, const Query &Q) {
          Q.ta1 == g.nt - 1;
 }
 
+// the one or two contiguous record runs of candidate column `col` (empty when
+// the column's footprint cannot come within the query radius)
+__device__ __forceinline__ void column_runs(const GridView &A, const Query &Q, int col, int ncol,
+                                            int ncy, double cull, int &s0, int &l0, int &s1,
+                                            int &l1) {
+  const GridParams &g = A.gp;
+  s0 = l0 = s1 = l1 = 0;
+  if (col >= ncol) return;
+  int ix = Q.ix0 + col / ncy, iy = Q.iy0 + col % ncy;
+  // closest approach of the column's footprint (edge columns are open-ended)
+  double xlo = g.x0 + ((double)ix - 1e-6) / g.inv_hx, xhi = g.x0 + ((double)ix + 1.000001) / g.inv_hx;
+  double ylo = g.y0 + ((double)iy - 1e-6) / g.inv_hy, yhi = g.y0 + ((double)iy + 1.000001) / g.inv_hy;
+  double dx = 0.0, dy = 0.0;
+  if (ix > 0 && Q.x < xlo) dx = xlo - Q.x;
+  if (ix < g.nx - 1 && Q.x > xhi) dx = Q.x - xhi;
+  if (iy > 0 && Q.y < ylo) dy = ylo - Q.y;
+  if (iy < g.ny - 1 && Q.y > yhi) dy = Q.y - yhi;
+  if (dx * dx + dy * dy > cull) return;
+  int cbase = (ix * g.ny + iy) * g.nt;
+  s0 = A.cell_start[cbase + Q.ta0];
+  l0 = A.cell_start[cbase + Q.ta1 + 1] - s0;
+  if (Q.tb0 <= Q.tb1) {
+    s1 = A.cell_start[cbase + Q.tb0];
+    l1 = A.cell_start[cbase + Q.tb1 + 1] - s1;
+  }
+}
+
 // One warp visits column batches first, first+stride, ... of query Q and calls
 // f(valid, x, y, theta, id) once per candidate slot with all 32 lanes converged
 // (valid == false on padding lanes).
@@ -118,33 +145,12 @@ template <class F>
 __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, int first,
                                              int stride, int *run_start, int *run_pref,
                                              int lane, F f) {
-  const GridParams &g = A.gp;
   const int ncy = Q.iy1 - Q.iy0 + 1;
   const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
   const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
   for (int cb = first * 32; cb < ncol; cb += stride * 32) {
-    int col = cb + lane;
-    int s0 = 0, l0 = 0, s1 = 0, l1 = 0;
-    if (col < ncol) {
-      int ix = Q.ix0 + col / ncy, iy = Q.iy0 + col % ncy;
-      // closest approach of the column's footprint (edge columns are open-ended)
-      double xlo = g.x0 + ((double)ix - 1e-6) / g.inv_hx, xhi = g.x0 + ((double)ix + 1.000001) / g.inv_hx;
-      double ylo = g.y0 + ((double)iy - 1e-6) / g.inv_hy, yhi = g.y0 + ((double)iy + 1.000001) / g.inv_hy;
-      double dx = 0.0, dy = 0.0;
-      if (ix > 0 && Q.x < xlo) dx = xlo - Q.x;
-      if (ix < g.nx - 1 && Q.x > xhi) dx = Q.x - xhi;
-      if (iy > 0 && Q.y < ylo) dy = ylo - Q.y;
-      if (iy < g.ny - 1 && Q.y > yhi) dy = Q.y - yhi;
-      if (!(dx * dx + dy * dy > cull)) {
-        int cbase = (ix * g.ny + iy) * g.nt;
-        s0 = A.cell_start[cbase + Q.ta0];
-        l0 = A.cell_start[cbase + Q.ta1 + 1] - s0;
-        if (Q.tb0 <= Q.tb1) {
-          s1 = A.cell_start[cbase + Q.tb0];
-          l1 = A.cell_start[cbase + Q.tb1 + 1] - s1;
-        }
-      }
-    }
+    int s0, l0, s1, l1;
+    column_runs(A, Q, cb + lane, ncol, ncy, cull, s0, l0, s1, l1);
     // exclusive scan of run lengths, two runs per lane
     int tot = l0 + l1, inc = tot;
 #pragma unroll
@@ -181,6 +187,75 @@ __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, 
       }
       f(valid, nx, ny, nt, id);
     }
+  }
+}
+
+// A whole CTA of NWARPS warps visits ALL candidate columns of query Q: every
+// thread resolves one column's runs, a CTA-wide prefix sum flattens them, and
+// each warp takes an equal, contiguous slice of the candidates (consecutive
+// lanes read consecutive 32-byte records).  run_start/run_pref hold 2*T and
+// 2*T+1 ints, tmp holds NWARPS ints.  f as in scan_columns.
+template <int NWARPS, class F>
+__device__ __forceinline__ void scan_columns_block(const GridView &A, const Query &Q,
+                                                   int *run_start, int *run_pref, int *tmp, F f) {
+  constexpr int T = NWARPS * 32;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int ncy = Q.iy1 - Q.iy0 + 1;
+  const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
+  const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
+  for (int cb = 0; cb < ncol; cb += T) {
+    int s0, l0, s1, l1;
+    column_runs(A, Q, cb + tid, ncol, ncy, cull, s0, l0, s1, l1);
+    int tot = l0 + l1, inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) tmp[w] = inc;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int ww = 0; ww < NWARPS; ww++) {
+      int v = tmp[ww];
+      if (ww < w) wbase += v;
+      total += v;
+    }
+    int excl = wbase + inc - tot;
+    run_start[2 * tid] = s0;
+    run_start[2 * tid + 1] = s1;
+    run_pref[2 * tid] = excl;
+    run_pref[2 * tid + 1] = excl + l0;
+    if (tid == T - 1) run_pref[2 * T] = total;
+    __syncthreads();
+    int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;
+    int c0 = w * per, c1 = min(total, c0 + per);
+    if (c0 < c1) {
+      int lo = 0, hi = 2 * T;  // largest j with run_pref[j] <= c0
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (run_pref[mid] <= c0) lo = mid; else hi = mid;
+      }
+      int j = lo;
+      for (int base = c0; base < c1; base += 32) {
+        while (run_pref[j + 1] <= base) j++;
+        int i = base + lane;
+        bool valid = i < c1;
+        double nx = 0.0, ny = 0.0, nt = 0.0;
+        int32_t id = 0;
+        if (valid) {
+          int jl = j;
+          while (run_pref[jl + 1] <= i) jl++;
+          const NodeRec *r = A.rec + (run_start[jl] + (i - run_pref[jl]));
+          double2 xy = *reinterpret_cast<const double2 *>(&r->x);
+          double2 ti = *reinterpret_cast<const double2 *>(&r->th);
+          nx = xy.x; ny = xy.y; nt = ti.x;
+          id = (int32_t)(__double_as_longlong(ti.y) & 0xffffffffll);
+        }
+        f(valid, nx, ny, nt, id);
+      }
+    }
+    __syncthreads();
   }
 }
 

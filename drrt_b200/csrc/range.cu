@@ -15,13 +15,15 @@
 // hyperplane that hides n.  The recorded key is the distance to the first
 // probe that admits n, as the reference's JList key (AddToRangeList).
 //
-// Execution: one single pass.  A warp (small neighbourhoods) or a whole CTA
-// (large ones) scans the candidate columns of its query in the cell-sorted
-// 32-byte NodeRec array -- all columns of a batch flattened so every lane has
-// a candidate -- evaluates the f64 metric in the reference's operation order,
-// compacts hits with ballots into shared memory, sorts them by node id there,
-// and writes them to their final CSR position, which it gets from an
-// in-kernel ordered allocation (decoupled look-back over per-CTA hit totals).
+// Execution: one pass, one kernel.  A warp (small neighbourhoods) or a whole
+// CTA (large ones) scans the candidate columns of its query in the cell-sorted
+// 32-byte NodeRec array -- runs flattened so every lane holds a candidate --
+// evaluates the f64 metric in the reference's operation order and compacts the
+// hits with ballots into shared memory.  The CTA publishes its hit total, and
+// while the in-kernel ordered allocation (decoupled look-back over CTA totals)
+// resolves, orders the staged hits by node id with a counting sort on id
+// buckets in shared memory.  The rows then go to their final CSR position
+// with coalesced stores.
 #include <math.h>
 
 #include <algorithm>
@@ -30,10 +32,10 @@
 
 namespace drrt {
 
-static constexpr int RANGE_WARPS = 8;
-static constexpr int RANGE_T = RANGE_WARPS * 32;
-static constexpr int WARP_STAGE = 256;    // hits staged per warp-mode query
-static constexpr int BLOCK_STAGE = 5120;  // hits staged per CTA-mode query
+static constexpr int WARP_MODE_WARPS = 8;    // one query per warp
+static constexpr int BLOCK_MODE_WARPS = 16;  // one query per CTA
+static constexpr int WARP_STAGE = 256;       // hits staged per warp-mode query
+static constexpr int BLOCK_STAGE = 4608;     // hits staged per CTA-mode query
 
 struct RangeArgs {
   GridView V;
@@ -113,20 +115,21 @@ __device__ __forceinline__ void emit(const Sink &K, bool hit, int32_t id, double
   }
 }
 
-// all-ascending bitonic network over n (any n) keys; `nthreads` threads, rank `tid`
 template <bool BLOCK>
 __device__ __forceinline__ void group_sync() {
   if (BLOCK) __syncthreads(); else __syncwarp();
 }
 
+// all-ascending bitonic network over n (any n) keys; `nthreads` threads, rank `tid`
 template <bool BLOCK>
 __device__ void sort_keys_shared(unsigned long long *keys, int n, int tid, int nthreads) {
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
-  for (int k = 2; k <= np2; k <<= 1) {
+  int lk = 1;
+  for (int k = 2; k <= np2; k <<= 1, lk++) {
     const int half = k >> 1;
     for (int p = tid; p < (np2 >> 1); p += nthreads) {
-      int blk = p / half, o = p - blk * half;
+      int blk = p >> (lk - 1), o = p & (half - 1);
       int i = blk * k + o, j = blk * k + k - 1 - o;
       if (j < n) {
         unsigned long long a = keys[i], b = keys[j];
@@ -136,7 +139,7 @@ __device__ void sort_keys_shared(unsigned long long *keys, int n, int tid, int n
     group_sync<BLOCK>();
     for (int jj = half >> 1; jj > 0; jj >>= 1) {
       for (int p = tid; p < (np2 >> 1); p += nthreads) {
-        int i = 2 * jj * (p / jj) + (p % jj), j = i + jj;
+        int i = ((p & ~(jj - 1)) << 1) | (p & (jj - 1)), j = i + jj;
         if (j < n) {
           unsigned long long a = keys[i], b = keys[j];
           if (a > b) { keys[i] = b; keys[j] = a; }
@@ -165,7 +168,7 @@ __device__ void sort_pairs_global(int32_t *ids, double *dist, int64_t n, int tid
     group_sync<BLOCK>();
     for (int64_t jj = half >> 1; jj > 0; jj >>= 1) {
       for (int64_t p = tid; p < (np2 >> 1); p += nthreads) {
-        int64_t i = 2 * jj * (p / jj) + (p % jj), j = i + jj;
+        int64_t i = ((p & ~(jj - 1)) << 1) | (p & (jj - 1)), j = i + jj;
         if (j < n && ids[i] > ids[j]) {
           int32_t a = ids[i]; ids[i] = ids[j]; ids[j] = a;
           double b = dist[i]; dist[i] = dist[j]; dist[j] = b;
@@ -176,19 +179,126 @@ __device__ void sort_pairs_global(int32_t *ids, double *dist, int64_t n, int tid
   }
 }
 
-// Ordered allocation: CTA `vb` publishes its hit total and receives the sum of
-// all earlier CTAs' totals (decoupled look-back; vb comes from a ticket so
+// Orders the n staged hits by node id: order[pos] = staging slot of the hit
+// that belongs at output position pos.  Counting sort on id buckets -- node ids
+// of a neighbourhood are spread over the id range, so a bucket holds about one
+// hit and (bucket start + arrival rank) is final for most; the thread owning a
+// bucket with several hits puts those few slots in id order.  When ids cluster
+// (some bucket crowded) the bitonic network sorts the keys instead.
+template <bool BLOCK, int NB, int T>
+__device__ void order_by_id(unsigned long long *keys, int n, int *hist, int *s_misc,
+                            uint16_t *order, int tid) {
+  constexpr int CROWDED = 24;
+  int mn = 0x7fffffff, mx = -1;
+  for (int i = tid; i < n; i += T) {
+    int id = (int)(keys[i] >> 32);
+    mn = min(mn, id);
+    mx = max(mx, id);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (BLOCK) {
+    if (tid == 0) { s_misc[0] = 0x7fffffff; s_misc[1] = -1; }
+    __syncthreads();
+    if ((tid & 31) == 0) { atomicMin(&s_misc[0], mn); atomicMax(&s_misc[1], mx); }
+  }
+  for (int b = tid; b <= NB; b += T) hist[b] = 0;
+  if (tid == 0) s_misc[2] = 0;
+  group_sync<BLOCK>();
+  if (BLOCK) { mn = s_misc[0]; mx = s_misc[1]; }
+  int shift = 0;
+  while (((mx - mn) >> shift) >= NB) shift++;
+  // arrival rank inside the bucket
+  bool crowded = false;
+  for (int i = tid; i < n; i += T) {
+    unsigned long long k = keys[i];
+    int b = ((int)(k >> 32) - mn) >> shift;
+    int rank = atomicAdd(&hist[b], 1);
+    keys[i] = (k & 0xffffffff00000000ull) | (unsigned)rank;
+    crowded |= rank >= CROWDED;
+  }
+  if (__any_sync(0xffffffffu, crowded) && (tid & 31) == 0) s_misc[2] = 1;
+  group_sync<BLOCK>();
+  if (s_misc[2]) {
+    for (int i = tid; i < n; i += T) keys[i] = (keys[i] & 0xffffffff00000000ull) | (unsigned)i;
+    group_sync<BLOCK>();
+    sort_keys_shared<BLOCK>(keys, n, tid, T);
+    // the network permuted the keys; their dist stays at the slot in the low half
+    for (int i = tid; i < n; i += T) order[i] = (uint16_t)(keys[i] & 0xffffu);
+    group_sync<BLOCK>();
+    // un-permute: slot s must again hold the key that owns sdist[s]
+    unsigned long long mine[(BLOCK ? BLOCK_STAGE : WARP_STAGE) / T + 1];
+    int c = 0;
+    for (int i = tid; i < n; i += T) mine[c++] = keys[i];
+    group_sync<BLOCK>();
+    c = 0;
+    for (int i = tid; i < n; i += T) { unsigned long long k = mine[c++]; keys[(unsigned)(k & 0xffffu)] = k; }
+    group_sync<BLOCK>();
+    return;
+  }
+  // exclusive scan of the bucket counts (NB / T consecutive buckets per thread)
+  constexpr int PER = NB / T;
+  int local[PER];
+  int sum = 0;
+#pragma unroll
+  for (int e = 0; e < PER; e++) { local[e] = hist[tid * PER + e]; sum += local[e]; }
+  int inc = sum;
+  const int lane = tid & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  int excl = inc - sum;
+  if (BLOCK) {
+    if (lane == 31) s_misc[4 + (tid >> 5)] = inc;
+    __syncthreads();
+    for (int ww = 0; ww < (tid >> 5); ww++) excl += s_misc[4 + ww];
+  }
+#pragma unroll
+  for (int e = 0; e < PER; e++) { hist[tid * PER + e] = excl; excl += local[e]; }
+  if (tid == T - 1) hist[NB] = excl;
+  group_sync<BLOCK>();
+  for (int i = tid; i < n; i += T) {
+    unsigned long long k = keys[i];
+    int pos = hist[((int)(k >> 32) - mn) >> shift] + (int)(unsigned)(k & 0xffffffffu);
+    order[pos] = (uint16_t)i;
+  }
+  group_sync<BLOCK>();
+  // buckets with more than one hit: insertion sort of their slots by id
+  for (int b = tid; b < NB; b += T) {
+    int s0 = hist[b], c = hist[b + 1] - s0;
+    for (int a = 1; a < c; a++) {
+      uint16_t v = order[s0 + a];
+      unsigned vid = (unsigned)(keys[v] >> 32);
+      int j = a - 1;
+      while (j >= 0 && (unsigned)(keys[order[s0 + j]] >> 32) > vid) {
+        order[s0 + j + 1] = order[s0 + j];
+        j--;
+      }
+      order[s0 + j + 1] = v;
+    }
+  }
+  group_sync<BLOCK>();
+}
+
+// Ordered allocation: CTA `vb` publishes its hit total, later receives the sum
+// of all earlier CTAs' totals (decoupled look-back; vb comes from a ticket so
 // every predecessor is already running).
 static constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_PREFIX = 2ull << 62;
 static constexpr unsigned long long VAL_MASK = (1ull << 62) - 1;
 
-__device__ long long lookback_exclusive(unsigned long long *desc, int vb, long long agg, int lane) {
+__device__ __forceinline__ void lookback_publish(unsigned long long *desc, int vb, long long agg) {
   volatile unsigned long long *vd = desc;
-  if (vb == 0) {
-    if (lane == 0) { __threadfence(); vd[0] = FLAG_PREFIX | (unsigned long long)agg; }
-    return 0;
-  }
-  if (lane == 0) { vd[vb] = FLAG_AGG | (unsigned long long)agg; }
+  vd[vb] = (vb == 0 ? FLAG_PREFIX : FLAG_AGG) | (unsigned long long)agg;
+}
+
+__device__ long long lookback_resolve(unsigned long long *desc, int vb, long long agg, int lane) {
+  volatile unsigned long long *vd = desc;
+  if (vb == 0) return 0;
   long long excl = 0;
   int pos = vb - 1;
   for (;;) {
@@ -207,91 +317,111 @@ __device__ long long lookback_exclusive(unsigned long long *desc, int vb, long l
     if (has_prefix || pos - 32 < 0) break;
     pos -= 32;
   }
-  if (lane == 0) { __threadfence(); vd[vb] = FLAG_PREFIX | (unsigned long long)(excl + agg); }
+  if (lane == 0) vd[vb] = FLAG_PREFIX | (unsigned long long)(excl + agg);
   return excl;
 }
 
 template <int METRIC, bool BLOCK>
-__global__ void __launch_bounds__(RANGE_T)
+__global__ void __launch_bounds__(BLOCK ? BLOCK_MODE_WARPS * 32 : WARP_MODE_WARPS * 32, BLOCK ? 2 : 4)
 range_kernel(RangeArgs A) {
+  constexpr int WARPS = BLOCK ? BLOCK_MODE_WARPS : WARP_MODE_WARPS;
+  constexpr int T = WARPS * 32;
+  constexpr int STAGE = BLOCK ? BLOCK_STAGE : WARP_STAGE;
+  constexpr int NSTAGE = BLOCK ? 1 : WARPS;
+  constexpr int NB = BLOCK ? 4096 : 128;  // id buckets of the output sort
+  constexpr int RUN_SLOTS = BLOCK ? 2 * T : WARPS * RUNS_PER_BATCH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_vb;
-  __shared__ int s_count[RANGE_WARPS];
+  __shared__ int s_count[WARPS];
   __shared__ long long s_base;
-  __shared__ int s_runs[RANGE_WARPS][RUNS_PER_BATCH];
-  __shared__ int s_pref[RANGE_WARPS][RUNS_PER_BATCH + 1];
+  __shared__ int s_runs[RUN_SLOTS];
+  __shared__ int s_pref[RUN_SLOTS + WARPS];
+  __shared__ int s_tmp[WARPS];
+  __shared__ int s_hist[NSTAGE][NB + 1];
+  __shared__ int s_misc[NSTAGE][4 + WARPS];
 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_vb = atomicAdd(A.ticket, 1);
-  if (threadIdx.x < RANGE_WARPS) s_count[threadIdx.x] = 0;
+  if (threadIdx.x < WARPS) s_count[threadIdx.x] = 0;
   __syncthreads();
   const int vb = s_vb;
 
-  constexpr int STAGE = BLOCK ? BLOCK_STAGE : WARP_STAGE;
-  constexpr int NSTAGE = BLOCK ? 1 : RANGE_WARPS;
   unsigned long long *all_keys = reinterpret_cast<unsigned long long *>(smem_raw);
-  double *all_dist = reinterpret_cast<double *>(smem_raw + sizeof(unsigned long long) * STAGE * NSTAGE);
+  double *all_dist = reinterpret_cast<double *>(all_keys + STAGE * NSTAGE);
+  uint16_t *all_order = reinterpret_cast<uint16_t *>(all_dist + STAGE * NSTAGE);
 
-  const int64_t qi = BLOCK ? (int64_t)vb : (int64_t)vb * RANGE_WARPS + w;
+  const int64_t qi = BLOCK ? (int64_t)vb : (int64_t)vb * WARPS + w;
   const bool active = qi < A.nq;
+  const int g = BLOCK ? 0 : w;  // staging group of this thread
   Query Q;
   Sink K;
-  K.keys = all_keys + (BLOCK ? 0 : w * STAGE);
-  K.sdist = all_dist + (BLOCK ? 0 : w * STAGE);
-  K.counter = &s_count[BLOCK ? 0 : w];
+  K.keys = all_keys + g * STAGE;
+  K.sdist = all_dist + g * STAGE;
+  K.counter = &s_count[g];
   K.capacity = STAGE;
   K.gids = nullptr;
   K.gdist = nullptr;
+  uint16_t *order = all_order + g * STAGE;
   const GridView &V = A.V;
   auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
     double d = 0.0;
     bool hit = valid && eval_candidate<METRIC>(Q, nx, ny, nt, id, V.gate, &d);
     emit(K, hit, id, d, lane);
   };
-  const int first = BLOCK ? w : 0, stride = BLOCK ? RANGE_WARPS : 1;
-  if (active) {
+  auto scan_all = [&]() {
+    if (BLOCK) {
+      if (V.n_indexed > 0) scan_columns_block<WARPS>(V, Q, s_runs, s_pref, s_tmp, visit);
+      scan_tail(V, w, WARPS, lane, visit);
+    } else {
+      if (V.n_indexed > 0)
+        scan_columns(V, Q, 0, 1, s_runs + w * RUNS_PER_BATCH, s_pref + w * (RUNS_PER_BATCH + 1),
+                     lane, visit);
+      scan_tail(V, 0, 1, lane, visit);
+    }
+  };
+  if (active) {  // uniform per CTA in CTA mode, per warp in warp mode
     setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
                         A.radius ? A.radius[qi] : A.radius_all, Q);
-    if (V.n_indexed > 0) scan_columns(V, Q, first, stride, s_runs[w], s_pref[w], lane, visit);
-    scan_tail(V, first, stride, lane, visit);
+    scan_all();
   }
   __syncthreads();
 
-  // ---- ordered allocation of the CTA's output range
+  // ---- publish the CTA's hit total, then sort while predecessors finish
+  long long agg = 0;
   if (w == 0) {
-    long long agg = 0;
-    if (BLOCK) agg = s_count[0];
-    else {
-      int c = (lane < RANGE_WARPS) ? s_count[lane] : 0;
+    int c = (lane < (BLOCK ? 1 : WARPS)) ? s_count[lane] : 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      agg = c;
-    }
-    long long excl = lookback_exclusive(A.desc, vb, agg, lane);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    agg = c;
+    if (lane == 0) lookback_publish(A.desc, vb, agg);
+  }
+  const int my_cnt = s_count[g];
+  const int tid = BLOCK ? (int)threadIdx.x : lane;
+  constexpr int GT = BLOCK ? T : 32;
+  const bool staged = active && my_cnt > 0 && my_cnt <= STAGE;  // uniform per group
+  if (staged) order_by_id<BLOCK, NB, GT>(K.keys, my_cnt, s_hist[g], s_misc[g], order, tid);
+  if (w == 0) {
+    long long excl = lookback_resolve(A.desc, vb, agg, lane);
     if (lane == 0) s_base = excl;
   }
   __syncthreads();
   long long my_off = s_base;
   if (!BLOCK)
     for (int i = 0; i < w; i++) my_off += s_count[i];
-  const int my_cnt = s_count[BLOCK ? 0 : w];
-  if (active && (BLOCK ? threadIdx.x == 0 : lane == 0)) {
+  if (active && tid == 0) {
     A.offsets[qi] = my_off;
     if (qi == A.nq - 1) A.offsets[A.nq] = my_off + my_cnt;
   }
-  if (!active || my_cnt == 0) return;       // uniform per group
-  if (my_off + my_cnt > A.cap) return;      // arena too small: host grows it and reruns
+  if (!active || my_cnt == 0) return;   // uniform per group
+  if (my_off + my_cnt > A.cap) return;  // arena too small: the host grows it and reruns
 
-  const int tid = BLOCK ? (int)threadIdx.x : lane;
-  const int nthr = BLOCK ? RANGE_T : 32;
   int32_t *oid = A.ids + my_off;
   double *od = A.dist + my_off;
-  if (my_cnt <= STAGE) {
-    sort_keys_shared<BLOCK>(K.keys, my_cnt, tid, nthr);
-    for (int i = tid; i < my_cnt; i += nthr) {
-      unsigned long long k = K.keys[i];
-      oid[i] = (int32_t)(k >> 32);
-      od[i] = K.sdist[(unsigned)(k & 0xffffffffu)];
+  if (staged) {
+    for (int i = tid; i < my_cnt; i += GT) {
+      int slot = order[i];
+      oid[i] = (int32_t)(K.keys[slot] >> 32);
+      od[i] = K.sdist[slot];
     }
   } else {
     // more hits than the staging area: second pass straight into the arena
@@ -300,29 +430,27 @@ range_kernel(RangeArgs A) {
     group_sync<BLOCK>();
     K.gids = oid;
     K.gdist = od;
-    if (V.n_indexed > 0) scan_columns(V, Q, first, stride, s_runs[w], s_pref[w], lane, visit);
-    scan_tail(V, first, stride, lane, visit);
+    scan_all();
     group_sync<BLOCK>();
-    __threadfence_block();
-    sort_pairs_global<BLOCK>(oid, od, my_cnt, tid, nthr);
+    sort_pairs_global<BLOCK>(oid, od, my_cnt, tid, GT);
   }
 }
 
 template <int METRIC>
 static int launch_range(const RangeArgs &A, bool block_mode, cudaStream_t st) {
   if (block_mode) {
-    size_t smem = (size_t)BLOCK_STAGE * 16;
+    size_t smem = (size_t)BLOCK_STAGE * 18;
     static bool attr_done = false;
     if (!attr_done) {
       DRRT_CUDA(cudaFuncSetAttribute(range_kernel<METRIC, true>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done = true;
     }
-    range_kernel<METRIC, true><<<(unsigned)A.nq, RANGE_T, smem, st>>>(A);
+    range_kernel<METRIC, true><<<(unsigned)A.nq, BLOCK_MODE_WARPS * 32, smem, st>>>(A);
   } else {
-    size_t smem = (size_t)WARP_STAGE * RANGE_WARPS * 16;
-    unsigned nb = (unsigned)((A.nq + RANGE_WARPS - 1) / RANGE_WARPS);
-    range_kernel<METRIC, false><<<nb, RANGE_T, smem, st>>>(A);
+    size_t smem = (size_t)WARP_STAGE * WARP_MODE_WARPS * 18;
+    unsigned nb = (unsigned)((A.nq + WARP_MODE_WARPS - 1) / WARP_MODE_WARPS);
+    range_kernel<METRIC, false><<<nb, WARP_MODE_WARPS * 32, smem, st>>>(A);
   }
   DRRT_LAUNCHED();
   DRRT_CUDA(cudaGetLastError());
@@ -374,7 +502,7 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
   }
   bool block_mode = expected > WARP_STAGE / 2;
 
-  int64_t nvb = block_mode ? nq : (nq + RANGE_WARPS - 1) / RANGE_WARPS;
+  int64_t nvb = block_mode ? nq : (nq + WARP_MODE_WARPS - 1) / WARP_MODE_WARPS;
   DRRT_CHECK(S->r_desc.reserve(nvb, st));
   int64_t guess = (int64_t)std::min(1.0e12, expected * 1.3 * (double)nq) + 1024;
   if ((int64_t)S->r_ids.cap < guess) {

@@ -153,3 +153,22 @@ def test_range_config2_sample(drrt, po):
     for gamma in (synth.GAMMA_SPARSE, synth.GAMMA_REF):
         rad = synth.shrinking_radius(len(pos), gamma)
         _check(t, r, q if gamma == synth.GAMMA_SPARSE else q[:96], rad)
+
+
+def test_range_clustered_ids_fall_back_to_network_sort(drrt, po):
+    # ids of a neighbourhood bunched at both ends of the id range crowd the id
+    # buckets of the output sort: the bitonic fallback must give the same rows
+    pos = synth.box_points(120_000, 91)
+    rng = np.random.default_rng(92)
+    blob = lambda n: np.stack([25 + rng.normal(0, 0.2, n), 25 + rng.normal(0, 0.2, n),
+                               3 + rng.normal(0, 0.2, n)], 1)
+    pos[:120] = blob(120)
+    pos[-150:] = blob(150)
+    pos[50_000:52_500] = np.stack([10 + rng.normal(0, 0.3, 2500), 10 + rng.normal(0, 0.3, 2500),
+                                   2 + rng.normal(0, 0.3, 2500)], 1)
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(400, 93)
+    q[:100] = blob(100)
+    q[100:200] = [10.0, 10.0, 2.0] + rng.normal(0, 0.2, (100, 3))
+    _check(t, r, q, 0.6)     # warp-per-query mode, crowded buckets
+    _check(t, r, q, 3.5)     # CTA-per-query mode, crowded buckets
