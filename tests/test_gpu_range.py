@@ -172,3 +172,26 @@ def test_range_clustered_ids_fall_back_to_network_sort(drrt, po):
     q[100:200] = [10.0, 10.0, 2.0] + rng.normal(0, 0.2, (100, 3))
     _check(t, r, q, 0.6)     # warp-per-query mode, crowded buckets
     _check(t, r, q, 3.5)     # CTA-per-query mode, crowded buckets
+
+
+def test_range_signed_prune_without_wrap(drrt, po):
+    # a tree created WITHOUT wrapped dimensions still uses the wrap-aware metric;
+    # the reference's signed theta prune (kdtree.cpp:744-756) then hides some
+    # in-range nodes depending on the tree shape.  The device reproduces that
+    # through gate[] (store.cuh), with no ghost pass to repair it.
+    pos = synth.box_points(80_000, 95)
+    t, r = _pair(drrt, po, pos, wraps=(), wrap_points=())
+    q = synth.box_points(3000, 96)
+    q[:1500, 2] = W - np.random.default_rng(97).uniform(0.0, 0.5, 1500)
+    off = _check(t, r, q, 1.2)
+    tw, rw = _pair(drrt, po, pos)
+    offw = _check(tw, rw, q, 1.2)
+    assert off[-1] < offw[-1]          # the prune really did hide neighbours
+    # hand-built case: D sits in the left subtree of the theta-split node C
+    p4 = np.array([[10, 10, 3.0], [10, 10, 3.0], [10, 10, 3.1], [10, 10, 0.02]])
+    t4, r4 = _pair(drrt, po, p4, wraps=(), wrap_points=())
+    _, ids, _ = t4.KDFindWithinRange(0.1, np.array([[10.0, 10.0, W - 0.02]]))
+    assert 3 not in ids
+    t5, r5 = _pair(drrt, po, p4)
+    _, ids, _ = t5.KDFindWithinRange(0.1, np.array([[10.0, 10.0, W - 0.02]]))
+    assert list(ids) == [3]
