@@ -31,7 +31,7 @@ struct ref_tree {
 
 int ref_num_threads(void) {
 #ifdef _OPENMP
-  return omp_get_max_threads();
+  return omp_get_num_procs();
 #else
   return 1;
 #endif
@@ -78,7 +78,11 @@ ref_tree *ref_tree_create(int dims, int n_wraps, const int *wrap_dims,
     t->wraps[i] = wrap_dims[i];
     t->wrap_points[i] = wrap_points[i];
   }
-  t->n_flag_sets = ref_num_threads();
+#ifdef _OPENMP
+  t->n_flag_sets = omp_get_num_procs(); /* the most threads a batch call may use */
+#else
+  t->n_flag_sets = 1;
+#endif
   if (t->n_flag_sets < 1) t->n_flag_sets = 1;
   t->flags = (unsigned char **)calloc(t->n_flag_sets, sizeof(unsigned char *));
   t->flags_cap = (int *)calloc(t->n_flag_sets, sizeof(int));
@@ -346,8 +350,9 @@ long ref_range(ref_tree *t, const double *q, double range, int *ids,
 
 static void set_threads(int nthreads) {
 #ifdef _OPENMP
-  if (nthreads > 0) omp_set_num_threads(nthreads);
-  else omp_set_num_threads(omp_get_num_procs());
+  int np = omp_get_num_procs();
+  if (nthreads <= 0 || nthreads > np) nthreads = np; /* one flag set per possible thread */
+  omp_set_num_threads(nthreads);
 #else
   (void)nthreads;
 #endif
@@ -524,7 +529,6 @@ long ref_range_brute(ref_tree *t, const double *q, double range, int *ids,
     const double *p = t->pos + (size_t)i * d;
     double dd = ref_metric(t->metric, q, p);
     int hit = (i == 0) ? (dd <= range) : (dd < range);
-    if (!hit && i == 0) hit = 0;
     for (int g = 0; g < ng && !hit; g++) {
       dd = ref_metric(t->metric, ghosts + g * d, p);
       hit = dd < range;
