@@ -424,6 +424,8 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
   T.n_all = n_obs;
   T.a_kind = S->oa_kind.p; T.a_live = S->oa_live.p; T.a_ox = S->oa_ox.p; T.a_oy = S->oa_oy.p;
   T.a_rad = S->oa_rad.p; T.a_vert_off = S->oa_voff.p; T.a_vx = S->oa_vx.p; T.a_vy = S->oa_vy.p;
+  S->h_o_ox = aox; S->h_o_oy = aoy; S->h_o_rad = arad;
+  S->ogrid_radius = -1.0;  // broadphase grid is stale
   S->has_obstacles = true;
   return DRRT_OK;
 }

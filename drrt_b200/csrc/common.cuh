@@ -76,6 +76,13 @@ struct ObstacleTable {
   const double *a_vx, *a_vy;
 };
 
+struct ObstacleGrid {
+  double x0, y0, inv_cell;
+  int nx, ny;
+  const int32_t *off;    // nx*ny + 1
+  const uint16_t *idx;   // active-obstacle indices
+};
+
 // ---------------------------------------------------------------------------
 // Metrics.  std::min(a,b) == (b<a)?b:a ; std::max(a,b) == (a<b)?b:a.
 

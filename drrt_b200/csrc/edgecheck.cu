@@ -13,12 +13,15 @@
 // kind 3 (polygon) that are used and alive can ever report a hit
 // (:761, :781-804); the host packs those into the "active" table.
 //
-// One thread per edge: solve the six Dubins candidates, bound the path by the
-// hull of its turn circles, cull the active obstacles against that hull
-// (exact: a culled obstacle fails the reference's own bounding reject :765-779
-// for every segment), then walk the 0.1-rad polyline once, testing each
-// segment against the survivors.  The obstacle table is staged in shared
-// memory when it fits.
+// One thread per edge: solve the six Dubins candidates, then walk the 0.1-rad
+// polyline once.  Each segment looks up the cells of a uniform obstacle grid
+// its bounding box touches; a cell lists the obstacles whose reach circle
+// (radius_ + robot radius) touches the cell, so an obstacle that is not listed
+// fails the reference's own bounding reject (:765-779) for that segment and
+// can be skipped exactly.  Listed obstacles get the reference's tests verbatim;
+// inside the polygon loop an edge farther from the segment's first point than
+// (radius + segment length) cannot bring SegmentDistSqrd under radius^2 and is
+// skipped.  The obstacle table is staged in shared memory when it fits.
 #include <math.h>
 
 #include <algorithm>
@@ -29,7 +32,6 @@
 namespace drrt {
 
 static constexpr int EDGE_T = 128;
-static constexpr int MAX_CAND = 24;  // culled obstacle list kept per thread
 
 struct ObsView {
   int n;
@@ -39,9 +41,11 @@ struct ObsView {
   const double *vx, *vy;
 };
 
-// ExplicitEdgeCheck2D for one active obstacle (kind 1 or 3)
+// ExplicitEdgeCheck2D for one active obstacle (kind 1 or 3).  far2 =
+// ((radius + |p1-p0|) * (1+1e-9) + 1e-9)^2 : polygon edges farther than that
+// from p0 are at more than `radius` from every point of the segment.
 __device__ __forceinline__ bool segment_hits(const ObsView &O, int o, double p0x, double p0y,
-                                             double p1x, double p1y, double radius) {
+                                             double p1x, double p1y, double radius, double far2) {
   double d2 = dist_sqrd_point_segment(O.ox[o], O.oy[o], p0x, p0y, p1x, p1y);  // :769-779
   double reach = radius + O.rad[o];
   if (d2 > reach * reach) return false;
@@ -52,61 +56,40 @@ __device__ __forceinline__ bool segment_hits(const ObsView &O, int o, double p0x
   const double rr = radius * radius;
   for (int v = v0; v < v1; v++) {  // :788-804
     double bx = O.vx[v], by = O.vy[v];
-    if (segment_dist_sqrd(p0x, p0y, p1x, p1y, ax, ay, bx, by) < rr) return true;
+    if (!(dist_sqrd_point_segment(p0x, p0y, ax, ay, bx, by) > far2)) {
+      if (segment_dist_sqrd(p0x, p0y, p1x, p1y, ax, ay, bx, by) < rr) return true;
+    }
     ax = bx;
     ay = by;
   }
   return false;
 }
 
-struct Cull {
-  int n;        // -1: too many survivors, test every obstacle
-  int16_t idx[MAX_CAND];
-};
-
-__device__ __forceinline__ void cull_obstacles(const ObsView &O, double lox, double loy, double hix,
-                                               double hiy, double radius, Cull &C) {
-  C.n = 0;
-  for (int o = 0; o < O.n; o++) {
-    double dx = fmax(fmax(lox - O.ox[o], O.ox[o] - hix), 0.0);
-    double dy = fmax(fmax(loy - O.oy[o], O.oy[o] - hiy), 0.0);
-    double reach = (radius + O.rad[o]) * (1.0 + 1e-9) + 1e-9;
-    if (dx * dx + dy * dy <= reach * reach) {
-      if (C.n < MAX_CAND) C.idx[C.n] = (int16_t)o;
-      C.n++;
-    }
-  }
-  if (C.n > MAX_CAND || O.n > 32767) C.n = -1;
-}
-
-__device__ __forceinline__ bool segment_vs_culled(const ObsView &O, const Cull &C, double p0x,
-                                                  double p0y, double p1x, double p1y,
-                                                  double radius) {
-  if (C.n >= 0) {
-    for (int c = 0; c < C.n; c++)
-      if (segment_hits(O, C.idx[c], p0x, p0y, p1x, p1y, radius)) return true;
+__device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const ObstacleGrid &G,
+                                                     double p0x, double p0y, double p1x,
+                                                     double p1y, double radius) {
+  double dx = p1x - p0x, dy = p1y - p0y;
+  double far = (radius + sqrt(dx * dx + dy * dy)) * (1.0 + 1e-9) + 1e-9;
+  double far2 = far * far;
+  double lox = fmin(p0x, p1x), hix = fmax(p0x, p1x), loy = fmin(p0y, p1y), hiy = fmax(p0y, p1y);
+  if (G.nx > 0 && lox <= hix && loy <= hiy) {
+    // cells the segment's bounding box touches; beyond the grid nothing is in reach
+    double fx0 = floor((lox - G.x0) * G.inv_cell), fx1 = floor((hix - G.x0) * G.inv_cell);
+    double fy0 = floor((loy - G.y0) * G.inv_cell), fy1 = floor((hiy - G.y0) * G.inv_cell);
+    if (fx1 < 0.0 || fy1 < 0.0 || fx0 > (double)(G.nx - 1) || fy0 > (double)(G.ny - 1)) return false;
+    int cx0 = (int)fmax(fx0, 0.0), cx1 = (int)fmin(fx1, (double)(G.nx - 1));
+    int cy0 = (int)fmax(fy0, 0.0), cy1 = (int)fmin(fy1, (double)(G.ny - 1));
+    for (int cx = cx0; cx <= cx1; cx++)
+      for (int cy = cy0; cy <= cy1; cy++) {
+        int c = cx * G.ny + cy;
+        for (int e = G.off[c]; e < G.off[c + 1]; e++)
+          if (segment_hits(O, G.idx[e], p0x, p0y, p1x, p1y, radius, far2)) return true;
+      }
     return false;
   }
   for (int o = 0; o < O.n; o++)
-    if (segment_hits(O, o, p0x, p0y, p1x, p1y, radius)) return true;
+    if (segment_hits(O, o, p0x, p0y, p1x, p1y, radius, far2)) return true;
   return false;
-}
-
-__device__ __forceinline__ void hull_of_path(const DubinsPath &P, double r_min, double &lox,
-                                             double &loy, double &hix, double &hiy) {
-  lox = loy = 1.0e300;
-  hix = hiy = -1.0e300;
-  for (int k = 0; k < 3; k++) {
-    const DubinsPart &p = P.part[k];
-    if (p.kind == PART_LINE) {
-      lox = fmin(lox, fmin(p.cx, p.a)); hix = fmax(hix, fmax(p.cx, p.a));
-      loy = fmin(loy, fmin(p.cy, p.b)); hiy = fmax(hiy, fmax(p.cy, p.b));
-    } else if (p.kind != PART_NONE) {
-      double rr = fabs(r_min) * (1.0 + 1e-9) + 1e-9;
-      lox = fmin(lox, p.cx - rr); hix = fmax(hix, p.cx + rr);
-      loy = fmin(loy, p.cy - rr); hiy = fmax(hiy, p.cy + rr);
-    }
-  }
 }
 
 struct EdgeArgs {
@@ -118,6 +101,7 @@ struct EdgeArgs {
   int edge_kind;
   double robot_radius, r_min;
   ObsView obs;
+  ObstacleGrid grid;
   int obs_smem;                     // stage the obstacle table in shared memory
   uint8_t *verdict;
   double *length;
@@ -171,20 +155,14 @@ edgecheck_kernel(EdgeArgs A) {
     dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
     dist = P.dist;
     if (O.n > 0 && P.type != TRAJ_XXX) {
-      double lox, loy, hix, hiy;
-      hull_of_path(P, A.r_min, lox, loy, hix, hiy);
-      Cull C;
-      cull_obstacles(O, lox, loy, hix, hiy, A.robot_radius, C);
-      if (C.n != 0) {
-        PolylineWalker W;
-        W.start(&P, A.r_min);
-        double px, py, cx, cy;
-        if (W.next(&px, &py)) {
-          while (W.next(&cx, &cy)) {  // dubinsedge.cpp:875-893
-            if (segment_vs_culled(O, C, px, py, cx, cy, A.robot_radius)) { hit = true; break; }
-            px = cx;
-            py = cy;
-          }
+      PolylineWalker W;
+      W.start(&P, A.r_min);
+      double px, py, cx, cy;
+      if (W.next(&px, &py)) {
+        while (W.next(&cx, &cy)) {  // dubinsedge.cpp:875-893
+          if (segment_vs_obstacles(O, A.grid, px, py, cx, cy, A.robot_radius)) { hit = true; break; }
+          px = cx;
+          py = cy;
         }
       }
     }
@@ -193,27 +171,89 @@ edgecheck_kernel(EdgeArgs A) {
     double th = atan2(ey - sy, ex - sx);
     dist = metric_dist(A.metric, sx, sy, th, ex, ey, th);
     if (O.n > 0) {
-      Cull C;
-      double pad = 1e-9 * (fabs(sx) + fabs(sy) + fabs(ex) + fabs(ey) + 1.0);
-      cull_obstacles(O, fmin(sx, ex) - pad, fmin(sy, ey) - pad, fmax(sx, ex) + pad,
-                     fmax(sy, ey) + pad, A.robot_radius, C);
-      if (C.n != 0) {
-        const double traj_length = 50;
-        double x_val = sx, y_val = sy;
-        const double x_dist = fabs(ex - x_val), y_dist = fabs(ey - y_val);
-        double px = x_val, py = y_val;
-        for (int i = 0; i < 50; i++) {
-          if (ex > sx) x_val += x_dist / traj_length; else x_val -= x_dist / traj_length;
-          if (ey > sy) y_val += y_dist / traj_length; else y_val -= y_dist / traj_length;
-          if (segment_vs_culled(O, C, px, py, x_val, y_val, A.robot_radius)) { hit = true; break; }
-          px = x_val;
-          py = y_val;
-        }
+      const double traj_length = 50;
+      double x_val = sx, y_val = sy;
+      const double x_dist = fabs(ex - x_val), y_dist = fabs(ey - y_val);
+      double px = x_val, py = y_val;
+      for (int i = 0; i < 50; i++) {
+        if (ex > sx) x_val += x_dist / traj_length; else x_val -= x_dist / traj_length;
+        if (ey > sy) y_val += y_dist / traj_length; else y_val -= y_dist / traj_length;
+        if (segment_vs_obstacles(O, A.grid, px, py, x_val, y_val, A.robot_radius)) { hit = true; break; }
+        px = x_val;
+        py = y_val;
       }
     }
   }
   A.verdict[e] = hit ? 1 : 0;
   if (A.length) A.length[e] = dist;
+}
+
+// uniform grid over the active obstacles' reach circles (host build, tiny)
+static int ensure_obstacle_grid(Store *S, double robot_radius, cudaStream_t st) {
+  if (S->ogrid_radius == robot_radius) return DRRT_OK;
+  const size_t n = S->h_o_ox.size();
+  ObstacleGrid G{};
+  if (n == 0 || n > 65535) {  // nx == 0: kernels test every obstacle
+    S->ogrid = G;
+    S->ogrid_radius = robot_radius;
+    return DRRT_OK;
+  }
+  std::vector<double> reach(n);
+  double lox = 1e300, loy = 1e300, hix = -1e300, hiy = -1e300, mean = 0.0;
+  for (size_t i = 0; i < n; i++) {
+    reach[i] = (fabs(robot_radius) + fabs(S->h_o_rad[i])) * (1.0 + 1e-9) + 1e-9;
+    lox = std::min(lox, S->h_o_ox[i] - reach[i]); hix = std::max(hix, S->h_o_ox[i] + reach[i]);
+    loy = std::min(loy, S->h_o_oy[i] - reach[i]); hiy = std::max(hiy, S->h_o_oy[i] + reach[i]);
+    mean += reach[i] / n;
+  }
+  if (!std::isfinite(lox + loy + hix + hiy + mean)) {
+    S->ogrid = G;
+    S->ogrid_radius = robot_radius;
+    return DRRT_OK;
+  }
+  double extent = std::max(std::max(hix - lox, hiy - loy), 1e-9);
+  double cell = std::max(extent / 96.0, 0.5 * mean);
+  G.x0 = lox; G.y0 = loy; G.inv_cell = 1.0 / cell;
+  G.nx = std::max(1, (int)ceil((hix - lox) / cell) + 1);
+  G.ny = std::max(1, (int)ceil((hiy - loy) / cell) + 1);
+  const int ncell = G.nx * G.ny;
+  std::vector<int32_t> off(ncell + 1, 0);
+  std::vector<uint16_t> idx;
+  for (int pass = 0; pass < 2; pass++) {
+    std::vector<int32_t> cur(off.begin(), off.end() - 1);
+    for (size_t i = 0; i < n; i++) {
+      const double ox = S->h_o_ox[i], oy = S->h_o_oy[i], r = reach[i];
+      int cx0 = std::max(0, (int)floor((ox - r - lox) / cell) - 1), cx1 = std::min(G.nx - 1, (int)floor((ox + r - lox) / cell) + 1);
+      int cy0 = std::max(0, (int)floor((oy - r - loy) / cell) - 1), cy1 = std::min(G.ny - 1, (int)floor((oy + r - loy) / cell) + 1);
+      for (int cx = cx0; cx <= cx1; cx++)
+        for (int cy = cy0; cy <= cy1; cy++) {
+          // circle vs (slightly grown) cell rectangle
+          double rx0 = lox + (cx - 1e-6) * cell, rx1 = lox + (cx + 1.000001) * cell;
+          double ry0 = loy + (cy - 1e-6) * cell, ry1 = loy + (cy + 1.000001) * cell;
+          double dx = std::max(std::max(rx0 - ox, ox - rx1), 0.0);
+          double dy = std::max(std::max(ry0 - oy, oy - ry1), 0.0);
+          if (dx * dx + dy * dy > r * r) continue;
+          int c = cx * G.ny + cy;
+          if (pass == 0) off[c + 1]++;
+          else idx[cur[c]++] = (uint16_t)i;
+        }
+    }
+    if (pass == 0) {
+      for (int c = 0; c < ncell; c++) off[c + 1] += off[c];
+      idx.resize(off[ncell] + 1);
+    }
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  DRRT_CHECK(S->og_off.reserve(off.size(), st));
+  DRRT_CHECK(S->og_idx.reserve(idx.size(), st));
+  DRRT_CUDA(cudaMemcpyAsync(S->og_off.p, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  DRRT_CUDA(cudaMemcpyAsync(S->og_idx.p, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  G.off = S->og_off.p;
+  G.idx = S->og_idx.p;
+  S->ogrid = G;
+  S->ogrid_radius = robot_radius;
+  return DRRT_OK;
 }
 
 static size_t obstacle_smem_bytes(const Store *S, int nverts) {
@@ -244,6 +284,8 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   A.verdict = verdict_dev; A.length = length_dev;
   size_t smem = 0;
   if (A.obs.n > 0) {
+    DRRT_CHECK(ensure_obstacle_grid(S, robot_radius, st));
+    A.grid = S->ogrid;
     size_t need = obstacle_smem_bytes(S, S->obs.n_active_verts);
     if (need <= 96 * 1024) { smem = need; A.obs_smem = 1; }
   }

@@ -19,6 +19,8 @@
 // matter (ensure_index).
 #pragma once
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace drrt {
@@ -83,6 +85,14 @@ struct Store {
   DevBuf<uint8_t> oa_live;
   DevBuf<double> o_ox, o_oy, o_rad, o_vx, o_vy, oa_ox, oa_oy, oa_rad, oa_vx, oa_vy;
   bool has_obstacles = false;
+  // broadphase over the active obstacles: uniform grid, cell -> obstacles whose
+  // reach circle (radius_ + robot radius) touches the cell; rebuilt when the
+  // table or the robot radius changes
+  std::vector<double> h_o_ox, h_o_oy, h_o_rad;
+  ObstacleGrid ogrid{};
+  double ogrid_radius = -1.0;
+  DevBuf<int32_t> og_off;
+  DevBuf<uint16_t> og_idx;
 };
 
 // store.cu
