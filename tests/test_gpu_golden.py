@@ -1,0 +1,78 @@
+"""The CUDA path against tests/golden/ref_v1.json -- outputs of the reference's
+own compiled sources (see tests/test_oracle_vs_ref.py) -- through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from test_oracle_vs_ref import gen, unhex
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(HERE, "golden", "ref_v1.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="module")
+def I():
+    return gen.inputs()
+
+
+def test_structure(drrt, gold, I):
+    t = drrt.KDTree()
+    t.KDInsert(I["pos"])
+    st = t.structure()
+    for k in ("parent", "left", "right", "split"):
+        assert st[k].tolist() == gold["structure"][k], k
+
+
+@pytest.mark.parametrize("name,wrap,metric", [("wrap_r2s1", True, 0), ("nowrap_r2s1", False, 0),
+                                              ("wrap_euclid", True, 1)])
+def test_range_and_nearest(drrt, gold, I, name, wrap, metric):
+    kw = dict(metric=metric) if wrap else dict(wraps=(), wrap_points=(), metric=metric)
+    if wrap and metric == 1:
+        kw = dict(metric=1, wraps=(2,), wrap_points=(2.0 * drrt.PI,))
+    t = drrt.KDTree(**kw)
+    t.KDInsert(I["pos"])
+    off, ids, dist = t.KDFindWithinRange(I["rad"], I["q"])
+    g = gold["range_" + name]
+    assert off.tolist() == g["off"] and ids.tolist() == g["ids"]     # bit-exact id sets
+    assert np.array_equal(dist, unhex(g["dist"]))                    # and JList keys
+    nid, nd = t.KDFindNearest(I["q"])
+    g = gold["nearest_" + name]
+    assert nid.tolist() == g["ids"]
+    assert np.allclose(nd, unhex(g["dist"]), rtol=1e-5, atol=0)
+
+
+def test_lattice(drrt, gold, I):
+    t = drrt.KDTree(metric=1)
+    t.KDInsert(I["grid"])
+    off, ids, dist = t.KDFindWithinRange(2.0, I["grid"][::5])
+    g = gold["range_lattice"]
+    assert off.tolist() == g["off"] and ids.tolist() == g["ids"]
+    assert np.array_equal(dist, unhex(g["dist"]))
+
+
+def test_edges_and_points(drrt, po, gold, I):
+    g = gold["edges"]
+    t = drrt.KDTree()
+    t.SetObstacles(**I["o"])
+    v, ln = t.ExplicitEdgeCheck(I["s"], I["e"])
+    want = np.array(g["verdict"], dtype=np.uint8)
+    diff = np.nonzero(v != want)[0]
+    if len(diff):   # only edges within 1e-6 of an obstacle boundary may differ (north star)
+        _, _, clr = po.RefObstacles(**I["o"]).edge_check_batch(I["s"], I["e"], want_clearance=True)
+        assert (clr[diff] < 1e-6).all()
+    assert np.allclose(ln, unhex(g["dist"]), rtol=1e-9)
+    xy, npts, names, length = t.CalculateTrajectory(I["s"], I["e"])
+    same = [i for i in range(len(names)) if names[i] == g["type"][i] and npts[i] == g["npts"][i]]
+    assert len(same) >= len(names) - 2
+    for i in same:
+        assert np.allclose(xy[i, :3].ravel()[:len(g["xy_first"][i])], unhex(g["xy_first"][i]), atol=1e-9)
+        assert np.allclose(xy[i, npts[i] - 2:npts[i]].ravel(), unhex(g["xy_last"][i]), atol=1e-9)
+    assert t.ExplicitNodeCheck(I["pts"]).tolist() == gold["points"]
