@@ -65,7 +65,8 @@ __global__ void counts_from_offsets(const int64_t *off, int64_t nq, int32_t *cou
   if (i < nq) counts[i] = (int32_t)(off[i + 1] - off[i]);
 }
 
-static int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist) {
+static int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist,
+                    bool nearest = false) {
   if (nq < 0 || k < 1 || (nq > 0 && (!q || !ids)))
     return set_error(DRRT_ERR_INVALID, "knn: arguments");
   cudaStream_t st = S->stream;
@@ -73,7 +74,7 @@ static int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, 
   DRRT_CHECK(S->i_stage.reserve(nq * k + 1, st));
   DRRT_CHECK(S->d_stage.reserve(nq * k + 1, st));
   DRRT_CHECK(upload(q, S->q_stage.p, 3 * nq * sizeof(double), st));
-  DRRT_CHECK(knn_batch_dev(S, nq, S->q_stage.p, k, S->i_stage.p, S->d_stage.p, st));
+  DRRT_CHECK(knn_batch_dev(S, nq, S->q_stage.p, k, S->i_stage.p, S->d_stage.p, st, nearest));
   DRRT_CHECK(download(ids, S->i_stage.p, nq * k * sizeof(int32_t), st));
   if (dist) DRRT_CHECK(download(dist, S->d_stage.p, nq * k * sizeof(double), st));
   DRRT_CUDA(cudaStreamSynchronize(st));
@@ -350,13 +351,13 @@ int drrt_range_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, const d
 
 int drrt_nearest_batch(drrt_store *h, int64_t nq, const double *q, int32_t *ids, double *dist) {
   ENTER(h);
-  return knn_host(S, nq, q, 1, ids, dist);
+  return knn_host(S, nq, q, 1, ids, dist, true);
 }
 int drrt_nearest_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, int32_t *ids_dev,
                            double *dist_dev, void *stream) {
   ENTER(h);
   if (!q_dev || !ids_dev || !dist_dev) return set_error(DRRT_ERR_INVALID, "nearest: arguments");
-  return knn_batch_dev(S, nq, q_dev, 1, ids_dev, dist_dev, pick(S, stream));
+  return knn_batch_dev(S, nq, q_dev, 1, ids_dev, dist_dev, pick(S, stream), true);
 }
 int drrt_knn_batch(drrt_store *h, int64_t nq, const double *q, int k, int32_t *ids, double *dist) {
   ENTER(h);

@@ -26,6 +26,7 @@ struct KnnArgs {
   const double *q;
   int64_t nq;
   int k;
+  int nearest;  // k == 1 with KDFindNearest's ghost pass
   double r0;
   int32_t *ids;
   double *dist;
@@ -87,11 +88,12 @@ knn_kernel(KnnArgs A) {
   T.id = reinterpret_cast<int32_t *>(smem_raw + sizeof(double) * KNN_WARPS * A.k) + (size_t)w * A.k;
   const double qx = A.q[3 * qi], qy = A.q[3 * qi + 1], qt = A.q[3 * qi + 2];
 
+  double px = qx, py = qy, pt = qt;  // current probe
   auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
     bool cand = false;
     double d = 0.0;
     if (valid) {
-      double s = metric_sum<METRIC>(qx, qy, qt, nx, ny, nt);
+      double s = metric_sum<METRIC>(px, py, pt, nx, ny, nt);
       d = sqrt(s);
       cand = (T.count < T.k) || pair_less(d, id, T.worst_d, T.worst_id);
     }
@@ -104,24 +106,43 @@ knn_kernel(KnnArgs A) {
       if ((T.count < T.k) || pair_less(cd, ci, T.worst_d, T.worst_id)) topk_insert(T, cd, ci, lane);
     }
   };
-
-  double r = A.r0;
-  for (;;) {
-    T.count = 0;
-    T.worst_d = 1.0e308;
-    T.worst_id = 0x7fffffff;
-    Query Q;
-    bool all = true;
-    if (V.n_indexed > 0) {
-      setup_query<METRIC>(V, qx, qy, qt, r, Q);
-      Q.has_ghost = false;
-      all = covers_all(V, Q);
-      scan_columns(V, Q, 0, 1, s_runs[w], s_pref[w], lane, visit);
+  auto search = [&]() {
+    double r = A.r0;
+    for (;;) {
+      T.count = 0;
+      T.worst_d = 1.0e308;
+      T.worst_id = 0x7fffffff;
+      Query Q;
+      bool all = true;
+      if (V.n_indexed > 0) {
+        setup_query<METRIC>(V, px, py, pt, r, Q);
+        Q.has_ghost = false;
+        all = covers_all(V, Q);
+        scan_columns(V, Q, 0, 1, s_runs[w], s_pref[w], lane, visit);
+      }
+      scan_tail(V, 0, 1, lane, visit);
+      // every unscanned node is farther than r
+      if (all || (T.count == T.k && T.worst_d <= r)) break;
+      r *= 2.0;
     }
-    scan_tail(V, 0, 1, lane, visit);
-    // every unscanned node is farther than r
-    if (all || (T.count == T.k && T.worst_d <= r)) break;
-    r *= 2.0;
+    __syncwarp();
+  };
+  search();
+  if (A.nearest && V.has_wrap && T.count == 1) {
+    // KDFindNearest's ghost pass (kdtree.cpp:277-303): the ghost is searched when
+    // it can beat the current nearest distance, and wins only when strictly closer
+    double d1 = T.d[0];
+    int32_t id1 = T.id[0];
+    double gt;
+    if (ghost_of<METRIC>(qx, qy, qt, V.wrap_point, d1, &gt)) {
+      __syncwarp();
+      pt = gt;
+      search();
+      if (!(T.d[0] < d1)) {
+        __syncwarp();
+        if (lane == 0) { T.d[0] = d1; T.id[0] = id1; }
+      }
+    }
   }
   __syncwarp();
   for (int i = lane; i < A.k; i += 32) {
@@ -132,7 +153,7 @@ knn_kernel(KnnArgs A) {
 }
 
 int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
-                  double *dist_dev, cudaStream_t st) {
+                  double *dist_dev, cudaStream_t st, bool nearest) {
   if (nq < 0 || k < 1) return set_error(DRRT_ERR_INVALID, "knn: bad nq/k");
   if (k > KNN_KMAX) return set_error(DRRT_ERR_UNSUPPORTED, "knn: k > %d", KNN_KMAX);
   if (nq == 0) return DRRT_OK;
@@ -140,6 +161,7 @@ int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids
   KnnArgs A{};
   A.V = make_view(S);
   A.q = q_dev; A.nq = nq; A.k = k; A.ids = ids_dev; A.dist = dist_dev;
+  A.nearest = (nearest && k == 1) ? 1 : 0;
   A.r0 = 1.0;
   if (S->n_indexed > 0) {
     const GridParams &g = S->gp;

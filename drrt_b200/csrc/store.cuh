@@ -111,7 +111,7 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
                     double radius_all, cudaStream_t st, drrt_range_result *out);
 // knn.cu
 int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
-                  double *dist_dev, cudaStream_t st);
+                  double *dist_dev, cudaStream_t st, bool nearest = false);
 // edgecheck.cu
 int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const double *end_dev,
                         const int32_t *sid_dev, const int32_t *eid_dev, int edge_kind,
