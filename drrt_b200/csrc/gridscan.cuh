@@ -203,6 +203,8 @@ __device__ __forceinline__ void scan_columns_block(const GridView &A, const Quer
   const int ncy = Q.iy1 - Q.iy0 + 1;
   const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
   const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
+  const bool two = Q.tb0 <= Q.tb1;  // a second (wrapped) theta run per column
+  const int nent = two ? 2 * T : T;
   for (int cb = 0; cb < ncol; cb += T) {
     int s0, l0, s1, l1;
     column_runs(A, Q, cb + tid, ncol, ncy, cull, s0, l0, s1, l1);
@@ -222,16 +224,21 @@ __device__ __forceinline__ void scan_columns_block(const GridView &A, const Quer
       total += v;
     }
     int excl = wbase + inc - tot;
-    run_start[2 * tid] = s0;
-    run_start[2 * tid + 1] = s1;
-    run_pref[2 * tid] = excl;
-    run_pref[2 * tid + 1] = excl + l0;
-    if (tid == T - 1) run_pref[2 * T] = total;
+    if (two) {
+      run_start[2 * tid] = s0;
+      run_start[2 * tid + 1] = s1;
+      run_pref[2 * tid] = excl;
+      run_pref[2 * tid + 1] = excl + l0;
+    } else {
+      run_start[tid] = s0;
+      run_pref[tid] = excl;
+    }
+    if (tid == T - 1) run_pref[nent] = total;
     __syncthreads();
     int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;
     int c0 = w * per, c1 = min(total, c0 + per);
     if (c0 < c1) {
-      int lo = 0, hi = 2 * T;  // largest j with run_pref[j] <= c0
+      int lo = 0, hi = nent;  // largest j with run_pref[j] <= c0
       while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
         if (run_pref[mid] <= c0) lo = mid; else hi = mid;

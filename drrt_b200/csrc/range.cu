@@ -209,13 +209,14 @@ __device__ void order_by_id(unsigned long long *keys, int n, int *hist, int *s_m
   if (tid == 0) s_misc[2] = 0;
   group_sync<BLOCK>();
   if (BLOCK) { mn = s_misc[0]; mx = s_misc[1]; }
-  int shift = 0;
-  while (((mx - mn) >> shift) >= NB) shift++;
+  // bucket = (id - mn) * NB / span (monotone in id, so bucket order is id order)
+  const double scale = (double)NB / ((double)(mx - mn) + 1.0);
   // arrival rank inside the bucket
   bool crowded = false;
   for (int i = tid; i < n; i += T) {
     unsigned long long k = keys[i];
-    int b = ((int)(k >> 32) - mn) >> shift;
+    int b = min((int)((double)((int)(k >> 32) - mn) * scale), NB - 1);
+
     int rank = atomicAdd(&hist[b], 1);
     keys[i] = (k & 0xffffffff00000000ull) | (unsigned)rank;
     crowded |= rank >= CROWDED;
@@ -264,13 +265,20 @@ __device__ void order_by_id(unsigned long long *keys, int n, int *hist, int *s_m
   group_sync<BLOCK>();
   for (int i = tid; i < n; i += T) {
     unsigned long long k = keys[i];
-    int pos = hist[((int)(k >> 32) - mn) >> shift] + (int)(unsigned)(k & 0xffffffffu);
+    int bb = min((int)((double)((int)(k >> 32) - mn) * scale), NB - 1);
+    int pos = hist[bb] + (int)(unsigned)(k & 0xffffffffu);
+
     order[pos] = (uint16_t)i;
   }
   group_sync<BLOCK>();
   // buckets with more than one hit: insertion sort of their slots by id
   for (int b = tid; b < NB; b += T) {
     int s0 = hist[b], c = hist[b + 1] - s0;
+    if (c == 2) {
+      uint16_t u = order[s0], v = order[s0 + 1];
+      if ((unsigned)(keys[u] >> 32) > (unsigned)(keys[v] >> 32)) { order[s0] = v; order[s0 + 1] = u; }
+      continue;
+    }
     for (int a = 1; a < c; a++) {
       uint16_t v = order[s0 + a];
       unsigned vid = (unsigned)(keys[v] >> 32);
