@@ -10,6 +10,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 BIN = os.path.join(_HERE, "_ref", "drrt_ref")
+# the same driver linked against the product's drop-in shim (make -C oracle shim)
+SHIM_BIN = os.path.join(_HERE, "_ref", "drrt_shim")
 
 
 def available():
@@ -90,13 +92,14 @@ EMPTY_OBS = dict(kind=[], used=[], life_span=[], origin=np.zeros((0, 2)), radius
                  verts=np.zeros((0, 2)))
 
 
-def edges(start, end, obstacles=None, r_min=1.0, robot_radius=0.5, metric=0, want_traj=False):
+def edges(start, end, obstacles=None, r_min=1.0, robot_radius=0.5, metric=0, want_traj=False,
+          cmd=None):
     s = np.ascontiguousarray(start, dtype=np.float64).reshape(-1, 3)
     e = np.ascontiguousarray(end, dtype=np.float64).reshape(-1, 3)
     n = len(s)
     payload = (struct.pack("<idd", metric, r_min, robot_radius)
                + _obs_payload(obstacles or EMPTY_OBS) + struct.pack("<q", n) + _f64(s) + _f64(e))
-    raw = _run("traj" if want_traj else "edgecheck", payload)
+    raw = _run(cmd or ("traj" if want_traj else "edgecheck"), payload)
     types = [raw[4 * i:4 * i + 3].decode() for i in range(n)]
     o = 4 * n
     dist = np.frombuffer(raw, dtype=np.float64, count=n, offset=o).copy()

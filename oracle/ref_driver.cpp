@@ -30,6 +30,13 @@
 
 #include "_ref/distance_function.inc"  // double distance_function(VectorXd a, VectorXd b)
 
+#ifdef DRRT_SHIM
+// the same driver linked against drrt_b200/shim/kdtree_gpu.cpp instead of the
+// reference's kdtree.cpp (oracle/_ref/drrt_shim): the reference's own JList /
+// Edge / Obstacle objects call into the CUDA library
+#include "drrt_gpu_shim.h"
+#endif
+
 // src/thetastar.cpp:10-15 (DistFunc) is compiled from the reference too
 // obstacle.h:262-264 declares QuickCheck2D with a Vector2d point, obstacle.cpp:925
 // defines it with a VectorXd one; this is the definition's prototype
@@ -259,6 +266,18 @@ static int cmd_edges(const char *cmd, Reader &in, Writer &out) {
         hit = ExplicitEdgeCheck2D(obs[o], edge->trajectory_.row(k - 1), edge->trajectory_.row(k),
                                   C->robot_radius_);
     verdict[i] = hit ? 1 : 0;
+#ifdef DRRT_SHIM
+    if (!strcmp(cmd, "edgecheck_gpu")) {
+      static bool uploaded = false;
+      if (!uploaded) {
+        for (size_t o = 0; o < obs.size(); o++) C->obstacles_->ListPush(obs[o]);
+        DrrtGpuUploadObstacles(T.get(), C);
+        uploaded = true;
+      }
+      verdict[i] = ExplicitEdgeCheckGpu(C, T.get(), edge) ? 1 : 0;
+      dist[i] = edge->dist_;
+    }
+#endif
   }
   out.arr(types); out.arr(dist); out.arr(npts); out.arr(verdict);
   if (want_traj) out.arr(xy);
@@ -310,7 +329,8 @@ int main(int argc, char **argv) {
   const char *cmd = argv[1];
   if (!strcmp(cmd, "range") || !strcmp(cmd, "nearest") || !strcmp(cmd, "structure") || !strcmp(cmd, "ghosts"))
     return cmd_tree(cmd, in, out);
-  if (!strcmp(cmd, "traj") || !strcmp(cmd, "edgecheck")) return cmd_edges(cmd, in, out);
+  if (!strcmp(cmd, "traj") || !strcmp(cmd, "edgecheck") || !strcmp(cmd, "edgecheck_gpu"))
+    return cmd_edges(cmd, in, out);
   if (!strcmp(cmd, "points")) return cmd_points(in, out);
   if (!strcmp(cmd, "geom")) return cmd_geom(in, out);
   fprintf(stderr, "unknown command %s\n", cmd);

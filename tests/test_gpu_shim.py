@@ -1,0 +1,60 @@
+"""Drop-in check: the REFERENCE'S OWN compiled objects (JList, Edge, Obstacle,
+the driver that calls KDTree's public methods) linked against the product's
+shim (drrt_b200/shim/kdtree_gpu.cpp, obstacle_gpu.cpp) instead of the
+reference's kdtree.cpp -- `make -C oracle shim` -> oracle/_ref/drrt_shim.  The
+reference-side code then runs unchanged and every tree call lands in the CUDA
+library; results must equal the all-CPU reference binary's golden outputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from test_oracle_vs_ref import gen, unhex
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def shim(drrt):
+    from oracle import pyref
+    if not os.path.exists(pyref.SHIM_BIN):
+        pytest.skip("oracle/_ref/drrt_shim not built (needs /root/reference at build time)")
+    old = pyref.BIN
+    pyref.BIN = pyref.SHIM_BIN
+    yield pyref
+    pyref.BIN = old
+
+
+@pytest.fixture(scope="module")
+def gold():
+    with open(os.path.join(HERE, "golden", "ref_v1.json")) as fh:
+        return json.load(fh)
+
+
+def test_reference_objects_over_gpu_tree(shim, gold):
+    I = gen.inputs()
+    st = shim.structure(I["pos"])              # kd_parent_/kd_child_*/kd_split_ mirrored from the device
+    for k in ("parent", "left", "right", "split"):
+        assert st[k].tolist() == gold["structure"][k], k
+    off, ids, dist = shim.range_batch(I["pos"], I["q"], I["rad"])   # KDFindWithinRange -> JList -> pops
+    g = gold["range_wrap_r2s1"]
+    assert off.tolist() == g["off"] and ids.tolist() == g["ids"]
+    assert np.array_equal(dist, unhex(g["dist"]))
+    nid, nd = shim.nearest_batch(I["pos"], I["q"])
+    assert nid.tolist() == gold["nearest_wrap_r2s1"]["ids"]
+    off, ids, dist = shim.range_batch(I["grid"], I["grid"][::5], 2.0, metric=1)   # Theta*'s DistFunc tree
+    g = gold["range_lattice"]
+    assert off.tolist() == g["off"] and ids.tolist() == g["ids"]
+
+
+def test_reference_edges_over_gpu_checker(shim, po, gold):
+    I = gen.inputs()
+    r = shim.edges(I["s"], I["e"], I["o"], cmd="edgecheck_gpu")
+    want = np.array(gold["edges"]["verdict"], dtype=np.uint8)
+    diff = np.nonzero(r["verdict"] != want)[0]
+    if len(diff):
+        _, _, clr = po.RefObstacles(**I["o"]).edge_check_batch(I["s"], I["e"], want_clearance=True)
+        assert (clr[diff] < 1e-6).all()
+    assert np.allclose(r["dist"], unhex(gold["edges"]["dist"]), rtol=1e-9)
