@@ -37,8 +37,10 @@ struct Query {
   double gt;
   bool has_ghost;
   int ix0, ix1, iy0, iy1;
-  int ta0, ta1, tb0, tb1;  // theta cell runs (b empty when tb0 > tb1)
-  double rr;
+  int ta0, ta1, tb0, tb1;  // theta cell runs of the whole query (b empty when tb0 > tb1)
+  double rr, key;          // padded radius; theta key of the probes
+  bool all;                // the ball covers the whole indexed box
+  bool may_wrap;           // some column can have a second (wrapped) theta run
 };
 
 __device__ __forceinline__ int cell_floor(double v, double v0, double inv_h) {
@@ -46,6 +48,36 @@ __device__ __forceinline__ int cell_floor(double v, double v0, double inv_h) {
   if (f < -1.0e9) return -1000000000;
   if (f > 1.0e9) return 1000000000;
   return (int)f;
+}
+
+// Cells of the theta axis within `half` of key: run a = [ta0,ta1], and the
+// periodic wrap run b = [tb0,tb1] (empty when tb0 > tb1).
+__device__ __forceinline__ void theta_runs(const GridParams &g, double key, double half, int &ta0,
+                                           int &ta1, int &tb0, int &tb1) {
+  const double slack = 1e-6 / g.inv_ht;
+  tb0 = 1; tb1 = 0;
+  if (g.periodic) {
+    if (!(2.0 * (half + slack) < g.period * (1.0 - 1e-9)) || !(key == key)) {
+      ta0 = 0; ta1 = g.nt - 1;
+      return;
+    }
+    int lo = cell_floor(key - half - slack, g.t0, g.inv_ht);
+    int hi = cell_floor(key + half + slack, g.t0, g.inv_ht);
+    if (hi - lo + 1 >= g.nt) { ta0 = 0; ta1 = g.nt - 1; return; }
+    ta0 = max(lo, 0); ta1 = min(hi, g.nt - 1);
+    if (lo < 0) { tb0 = lo + g.nt; tb1 = g.nt - 1; }
+    else if (hi > g.nt - 1) { tb0 = 0; tb1 = hi - g.nt; }
+    if (tb0 <= tb1 && tb0 <= ta1 && ta0 <= tb1) {  // overlap: merge
+      ta0 = 0; ta1 = g.nt - 1; tb0 = 1; tb1 = 0;
+    }
+  } else {
+    int lo = cell_floor(key - half - slack, g.t0, g.inv_ht);
+    int hi = cell_floor(key + half + slack, g.t0, g.inv_ht);
+    ta0 = max(lo, 0); ta1 = min(hi, g.nt - 1);
+    if (hi < 0) { ta0 = ta1 = 0; }
+    if (lo > g.nt - 1) { ta0 = ta1 = g.nt - 1; }
+    if (!(key == key)) { ta0 = 0; ta1 = g.nt - 1; }
+  }
 }
 
 // Fills the probe (ghost) and the candidate cell ranges of a query of radius r:
@@ -72,43 +104,23 @@ __device__ __forceinline__ void setup_query(const GridView &A, double qx, double
   Q.iy0 = max(a, 0); Q.iy1 = min(b, g.ny - 1);
   if (b < 0) { Q.iy0 = Q.iy1 = 0; }
   if (a > g.ny - 1) { Q.iy0 = Q.iy1 = g.ny - 1; }
-  // theta cells
-  double slack = 1e-6 / g.inv_ht;
-  Q.tb0 = 1; Q.tb1 = 0;
-  if (g.periodic) {
-    double k = theta_key(Q.t, g.period);
-    if (!(2.0 * (rr + slack) < g.period * (1.0 - 1e-9)) || !(k == k)) {
-      Q.ta0 = 0; Q.ta1 = g.nt - 1;
-    } else {
-      int lo = cell_floor(k - rr - slack, g.t0, g.inv_ht);
-      int hi = cell_floor(k + rr + slack, g.t0, g.inv_ht);
-      if (hi - lo + 1 >= g.nt) {
-        Q.ta0 = 0; Q.ta1 = g.nt - 1;
-      } else {
-        Q.ta0 = max(lo, 0); Q.ta1 = min(hi, g.nt - 1);
-        if (lo < 0) { Q.tb0 = lo + g.nt; Q.tb1 = g.nt - 1; }
-        else if (hi > g.nt - 1) { Q.tb0 = 0; Q.tb1 = hi - g.nt; }
-        if (Q.tb0 <= Q.tb1 && Q.tb0 <= Q.ta1 && Q.ta0 <= Q.tb1) {  // overlap: merge
-          Q.ta0 = 0; Q.ta1 = g.nt - 1; Q.tb0 = 1; Q.tb1 = 0;
-        }
-      }
-    }
-  } else {
-    int lo = cell_floor(Q.t - rr - slack, g.t0, g.inv_ht);
-    int hi = cell_floor(Q.t + rr + slack, g.t0, g.inv_ht);
-    Q.ta0 = max(lo, 0); Q.ta1 = min(hi, g.nt - 1);
-    if (hi < 0) { Q.ta0 = Q.ta1 = 0; }
-    if (lo > g.nt - 1) { Q.ta0 = Q.ta1 = g.nt - 1; }
-    if (!(Q.t == Q.t)) { Q.ta0 = 0; Q.ta1 = g.nt - 1; }
-  }
+  // theta cells for the whole query (per column they are narrowed, column_runs)
+  Q.key = g.periodic ? theta_key(Q.t, g.period) : Q.t;
+  theta_runs(g, Q.key, rr, Q.ta0, Q.ta1, Q.tb0, Q.tb1);
+  // the ball swallows the whole indexed box: every column gets its full theta range
+  double ex = fmax(fabs(Q.x - g.x0), fabs(Q.x - (g.x0 + g.nx / g.inv_hx)));
+  double ey = fmax(fabs(Q.y - g.y0), fabs(Q.y - (g.y0 + g.ny / g.inv_hy)));
+  double et = g.periodic ? 0.5 * g.period
+                         : fmax(fabs(Q.t - g.t0), fabs(Q.t - (g.t0 + g.nt / g.inv_ht)));
+  Q.all = (ex * ex + ey * ey + et * et <= Q.r * Q.r) || !(Q.key == Q.key);
+  // a narrower per-column range can wrap even when the query-wide one is the full circle
+  Q.may_wrap = g.periodic && !Q.all && (Q.tb0 <= Q.tb1 || (Q.ta0 == 0 && Q.ta1 == g.nt - 1));
 }
 
-
-// whether the selected cells cover the whole index
+// whether the scan of Q visits every indexed node
 __device__ __forceinline__ bool covers_all(const GridView &A, const Query &Q) {
-  const GridParams &g = A.gp;
-  return Q.ix0 == 0 && Q.ix1 == g.nx - 1 && Q.iy0 == 0 && Q.iy1 == g.ny - 1 && Q.ta0 == 0 &&
-         Q.ta1 == g.nt - 1;
+  (void)A;
+  return Q.all;
 }
 
 // the one or two contiguous record runs of candidate column `col` (empty when
@@ -128,13 +140,21 @@ __device__ __forceinline__ void column_runs(const GridView &A, const Query &Q, i
   if (ix < g.nx - 1 && Q.x > xhi) dx = Q.x - xhi;
   if (iy > 0 && Q.y < ylo) dy = ylo - Q.y;
   if (iy < g.ny - 1 && Q.y > yhi) dy = Q.y - yhi;
-  if (dx * dx + dy * dy > cull) return;
+  double rho2 = dx * dx + dy * dy;
+  if (rho2 > cull) return;
+  // a node of this column is at least rho from the probe in (x,y): its theta term
+  // must stay under sqrt(r^2 - rho^2) to be in range
+  int ta0 = Q.ta0, ta1 = Q.ta1, tb0 = Q.tb0, tb1 = Q.tb1;
+  if (!Q.all) {
+    double half = sqrt(fmax(Q.rr * Q.rr - rho2, 0.0)) * (1.0 + 1e-9) + 1e-9 * (1.0 + Q.rr);
+    theta_runs(g, Q.key, half, ta0, ta1, tb0, tb1);
+  }
   int cbase = (ix * g.ny + iy) * g.nt;
-  s0 = A.cell_start[cbase + Q.ta0];
-  l0 = A.cell_start[cbase + Q.ta1 + 1] - s0;
-  if (Q.tb0 <= Q.tb1) {
-    s1 = A.cell_start[cbase + Q.tb0];
-    l1 = A.cell_start[cbase + Q.tb1 + 1] - s1;
+  s0 = A.cell_start[cbase + ta0];
+  l0 = A.cell_start[cbase + ta1 + 1] - s0;
+  if (tb0 <= tb1) {
+    s1 = A.cell_start[cbase + tb0];
+    l1 = A.cell_start[cbase + tb1 + 1] - s1;
   }
 }
 
@@ -203,7 +223,7 @@ __device__ __forceinline__ void scan_columns_block(const GridView &A, const Quer
   const int ncy = Q.iy1 - Q.iy0 + 1;
   const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
   const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
-  const bool two = Q.tb0 <= Q.tb1;  // a second (wrapped) theta run per column
+  const bool two = Q.may_wrap;  // a second (wrapped) theta run per column
   const int nent = two ? 2 * T : T;
   for (int cb = 0; cb < ncol; cb += T) {
     int s0, l0, s1, l1;
