@@ -182,9 +182,9 @@ __device__ void sort_pairs_global(int32_t *ids, double *dist, int64_t n, int tid
 // Orders the n staged hits by node id: order[pos] = staging slot of the hit
 // that belongs at output position pos.  Counting sort on id buckets -- node ids
 // of a neighbourhood are spread over the id range, so a bucket holds about one
-// hit and (bucket start + arrival rank) is final for most; the thread owning a
-// bucket with several hits puts those few slots in id order.  When ids cluster
-// (some bucket crowded) the bitonic network sorts the keys instead.
+// hit; a hit's final position is its bucket's start plus the number of bucket
+// mates with a smaller id (a scan of the one to three mates, element-parallel).
+// When ids cluster (some bucket crowded) the bitonic network sorts the keys.
 template <bool BLOCK, int NB, int T>
 __device__ void order_by_id(unsigned long long *keys, int n, int *hist, int *s_misc,
                             uint16_t *order, int tid) {
@@ -263,33 +263,26 @@ __device__ void order_by_id(unsigned long long *keys, int n, int *hist, int *s_m
   for (int e = 0; e < PER; e++) { hist[tid * PER + e] = excl; excl += local[e]; }
   if (tid == T - 1) hist[NB] = excl;
   group_sync<BLOCK>();
+  // slot by arrival rank: order[] lists each bucket's members contiguously
   for (int i = tid; i < n; i += T) {
     unsigned long long k = keys[i];
     int bb = min((int)((double)((int)(k >> 32) - mn) * scale), NB - 1);
-    int pos = hist[bb] + (int)(unsigned)(k & 0xffffffffu);
-
-    order[pos] = (uint16_t)i;
+    order[hist[bb] + (int)(unsigned)(k & 0xffffffffu)] = (uint16_t)i;
   }
   group_sync<BLOCK>();
-  // buckets with more than one hit: insertion sort of their slots by id
-  for (int b = tid; b < NB; b += T) {
-    int s0 = hist[b], c = hist[b + 1] - s0;
-    if (c == 2) {
-      uint16_t u = order[s0], v = order[s0 + 1];
-      if ((unsigned)(keys[u] >> 32) > (unsigned)(keys[v] >> 32)) { order[s0] = v; order[s0 + 1] = u; }
-      continue;
-    }
-    for (int a = 1; a < c; a++) {
-      uint16_t v = order[s0 + a];
-      unsigned vid = (unsigned)(keys[v] >> 32);
-      int j = a - 1;
-      while (j >= 0 && (unsigned)(keys[order[s0 + j]] >> 32) > vid) {
-        order[s0 + j + 1] = order[s0 + j];
-        j--;
-      }
-      order[s0 + j + 1] = v;
-    }
+  // final position = bucket start + number of bucket mates with a smaller id
+  for (int i = tid; i < n; i += T) {
+    unsigned long long k = keys[i];
+    unsigned id = (unsigned)(k >> 32);
+    int bb = min((int)((double)((int)id - mn) * scale), NB - 1);
+    int s0 = hist[bb], c = hist[bb + 1] - s0;
+    int fin = s0;
+    if (c > 1)
+      for (int j = 0; j < c; j++) fin += ((unsigned)(keys[order[s0 + j]] >> 32) < id) ? 1 : 0;
+    keys[i] = (k & 0xffffffff00000000ull) | (unsigned)fin;
   }
+  group_sync<BLOCK>();
+  for (int i = tid; i < n; i += T) order[(unsigned)(keys[i] & 0xffffffffu)] = (uint16_t)i;
   group_sync<BLOCK>();
 }
 
@@ -345,6 +338,7 @@ range_kernel(RangeArgs A) {
   __shared__ int s_runs[RUN_SLOTS];
   __shared__ int s_pref[RUN_SLOTS + WARPS];
   __shared__ int s_tmp[WARPS];
+  __shared__ Query s_query;
   __shared__ int s_hist[NSTAGE][NB + 1];
   __shared__ int s_misc[NSTAGE][4 + WARPS];
 
@@ -388,8 +382,19 @@ range_kernel(RangeArgs A) {
     }
   };
   if (active) {  // uniform per CTA in CTA mode, per warp in warp mode
-    setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
-                        A.radius ? A.radius[qi] : A.radius_all, Q);
+    if (BLOCK) {
+      // one warp resolves the probe and the cell ranges for the whole CTA
+      if (w == 0) {
+        setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
+                            A.radius ? A.radius[qi] : A.radius_all, Q);
+        if (lane == 0) s_query = Q;
+      }
+      __syncthreads();
+      Q = s_query;
+    } else {
+      setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
+                          A.radius ? A.radius[qi] : A.radius_all, Q);
+    }
     scan_all();
   }
   __syncthreads();
