@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""BASELINE config 4: largetest.cpp-scale replanning on one GPU.
+
+Box [-50,50]^2 x [0,2pi') (src/largetest.cpp:253-254), delta = 10, gamma = 100.
+The store grows to --nodes (default 2 M) by insert batches of 4096; after every
+batch the batch's own nodes are range-queried at the RRTx radius and every
+(new -> hit) and (hit -> new) Dubins edge is collision-checked against 256
+polygons; every 64 batches 16 obstacles move by (+-1, +-1) and the
+obstacle-conflict queries of FindPointsInConflictWithObstacle
+(src/obstacle.cpp:540-610: radius robot_radius + O.radius + PI', centre theta = PI')
+are re-issued.  Everything stays on the device; one JSON line is printed.
+
+    python benchmarks/replanning.py [--nodes 2000000] [--batch 4096]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nodes", type=int, default=2_000_000)
+    ap.add_argument("--batch", type=int, default=4096)
+    args = ap.parse_args()
+    import torch
+    import drrt_b200
+    from drrt_b200 import capi, synth
+    from drrt_b200.kdtree import KDTree
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    rng = np.random.default_rng(0xD2270004)
+    pos = np.empty((args.nodes, 3))
+    pos[:, 0] = rng.uniform(-50, 50, args.nodes)
+    pos[:, 1] = rng.uniform(-50, 50, args.nodes)
+    pos[:, 2] = rng.uniform(0, synth.TWO_PI, args.nodes)
+    pos_t = torch.from_numpy(pos).to(dev)
+    obs = synth.obstacles(256, 0xD2270003, lo=-48.0, hi=48.0)
+    tree = KDTree(device=0, capacity=args.nodes)
+    tree.SetObstacles(**obs)
+    delta, gamma = 10.0, 100.0
+
+    n_batches = args.nodes // args.batch
+    tot_q = tot_hits = tot_edges = tot_coll = tot_conf_q = tot_conf_hits = 0
+    t_insert = t_range = t_edge = t_conf = 0.0
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    l0 = capi.launches()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for b in range(n_batches):
+        lo, hi = b * args.batch, (b + 1) * args.batch
+        batch = pos_t[lo:hi]
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        tree.KDInsert_dev(batch)
+        e1.record()
+        r = synth.shrinking_radius(hi, gamma, delta)
+        res = tree.KDFindWithinRange_dev(r, batch)
+        e2.record()
+        off, ids, _ = KDTree.range_result_tensors(res)
+        counts = off[1:] - off[:-1]
+        src = torch.repeat_interleave(torch.arange(lo, hi, device=dev, dtype=torch.int32), counts)
+        start = torch.cat([src, ids])
+        end = torch.cat([ids, src])
+        verdict = torch.empty(start.shape[0], dtype=torch.uint8, device=dev)
+        length = torch.empty(start.shape[0], dtype=torch.float64, device=dev)
+        tree.ExplicitEdgeCheck_dev(verdict, start_ids=start, end_ids=end, robot_radius=synth.ROBOT_RADIUS,
+                                   r_min=synth.R_MIN, length_out=length)
+        e3.record()
+        torch.cuda.synchronize()
+        t_insert += e0.elapsed_time(e1)
+        t_range += e1.elapsed_time(e2)
+        t_edge += e2.elapsed_time(e3)
+        tot_q += args.batch
+        tot_hits += int(res.total)
+        tot_edges += int(start.shape[0])
+        tot_coll += int(verdict.sum().item())
+        if (b + 1) % 64 == 0:
+            # 16 obstacles move; nodes in conflict with each are looked up again
+            which = rng.choice(256, 16, replace=False)
+            step = rng.choice([-1.0, 1.0], (16, 2))
+            for k, o in enumerate(which):
+                obs["origin"][o] += step[k]
+                obs["verts"][obs["vert_off"][o]:obs["vert_off"][o + 1]] += step[k]
+            tree.SetObstacles(**obs)
+            centres = np.concatenate([obs["origin"][which], np.full((16, 1), synth.PI)], 1)
+            radii = synth.ROBOT_RADIUS + obs["radius"][which] + synth.PI
+            c0, c1 = ev(), ev()
+            c0.record()
+            resc = tree.KDFindWithinRange_dev(torch.from_numpy(radii).to(dev), torch.from_numpy(centres).to(dev))
+            c1.record()
+            torch.cuda.synchronize()
+            t_conf += c0.elapsed_time(c1)
+            tot_conf_q += 16
+            tot_conf_hits += int(resc.total)
+    wall = time.perf_counter() - wall0
+    line = {"workload": "config4 replanning: grow to %d nodes by %d-node insert batches; per batch range + "
+                        "2*hits Dubins edge checks; 16 obstacles move every 64 batches" % (args.nodes, args.batch),
+            "nodes": n_batches * args.batch, "batches": n_batches,
+            "wall_s": wall, "gpu_ms": {"insert": t_insert, "range": t_range, "edge_check": t_edge,
+                                       "conflict_range": t_conf},
+            "inserts_per_s": n_batches * args.batch / (t_insert * 1e-3),
+            "range_queries_per_s": tot_q / (t_range * 1e-3), "hits_per_query": tot_hits / tot_q,
+            "edge_checks_per_s": tot_edges / (t_edge * 1e-3), "edges": tot_edges,
+            "collision_rate": tot_coll / max(tot_edges, 1),
+            "conflict_queries": tot_conf_q, "conflict_hits_per_query": tot_conf_hits / max(tot_conf_q, 1),
+            "gpu_launches": capi.launches() - l0}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

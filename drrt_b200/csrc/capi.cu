@@ -180,6 +180,7 @@ int drrt_store_create(int device, int dims, int n_wraps, const int *wrap_dims,
   cudaError_t e = cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&S->d_pending, 64);
   if (e == cudaSuccess) e = cudaMalloc(&S->d_ticket, 64);
+  if (e == cudaSuccess) e = cudaMalloc(&S->d_edge_counter, 64);
   if (e == cudaSuccess) e = cudaMalloc(&S->d_bounds, 6 * sizeof(double));
   if (e == cudaSuccess) e = cudaMallocHost(&S->h_pending, 64);
   if (e == cudaSuccess) e = cudaMallocHost(&S->h_bounds, 6 * sizeof(double));
@@ -217,6 +218,9 @@ int drrt_store_destroy(drrt_store *h) {
     S->oa_rad.release(); S->oa_vx.release(); S->oa_vy.release();
     if (S->d_pending) cudaFree(S->d_pending);
     if (S->d_ticket) cudaFree(S->d_ticket);
+    if (S->d_edge_counter) cudaFree(S->d_edge_counter);
+    S->edge_paths.release(); S->og_off.release(); S->og_idx.release(); S->og_eobs.release();
+    S->og_ball.release(); S->og_eax.release(); S->og_eay.release(); S->og_ebx.release(); S->og_eby.release();
     if (S->d_bounds) cudaFree(S->d_bounds);
     if (S->h_pending) cudaFreeHost(S->h_pending);
     if (S->h_bounds) cudaFreeHost(S->h_bounds);
@@ -425,7 +429,8 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
   T.n_all = n_obs;
   T.a_kind = S->oa_kind.p; T.a_live = S->oa_live.p; T.a_ox = S->oa_ox.p; T.a_oy = S->oa_oy.p;
   T.a_rad = S->oa_rad.p; T.a_vert_off = S->oa_voff.p; T.a_vx = S->oa_vx.p; T.a_vy = S->oa_vy.p;
-  S->h_o_ox = aox; S->h_o_oy = aoy; S->h_o_rad = arad;
+  S->h_o_ox = aox; S->h_o_oy = aoy; S->h_o_rad = arad; S->h_o_vx = avx; S->h_o_vy = avy;
+  S->h_o_kind = k_act; S->h_o_voff = vo_act;
   S->ogrid_radius = -1.0;  // broadphase grid is stale
   S->has_obstacles = true;
   return DRRT_OK;

@@ -13,15 +13,20 @@
 // kind 3 (polygon) that are used and alive can ever report a hit
 // (:761, :781-804); the host packs those into the "active" table.
 //
-// One thread per edge: solve the six Dubins candidates, then walk the 0.1-rad
-// polyline once.  Each segment looks up the cells of a uniform obstacle grid
-// its bounding box touches; a cell lists the obstacles whose reach circle
-// (radius_ + robot radius) touches the cell, so an obstacle that is not listed
-// fails the reference's own bounding reject (:765-779) for that segment and
-// can be skipped exactly.  Listed obstacles get the reference's tests verbatim;
-// inside the polygon loop an edge farther from the segment's first point than
-// (radius + segment length) cannot bring SegmentDistSqrd under radius^2 and is
-// skipped.  The obstacle table is staged in shared memory when it fits.
+// Dubins edges take two kernels.  dubins_solve_kernel (one thread per edge,
+// uniform work) solves the six candidates and leaves a 112-byte path record.
+// dubins_walk_kernel is persistent: every lane walks one edge's 0.1-rad polyline
+// a segment per iteration and, when its edge is decided (first hit, or end of
+// path), takes the next unclaimed edge, so lanes of a warp stay busy although
+// polylines have 3..191 segments and three quarters of them end early on a hit.
+// Straight (LineCheck) edges have 50 segments each and use one kernel.
+// Each segment looks up the cells of a uniform grid its bounding box touches; a
+// cell lists the polygon EDGES (and kind-1 balls) that come within the robot
+// radius of it, so an edge that is not listed cannot bring SegmentDistSqrd
+// under radius^2 for that segment.  A listed edge farther from the segment's
+// first point than (radius + segment length) is skipped; the rest get the
+// reference's SegmentDistSqrd and, on a hit, its obstacle's bounding reject
+// (:765-779) verbatim -- the verdict is the same OR over obstacles.  The obstacle table is staged in shared memory when it fits.
 #include <math.h>
 
 #include <algorithm>
@@ -65,6 +70,18 @@ __device__ __forceinline__ bool segment_hits(const ObsView &O, int o, double p0x
   return false;
 }
 
+// the reference's bounding reject for obstacle o (obstacle.cpp:765-779)
+__device__ __forceinline__ bool within_reach(const ObsView &O, int o, double p0x, double p0y,
+                                             double p1x, double p1y, double radius) {
+  double d2 = dist_sqrd_point_segment(O.ox[o], O.oy[o], p0x, p0y, p1x, p1y);
+  double reach = radius + O.rad[o];
+  return !(d2 > reach * reach);
+}
+
+// ExplicitEdgeCheck2D of one polyline segment against every obstacle, through the edge grid:
+//   true  <=>  some live ball passes the bounding reject, or some polygon edge has
+//              SegmentDistSqrd < radius^2 and its obstacle passes the bounding reject
+// which is the OR over obstacles of obstacle.cpp:761-804.
 __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const ObstacleGrid &G,
                                                      double p0x, double p0y, double p1x,
                                                      double p1y, double radius) {
@@ -79,11 +96,23 @@ __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const Obs
     if (fx1 < 0.0 || fy1 < 0.0 || fx0 > (double)(G.nx - 1) || fy0 > (double)(G.ny - 1)) return false;
     int cx0 = (int)fmax(fx0, 0.0), cx1 = (int)fmin(fx1, (double)(G.nx - 1));
     int cy0 = (int)fmax(fy0, 0.0), cy1 = (int)fmin(fy1, (double)(G.ny - 1));
+    const double rr = radius * radius;
     for (int cx = cx0; cx <= cx1; cx++)
       for (int cy = cy0; cy <= cy1; cy++) {
         int c = cx * G.ny + cy;
-        for (int e = G.off[c]; e < G.off[c + 1]; e++)
-          if (segment_hits(O, G.idx[e], p0x, p0y, p1x, p1y, radius, far2)) return true;
+        for (int e = G.off[c]; e < G.off[c + 1]; e++) {
+          int j = G.idx[e];
+          if (j >= G.n_edges) {  // ball: obstacle.cpp:781
+            if (within_reach(O, G.ball[j - G.n_edges], p0x, p0y, p1x, p1y, radius)) return true;
+            continue;
+          }
+          double ax = G.eax[j], ay = G.eay[j], bx = G.ebx[j], by = G.eby[j];
+          // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
+          if (dist_sqrd_point_segment(p0x, p0y, ax, ay, bx, by) > far2) continue;
+          if (segment_dist_sqrd(p0x, p0y, p1x, p1y, ax, ay, bx, by) < rr &&   // :796-803
+              within_reach(O, G.eobs[j], p0x, p0y, p1x, p1y, radius))          // :765-779
+            return true;
+        }
       }
     return false;
   }
@@ -137,8 +166,79 @@ __device__ __forceinline__ void stage_obstacles(ObsView &O, unsigned char *smem)
   O.kind = s_kind; O.voff = s_voff;
 }
 
+// K4a: Edge::NewEdge + the candidate solve of CalculateTrajectory, one thread per edge
 __global__ void __launch_bounds__(EDGE_T)
-edgecheck_kernel(EdgeArgs A) {
+dubins_solve_kernel(EdgeArgs A, DubinsPath *paths) {
+  const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
+  if (e >= A.n) return;
+  double sx, sy, st, ex, ey, et;
+  load_pose(A, e, false, sx, sy, st);
+  load_pose(A, e, true, ex, ey, et);
+  DubinsPath P;
+  double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
+  dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
+  paths[e] = P;
+  if (A.length) A.length[e] = P.dist;
+}
+
+// K4b: polyline walk + ExplicitEdgeCheck2D per segment, lanes refill from a global counter
+__global__ void __launch_bounds__(EDGE_T)
+dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next_edge) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ObsView O = A.obs;
+  if (A.obs_smem && O.n > 0) stage_obstacles(O, smem_raw);
+  const int lane = threadIdx.x & 31;
+  PolylineWalker W;
+  W.part = 3;
+  long long e = -1;       // edge this lane is walking
+  bool exhausted = false; // no unclaimed edges left
+  bool have_prev = false;
+  double px = 0.0, py = 0.0;
+  for (;;) {
+    // lanes without an edge claim the next ones (one atomic per warp)
+    unsigned need = __ballot_sync(0xffffffffu, e < 0 && !exhausted);
+    if (need) {
+      int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(next_edge, (unsigned long long)__popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (e < 0 && !exhausted) {
+        long long mine = (long long)base + __popc(need & ((1u << lane) - 1));
+        if (mine >= A.n) {
+          exhausted = true;
+        } else {
+          e = mine;
+          W.start(paths + e, A.r_min);
+          have_prev = false;
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, e < 0)) break;
+    if (e >= 0) {
+      double cx, cy;
+      bool decided = false, hit = false;
+      if (!W.next(&cx, &cy)) {
+        decided = true;  // end of path, no segment collided (dubinsedge.cpp:897)
+      } else {
+        if (have_prev && segment_vs_obstacles(O, A.grid, px, py, cx, cy, A.robot_radius)) {
+          decided = true;  // :878-889 first hit
+          hit = true;
+        }
+        px = cx;
+        py = cy;
+        have_prev = true;
+      }
+      if (decided) {
+        A.verdict[e] = hit ? 1 : 0;
+        e = -1;
+      }
+    }
+  }
+}
+
+// K5: LineCheck (obstacle.cpp:1098-1133), one thread per edge
+__global__ void __launch_bounds__(EDGE_T)
+linecheck_kernel(EdgeArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ObsView O = A.obs;
   if (A.obs_smem && O.n > 0) stage_obstacles(O, smem_raw);
@@ -148,95 +248,139 @@ edgecheck_kernel(EdgeArgs A) {
   load_pose(A, e, false, sx, sy, st);
   load_pose(A, e, true, ex, ey, et);
   bool hit = false;
-  double dist;
-  if (A.edge_kind == DRRT_EDGE_DUBINS) {
-    DubinsPath P;
-    double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
-    dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
-    dist = P.dist;
-    if (O.n > 0 && P.type != TRAJ_XXX) {
-      PolylineWalker W;
-      W.start(&P, A.r_min);
-      double px, py, cx, cy;
-      if (W.next(&px, &py)) {
-        while (W.next(&cx, &cy)) {  // dubinsedge.cpp:875-893
-          if (segment_vs_obstacles(O, A.grid, px, py, cx, cy, A.robot_radius)) { hit = true; break; }
-          px = cx;
-          py = cy;
-        }
-      }
-    }
-  } else {
-    // LineCheck obstacle.cpp:1098-1133
-    double th = atan2(ey - sy, ex - sx);
-    dist = metric_dist(A.metric, sx, sy, th, ex, ey, th);
-    if (O.n > 0) {
-      const double traj_length = 50;
-      double x_val = sx, y_val = sy;
-      const double x_dist = fabs(ex - x_val), y_dist = fabs(ey - y_val);
-      double px = x_val, py = y_val;
-      for (int i = 0; i < 50; i++) {
-        if (ex > sx) x_val += x_dist / traj_length; else x_val -= x_dist / traj_length;
-        if (ey > sy) y_val += y_dist / traj_length; else y_val -= y_dist / traj_length;
-        if (segment_vs_obstacles(O, A.grid, px, py, x_val, y_val, A.robot_radius)) { hit = true; break; }
-        px = x_val;
-        py = y_val;
-      }
+  double th = atan2(ey - sy, ex - sx);
+  double dist = metric_dist(A.metric, sx, sy, th, ex, ey, th);
+  if (O.n > 0) {
+    const double traj_length = 50;
+    double x_val = sx, y_val = sy;
+    const double x_dist = fabs(ex - x_val), y_dist = fabs(ey - y_val);
+    double px = x_val, py = y_val;
+    for (int i = 0; i < 50; i++) {
+      if (ex > sx) x_val += x_dist / traj_length; else x_val -= x_dist / traj_length;
+      if (ey > sy) y_val += y_dist / traj_length; else y_val -= y_dist / traj_length;
+      if (segment_vs_obstacles(O, A.grid, px, py, x_val, y_val, A.robot_radius)) { hit = true; break; }
+      px = x_val;
+      py = y_val;
     }
   }
   A.verdict[e] = hit ? 1 : 0;
   if (A.length) A.length[e] = dist;
 }
 
-// uniform grid over the active obstacles' reach circles (host build, tiny)
+// distance from an axis-aligned rectangle to a segment (0 when they touch)
+static double rect_segment_dist(double rx0, double ry0, double rx1, double ry1, double ax, double ay,
+                                double bx, double by) {
+  // Liang-Barsky: does the segment enter the rectangle?
+  double t0 = 0.0, t1 = 1.0, dx = bx - ax, dy = by - ay;
+  const double p[4] = {-dx, dx, -dy, dy}, q[4] = {ax - rx0, rx1 - ax, ay - ry0, ry1 - ay};
+  bool inside = true;
+  for (int k = 0; k < 4 && inside; k++) {
+    if (p[k] == 0.0) { if (q[k] < 0.0) inside = false; }
+    else {
+      double r = q[k] / p[k];
+      if (p[k] < 0.0) { if (r > t1) inside = false; else if (r > t0) t0 = r; }
+      else { if (r < t0) inside = false; else if (r < t1) t1 = r; }
+    }
+  }
+  if (inside) return 0.0;
+  auto pt_seg = [](double px, double py, double sx, double sy, double ex, double ey) {
+    double vx = px - sx, vy = py - sy, ux = ex - sx, uy = ey - sy;
+    double det = vx * ux + vy * uy, len = ux * ux + uy * uy;
+    double t = len > 0.0 ? std::min(1.0, std::max(0.0, det / len)) : 0.0;
+    double cx = sx + t * ux - px, cy = sy + t * uy - py;
+    return sqrt(cx * cx + cy * cy);
+  };
+  auto pt_rect = [&](double px, double py) {
+    double ex = std::max(std::max(rx0 - px, px - rx1), 0.0), ey = std::max(std::max(ry0 - py, py - ry1), 0.0);
+    return sqrt(ex * ex + ey * ey);
+  };
+  double d = std::min(pt_rect(ax, ay), pt_rect(bx, by));
+  d = std::min(d, pt_seg(rx0, ry0, ax, ay, bx, by));
+  d = std::min(d, pt_seg(rx1, ry0, ax, ay, bx, by));
+  d = std::min(d, pt_seg(rx0, ry1, ax, ay, bx, by));
+  d = std::min(d, pt_seg(rx1, ry1, ax, ay, bx, by));
+  return d;
+}
+
+// Edge grid over the active obstacles (host build; a few thousand edges).  A cell
+// lists every polygon edge within pad = radius(1+1e-6)+1e-6 of the cell rectangle,
+// and every ball whose reach circle touches it.
 static int ensure_obstacle_grid(Store *S, double robot_radius, cudaStream_t st) {
   if (S->ogrid_radius == robot_radius) return DRRT_OK;
   const size_t n = S->h_o_ox.size();
   ObstacleGrid G{};
-  if (n == 0 || n > 65535) {  // nx == 0: kernels test every obstacle
+  auto disable = [&]() {  // nx == 0: kernels test every obstacle
     S->ogrid = G;
     S->ogrid_radius = robot_radius;
     return DRRT_OK;
+  };
+  if (n == 0) return disable();
+  std::vector<double> eax, eay, ebx, eby;
+  std::vector<int32_t> eobs, ball;
+  for (size_t o = 0; o < n; o++) {
+    if (S->h_o_kind[o] == 1) { ball.push_back((int32_t)o); continue; }
+    int v0 = S->h_o_voff[o], v1 = S->h_o_voff[o + 1];
+    if (v1 - v0 < 2) continue;  // obstacle.cpp:785
+    double ax = S->h_o_vx[v1 - 1], ay = S->h_o_vy[v1 - 1];
+    for (int v = v0; v < v1; v++) {  // obstacle.cpp:788-804: (last,first), (0,1), ...
+      eax.push_back(ax); eay.push_back(ay);
+      ebx.push_back(S->h_o_vx[v]); eby.push_back(S->h_o_vy[v]);
+      eobs.push_back((int32_t)o);
+      ax = S->h_o_vx[v]; ay = S->h_o_vy[v];
+    }
   }
-  std::vector<double> reach(n);
-  double lox = 1e300, loy = 1e300, hix = -1e300, hiy = -1e300, mean = 0.0;
-  for (size_t i = 0; i < n; i++) {
-    reach[i] = (fabs(robot_radius) + fabs(S->h_o_rad[i])) * (1.0 + 1e-9) + 1e-9;
-    lox = std::min(lox, S->h_o_ox[i] - reach[i]); hix = std::max(hix, S->h_o_ox[i] + reach[i]);
-    loy = std::min(loy, S->h_o_oy[i] - reach[i]); hiy = std::max(hiy, S->h_o_oy[i] + reach[i]);
-    mean += reach[i] / n;
+  const size_t ne = eax.size(), nb = ball.size();
+  if (ne + nb == 0 || ne + nb > 100000000) return disable();
+  const double pad = fabs(robot_radius) * (1.0 + 1e-6) + 1e-6;
+  double lox = 1e300, loy = 1e300, hix = -1e300, hiy = -1e300;
+  for (size_t j = 0; j < ne; j++) {
+    lox = std::min(lox, std::min(eax[j], ebx[j]) - pad); hix = std::max(hix, std::max(eax[j], ebx[j]) + pad);
+    loy = std::min(loy, std::min(eay[j], eby[j]) - pad); hiy = std::max(hiy, std::max(eay[j], eby[j]) + pad);
   }
-  if (!std::isfinite(lox + loy + hix + hiy + mean)) {
-    S->ogrid = G;
-    S->ogrid_radius = robot_radius;
-    return DRRT_OK;
+  std::vector<double> reach(nb);
+  for (size_t k = 0; k < nb; k++) {
+    int o = ball[k];
+    reach[k] = (fabs(robot_radius) + fabs(S->h_o_rad[o])) * (1.0 + 1e-6) + 1e-6;
+    lox = std::min(lox, S->h_o_ox[o] - reach[k]); hix = std::max(hix, S->h_o_ox[o] + reach[k]);
+    loy = std::min(loy, S->h_o_oy[o] - reach[k]); hiy = std::max(hiy, S->h_o_oy[o] + reach[k]);
   }
+  if (!std::isfinite(lox + loy + hix + hiy)) return disable();
   double extent = std::max(std::max(hix - lox, hiy - loy), 1e-9);
-  double cell = std::max(extent / 96.0, 0.5 * mean);
+  double cell = std::max(extent / 160.0, pad);
   G.x0 = lox; G.y0 = loy; G.inv_cell = 1.0 / cell;
   G.nx = std::max(1, (int)ceil((hix - lox) / cell) + 1);
   G.ny = std::max(1, (int)ceil((hiy - loy) / cell) + 1);
+  G.n_edges = (int32_t)ne;
   const int ncell = G.nx * G.ny;
-  std::vector<int32_t> off(ncell + 1, 0);
-  std::vector<uint16_t> idx;
+  std::vector<int32_t> off(ncell + 1, 0), idx;
   for (int pass = 0; pass < 2; pass++) {
     std::vector<int32_t> cur(off.begin(), off.end() - 1);
-    for (size_t i = 0; i < n; i++) {
-      const double ox = S->h_o_ox[i], oy = S->h_o_oy[i], r = reach[i];
-      int cx0 = std::max(0, (int)floor((ox - r - lox) / cell) - 1), cx1 = std::min(G.nx - 1, (int)floor((ox + r - lox) / cell) + 1);
-      int cy0 = std::max(0, (int)floor((oy - r - loy) / cell) - 1), cy1 = std::min(G.ny - 1, (int)floor((oy + r - loy) / cell) + 1);
+    auto visit = [&](double bx0, double by0, double bx1, double by1, int entry, double r,
+                     const double *seg) {
+      int cx0 = std::max(0, (int)floor((bx0 - lox) / cell) - 1), cx1 = std::min(G.nx - 1, (int)floor((bx1 - lox) / cell) + 1);
+      int cy0 = std::max(0, (int)floor((by0 - loy) / cell) - 1), cy1 = std::min(G.ny - 1, (int)floor((by1 - loy) / cell) + 1);
       for (int cx = cx0; cx <= cx1; cx++)
         for (int cy = cy0; cy <= cy1; cy++) {
-          // circle vs (slightly grown) cell rectangle
+          // the (slightly grown) cell rectangle; device cell = floor((x - x0) * inv_cell)
           double rx0 = lox + (cx - 1e-6) * cell, rx1 = lox + (cx + 1.000001) * cell;
           double ry0 = loy + (cy - 1e-6) * cell, ry1 = loy + (cy + 1.000001) * cell;
-          double dx = std::max(std::max(rx0 - ox, ox - rx1), 0.0);
-          double dy = std::max(std::max(ry0 - oy, oy - ry1), 0.0);
-          if (dx * dx + dy * dy > r * r) continue;
+          double d = seg ? rect_segment_dist(rx0, ry0, rx1, ry1, seg[0], seg[1], seg[2], seg[3])
+                         : rect_segment_dist(rx0, ry0, rx1, ry1, bx0 + r, by0 + r, bx0 + r, by0 + r);
+          if (d > r) continue;
           int c = cx * G.ny + cy;
           if (pass == 0) off[c + 1]++;
-          else idx[cur[c]++] = (uint16_t)i;
+          else idx[cur[c]++] = entry;
         }
+    };
+    for (size_t j = 0; j < ne; j++) {
+      double seg[4] = {eax[j], eay[j], ebx[j], eby[j]};
+      visit(std::min(eax[j], ebx[j]) - pad, std::min(eay[j], eby[j]) - pad,
+            std::max(eax[j], ebx[j]) + pad, std::max(eay[j], eby[j]) + pad, (int)j, pad, seg);
+    }
+    for (size_t k = 0; k < nb; k++) {
+      int o = ball[k];
+      visit(S->h_o_ox[o] - reach[k], S->h_o_oy[o] - reach[k], S->h_o_ox[o] + reach[k],
+            S->h_o_oy[o] + reach[k], (int)(ne + k), reach[k], nullptr);
     }
     if (pass == 0) {
       for (int c = 0; c < ncell; c++) off[c + 1] += off[c];
@@ -244,13 +388,20 @@ static int ensure_obstacle_grid(Store *S, double robot_radius, cudaStream_t st) 
     }
   }
   DRRT_CUDA(cudaStreamSynchronize(st));
-  DRRT_CHECK(S->og_off.reserve(off.size(), st));
-  DRRT_CHECK(S->og_idx.reserve(idx.size(), st));
-  DRRT_CUDA(cudaMemcpyAsync(S->og_off.p, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  DRRT_CUDA(cudaMemcpyAsync(S->og_idx.p, idx.data(), idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  auto up = [&](auto &buf, const auto &v) -> int {
+    DRRT_CHECK(buf.reserve(v.size() + 1, st));
+    if (!v.empty())
+      DRRT_CUDA(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, st));
+    return DRRT_OK;
+  };
+  DRRT_CHECK(up(S->og_off, off)); DRRT_CHECK(up(S->og_idx, idx));
+  DRRT_CHECK(up(S->og_eax, eax)); DRRT_CHECK(up(S->og_eay, eay));
+  DRRT_CHECK(up(S->og_ebx, ebx)); DRRT_CHECK(up(S->og_eby, eby));
+  DRRT_CHECK(up(S->og_eobs, eobs)); DRRT_CHECK(up(S->og_ball, ball));
   DRRT_CUDA(cudaStreamSynchronize(st));
-  G.off = S->og_off.p;
-  G.idx = S->og_idx.p;
+  G.off = S->og_off.p; G.idx = S->og_idx.p;
+  G.eax = S->og_eax.p; G.eay = S->og_eay.p; G.ebx = S->og_ebx.p; G.eby = S->og_eby.p;
+  G.eobs = S->og_eobs.p; G.ball = S->og_ball.p;
   S->ogrid = G;
   S->ogrid_radius = robot_radius;
   return DRRT_OK;
@@ -291,13 +442,36 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   }
   static bool attr_done = false;
   if (!attr_done) {
-    DRRT_CUDA(cudaFuncSetAttribute(edgecheck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DRRT_CUDA(cudaFuncSetAttribute(dubins_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   96 * 1024));
+    DRRT_CUDA(cudaFuncSetAttribute(linecheck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    96 * 1024));
     attr_done = true;
   }
   unsigned nb = (unsigned)((n + EDGE_T - 1) / EDGE_T);
-  edgecheck_kernel<<<nb, EDGE_T, smem, st>>>(A);
-  DRRT_LAUNCHED();
+  if (edge_kind == DRRT_EDGE_STRAIGHT) {
+    linecheck_kernel<<<nb, EDGE_T, smem, st>>>(A);
+    DRRT_LAUNCHED();
+  } else {
+    if (st != S->stream) DRRT_CUDA(cudaStreamSynchronize(S->stream));
+    DRRT_CHECK(S->edge_paths.reserve((size_t)n * sizeof(DubinsPath), st));
+    DubinsPath *paths = reinterpret_cast<DubinsPath *>(S->edge_paths.p);
+    dubins_solve_kernel<<<nb, EDGE_T, 0, st>>>(A, paths);
+    DRRT_LAUNCHED();
+    if (A.obs.n == 0) {
+      DRRT_CUDA(cudaMemsetAsync(verdict_dev, 0, (size_t)n, st));  // nothing to collide with
+    } else {
+      DRRT_CUDA(cudaMemsetAsync(S->d_edge_counter, 0, sizeof(unsigned long long), st));
+      // persistent grid: enough CTAs to fill the machine, lanes pull edges until none are left
+      int per_sm = 0;
+      DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dubins_walk_kernel, EDGE_T, smem));
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
+      unsigned grid = (unsigned)std::min<int64_t>(nb, (int64_t)std::max(per_sm, 1) * sms);
+      dubins_walk_kernel<<<grid, EDGE_T, smem, st>>>(A, paths, S->d_edge_counter);
+      DRRT_LAUNCHED();
+    }
+  }
   DRRT_CUDA(cudaGetLastError());
   return DRRT_OK;
 }

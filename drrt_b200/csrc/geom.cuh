@@ -121,22 +121,25 @@ enum { TRAJ_XXX = 0, TRAJ_RSL, TRAJ_RSR, TRAJ_RLR, TRAJ_LSR, TRAJ_LSL, TRAJ_LRL,
 enum { PART_NONE = 0, PART_ARC_R = 1, PART_ARC_L = 2, PART_LINE = 3 };
 
 struct DubinsPart {
-  int kind;
   double cx, cy;  // arc centre            | line: first point
   double a, b;    // arc phi_start/phi_end | line: second point
 };
 
-struct DubinsPath {
-  int type;
+// 112 bytes; also the record the solve kernel hands to the walk kernel
+struct __align__(16) DubinsPath {
   double dist;  // edge->dist_ (dubinsedge.cpp:808; INF when no candidate exists)
+  int type;
+  int kinds;    // part kinds, 2 bits each
   DubinsPart part[3];
+  __host__ __device__ __forceinline__ int kind(int k) const { return (kinds >> (2 * k)) & 3; }
 };
 
 __device__ __forceinline__ double len2(double dx, double dy) { return sqrt(dx * dx + dy * dy); }
 
-__device__ __forceinline__ void arc_part(DubinsPart &P, int kind, double cx, double cy, double fx,
-                                         double fy, double tx, double ty) {
-  P.kind = kind;
+__device__ __forceinline__ void arc_part(DubinsPath &out, int k, int kind, double cx, double cy,
+                                         double fx, double fy, double tx, double ty) {
+  DubinsPart &P = out.part[k];
+  out.kinds |= kind << (2 * k);
   P.cx = cx;
   P.cy = cy;
   P.a = atan2(fy - cy, fx - cx);
@@ -259,41 +262,41 @@ __device__ void dubins_solve(double sx, double sy, double st, double ex, double 
 
   out.type = type;
   out.dist = best;
-  DubinsPart &P0 = out.part[0], &P1 = out.part[1], &P2 = out.part[2];
-  P0.kind = P1.kind = P2.kind = PART_NONE;
+  out.kinds = 0;
+  DubinsPart &P1 = out.part[1];
   switch (type) {  // :467-723
     case TRAJ_RSL:
-      arc_part(P0, PART_ARC_R, ircx, ircy, sx, sy, rsl_x0, rsl_y0);
-      P1.kind = PART_LINE; P1.cx = rsl_x0; P1.cy = rsl_y0; P1.a = rsl_x1; P1.b = rsl_y1;
-      arc_part(P2, PART_ARC_L, glcx, glcy, rsl_x1, rsl_y1, ex, ey);
+      arc_part(out, 0, PART_ARC_R, ircx, ircy, sx, sy, rsl_x0, rsl_y0);
+      out.kinds |= PART_LINE << 2; P1.cx = rsl_x0; P1.cy = rsl_y0; P1.a = rsl_x1; P1.b = rsl_y1;
+      arc_part(out, 2, PART_ARC_L, glcx, glcy, rsl_x1, rsl_y1, ex, ey);
       break;
     case TRAJ_RSR:
-      arc_part(P0, PART_ARC_R, ircx, ircy, sx, sy, rsr_x0, rsr_y0);
-      P1.kind = PART_LINE; P1.cx = rsr_x0; P1.cy = rsr_y0; P1.a = rsr_x1; P1.b = rsr_y1;
-      arc_part(P2, PART_ARC_R, grcx, grcy, rsr_x1, rsr_y1, ex, ey);
+      arc_part(out, 0, PART_ARC_R, ircx, ircy, sx, sy, rsr_x0, rsr_y0);
+      out.kinds |= PART_LINE << 2; P1.cx = rsr_x0; P1.cy = rsr_y0; P1.a = rsr_x1; P1.b = rsr_y1;
+      arc_part(out, 2, PART_ARC_R, grcx, grcy, rsr_x1, rsr_y1, ex, ey);
       break;
     case TRAJ_RLR:
-      arc_part(P0, PART_ARC_R, ircx, ircy, sx, sy, rlr_rlx, rlr_rly);
-      arc_part(P1, PART_ARC_L, rlr_cx, rlr_cy, rlr_rlx, rlr_rly, rlr_lrx, rlr_lry);
-      arc_part(P2, PART_ARC_R, grcx, grcy, rlr_lrx, rlr_lry, ex, ey);
+      arc_part(out, 0, PART_ARC_R, ircx, ircy, sx, sy, rlr_rlx, rlr_rly);
+      arc_part(out, 1, PART_ARC_L, rlr_cx, rlr_cy, rlr_rlx, rlr_rly, rlr_lrx, rlr_lry);
+      arc_part(out, 2, PART_ARC_R, grcx, grcy, rlr_lrx, rlr_lry, ex, ey);
       break;
     case TRAJ_LSR:
-      arc_part(P0, PART_ARC_L, ilcx, ilcy, sx, sy, lsr_x0, lsr_y0);
-      P1.kind = PART_LINE; P1.cx = lsr_x0; P1.cy = lsr_y0; P1.a = lsr_x1; P1.b = lsr_y1;
-      arc_part(P2, PART_ARC_R, grcx, grcy, lsr_x1, lsr_y1, ex, ey);
+      arc_part(out, 0, PART_ARC_L, ilcx, ilcy, sx, sy, lsr_x0, lsr_y0);
+      out.kinds |= PART_LINE << 2; P1.cx = lsr_x0; P1.cy = lsr_y0; P1.a = lsr_x1; P1.b = lsr_y1;
+      arc_part(out, 2, PART_ARC_R, grcx, grcy, lsr_x1, lsr_y1, ex, ey);
       break;
     case TRAJ_LSL:
-      arc_part(P0, PART_ARC_L, ilcx, ilcy, sx, sy, lsl_x0, lsl_y0);
-      P1.kind = PART_LINE; P1.cx = lsl_x0; P1.cy = lsl_y0; P1.a = lsl_x1; P1.b = lsl_y1;
-      arc_part(P2, PART_ARC_L, glcx, glcy, lsl_x1, lsl_y1, ex, ey);
+      arc_part(out, 0, PART_ARC_L, ilcx, ilcy, sx, sy, lsl_x0, lsl_y0);
+      out.kinds |= PART_LINE << 2; P1.cx = lsl_x0; P1.cy = lsl_y0; P1.a = lsl_x1; P1.b = lsl_y1;
+      arc_part(out, 2, PART_ARC_L, glcx, glcy, lsl_x1, lsl_y1, ex, ey);
       break;
     case TRAJ_LRL:
-      arc_part(P0, PART_ARC_L, ilcx, ilcy, sx, sy, lrl_lrx, lrl_lry);
-      arc_part(P1, PART_ARC_R, lrl_cx, lrl_cy, lrl_lrx, lrl_lry, lrl_rlx, lrl_rly);
-      arc_part(P2, PART_ARC_L, glcx, glcy, lrl_rlx, lrl_rly, ex, ey);
+      arc_part(out, 0, PART_ARC_L, ilcx, ilcy, sx, sy, lrl_lrx, lrl_lry);
+      arc_part(out, 1, PART_ARC_R, lrl_cx, lrl_cy, lrl_lrx, lrl_lry, lrl_rlx, lrl_rly);
+      arc_part(out, 2, PART_ARC_L, glcx, glcy, lrl_rlx, lrl_rly, ex, ey);
       break;
     case TRAJ_0S0:
-      P1.kind = PART_LINE; P1.cx = sx; P1.cy = sy; P1.a = ex; P1.b = ey;
+      out.kinds |= PART_LINE << 2; P1.cx = sx; P1.cy = sy; P1.a = ex; P1.b = ey;
       break;
     default:
       break;
@@ -303,26 +306,30 @@ __device__ void dubins_solve(double sx, double sy, double st, double ex, double 
 // Walks the polyline of a solved path point by point, in the order
 // CalculateTrajectory stores it (:484-502 and siblings; :577-583).
 struct PolylineWalker {
-  const DubinsPath *path;
+  const DubinsPath *path;  // local or global
   double r_min;
   int part;       // current part, 3 = done
   int i, n;       // index / count within the part
+  int kind;       // current part's kind and fields, cached in registers
+  double cx, cy, a, b;
   double val, phi_end;
   bool ended, equal;
 
   __device__ __forceinline__ void begin_part() {
     while (part < 3) {
-      const DubinsPart &P = path->part[part];
-      if (P.kind == PART_LINE) { n = 2; i = 0; return; }
-      if (P.kind == PART_ARC_R || P.kind == PART_ARC_L) {
-        double pe = P.b;
-        if (P.kind == PART_ARC_R) { if (pe > P.a) pe -= 2.0 * DRRT_PI; }
-        else { if (pe < P.a) pe += 2.0 * DRRT_PI; }
+      kind = path->kind(part);
+      if (kind != PART_NONE) {
+        const DubinsPart &P = path->part[part];
+        cx = P.cx; cy = P.cy; a = P.a; b = P.b;
+        if (kind == PART_LINE) { n = 2; i = 0; return; }
+        double pe = b;
+        if (kind == PART_ARC_R) { if (pe > a) pe -= 2.0 * DRRT_PI; }
+        else { if (pe < a) pe += 2.0 * DRRT_PI; }
         phi_end = pe;
-        n = (int)(ceil(fabs(pe - P.a) / 0.1) + 1);
+        n = (int)(ceil(fabs(pe - a) / 0.1) + 1);
         if (n > DRRT_TRAJ_MAX) n = DRRT_TRAJ_MAX;
-        equal = (pe == P.a);
-        val = P.a;
+        equal = (pe == a);
+        val = a;
         ended = false;
         i = 0;
         if (n > 0) return;
@@ -331,29 +338,29 @@ struct PolylineWalker {
     }
   }
   __device__ __forceinline__ void start(const DubinsPath *p, double r) {
-    path = p; r_min = r; part = 0; i = 0; n = 0;
+    path = p; r_min = r; part = 0; i = 0; n = 0; kind = PART_NONE;
     begin_part();
   }
+  __device__ __forceinline__ bool done() const { return part >= 3; }
   __device__ __forceinline__ bool next(double *x, double *y) {
     if (part >= 3) return false;
-    const DubinsPart &P = path->part[part];
-    if (P.kind == PART_LINE) {
-      if (i == 0) { *x = P.cx; *y = P.cy; } else { *x = P.a; *y = P.b; }
+    if (kind == PART_LINE) {
+      if (i == 0) { *x = cx; *y = cy; } else { *x = a; *y = b; }
     } else {
       double phi;
       if (equal) {
-        phi = (i == 0) ? P.a : 0.0;
+        phi = (i == 0) ? a : 0.0;
       } else if (!ended) {
-        bool in = (P.kind == PART_ARC_R) ? (val >= phi_end) : (val <= phi_end);
-        if (in) { phi = val; if (P.kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
+        bool in = (kind == PART_ARC_R) ? (val >= phi_end) : (val <= phi_end);
+        if (in) { phi = val; if (kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
         else { phi = phi_end; ended = true; }
       } else {
         phi = 0.0;  // entries the reference's loop never reaches stay Zero()
       }
       double sn, cs;
       sincos(phi, &sn, &cs);
-      *x = P.cx + r_min * cs;
-      *y = P.cy + r_min * sn;
+      *x = cx + r_min * cs;
+      *y = cy + r_min * sn;
     }
     i++;
     if (i >= n) { part++; begin_part(); }

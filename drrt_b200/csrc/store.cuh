@@ -88,11 +88,15 @@ struct Store {
   // broadphase over the active obstacles: uniform grid, cell -> obstacles whose
   // reach circle (radius_ + robot radius) touches the cell; rebuilt when the
   // table or the robot radius changes
-  std::vector<double> h_o_ox, h_o_oy, h_o_rad;
+  std::vector<double> h_o_ox, h_o_oy, h_o_rad, h_o_vx, h_o_vy;
+  std::vector<int32_t> h_o_kind, h_o_voff;
   ObstacleGrid ogrid{};
   double ogrid_radius = -1.0;
-  DevBuf<int32_t> og_off;
-  DevBuf<uint16_t> og_idx;
+  DevBuf<int32_t> og_off, og_idx, og_eobs, og_ball;
+  DevBuf<double> og_eax, og_eay, og_ebx, og_eby;
+  // solved Dubins paths handed from the solve kernel to the walk kernel
+  DevBuf<unsigned char> edge_paths;
+  unsigned long long *d_edge_counter = nullptr;
 };
 
 // store.cu

@@ -30,6 +30,23 @@ def _dev_ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class _DevView:
+    """__cuda_array_interface__ wrapper so torch can adopt a library-owned device buffer"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+def dev_tensor(ptr, n, typestr):
+    """torch view (no copy) of n items at device pointer ptr; typestr e.g. '<i4', '<i8', '<f8'"""
+    import torch
+    if n == 0:
+        return torch.empty(0, dtype={"<i4": torch.int32, "<i8": torch.int64, "<f8": torch.float64}[typestr],
+                           device="cuda")
+    return torch.as_tensor(_DevView(ptr, n, typestr), device="cuda")
+
+
 def _torch_stream():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -142,6 +159,13 @@ class KDTree:
         check(self._lib.drrt_range_batch_dev(self._h, q.shape[0], _dev_ptr(q), _dev_ptr(rad_t),
                                              r_all, _torch_stream(), C.byref(res)))
         return res
+
+    @staticmethod
+    def range_result_tensors(res):
+        """(offsets int64[nq+1], ids int32[total], dist f64[total]) as torch views of the
+        library-owned result of the last KDFindWithinRange_dev"""
+        return (dev_tensor(res.offsets_dev, res.nq + 1, "<i8"), dev_tensor(res.ids_dev, res.total, "<i4"),
+                dev_tensor(res.dist_dev, res.total, "<f8"))
 
     # -- KDTree::KDFindNearest kdtree.cpp:264-307
     def KDFindNearest(self, query_points):
