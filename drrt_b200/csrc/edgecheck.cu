@@ -121,6 +121,111 @@ __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const Obs
   return false;
 }
 
+// Per-warp scratch of the cooperative segment test.
+struct WarpScratch {
+  double seg[32][5];   // p0x p0y p1x p1y far2 of each lane's segment
+  int start[32][4];    // up to four grid cells per segment: entry range start / length
+  int len[32][4];
+  int pre[33];         // exclusive prefix of the lanes' entry counts
+  unsigned hit;
+};
+
+// one grid entry (polygon edge or ball) against one segment: the reference's tests verbatim
+__device__ __forceinline__ bool entry_hits(const ObsView &O, const ObstacleGrid &G, int j,
+                                           const double *sg, double radius) {
+  if (j >= G.n_edges)  // ball: obstacle.cpp:781
+    return within_reach(O, G.ball[j - G.n_edges], sg[0], sg[1], sg[2], sg[3], radius);
+  double ax = G.eax[j], ay = G.eay[j], bx = G.ebx[j], by = G.eby[j];
+  // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
+  if (dist_sqrd_point_segment(sg[0], sg[1], ax, ay, bx, by) > sg[4]) return false;
+  return segment_dist_sqrd(sg[0], sg[1], sg[2], sg[3], ax, ay, bx, by) < radius * radius &&  // :796-803
+         within_reach(O, G.eobs[j], sg[0], sg[1], sg[2], sg[3], radius);                     // :765-779
+}
+
+// Warp-cooperative ExplicitEdgeCheck2D: every lane brings (at most) one polyline
+// segment; the (segment, grid entry) pairs of the whole warp are flattened so
+// that all 32 lanes test pairs, whichever lane's segment they belong to.  Most
+// segments meet no entry at all and a few meet several, so a per-lane loop runs
+// at ~2 active lanes; this keeps them all busy.  Returns whether the calling
+// lane's own segment collides.  All 32 lanes must call.
+__device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid &G, bool test,
+                                           double p0x, double p0y, double p1x, double p1y,
+                                           double radius, WarpScratch *ws, int lane) {
+  if (G.nx == 0)  // no grid (degenerate table): per-lane loop over all obstacles
+    return test && segment_vs_obstacles(O, G, p0x, p0y, p1x, p1y, radius);
+  double lox = fmin(p0x, p1x), hix = fmax(p0x, p1x), loy = fmin(p0y, p1y), hiy = fmax(p0y, p1y);
+  int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;  // empty
+  if (test && lox <= hix && loy <= hiy) {
+    double fx0 = floor((lox - G.x0) * G.inv_cell), fx1 = floor((hix - G.x0) * G.inv_cell);
+    double fy0 = floor((loy - G.y0) * G.inv_cell), fy1 = floor((hiy - G.y0) * G.inv_cell);
+    if (!(fx1 < 0.0 || fy1 < 0.0 || fx0 > (double)(G.nx - 1) || fy0 > (double)(G.ny - 1))) {
+      cx0 = (int)fmax(fx0, 0.0); cx1 = (int)fmin(fx1, (double)(G.nx - 1));
+      cy0 = (int)fmax(fy0, 0.0); cy1 = (int)fmin(fy1, (double)(G.ny - 1));
+    }
+  }
+  const int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
+  const int ncells = (ncx > 0 && ncy > 0) ? ncx * ncy : 0;
+  const bool wide = ncells > 4;  // long straight piece: handled by the whole warp below
+  int total = 0, st[4], ln[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    st[k] = 0; ln[k] = 0;
+    if (!wide && k < ncells) {
+      int c = (cx0 + k / ncy) * G.ny + (cy0 + k % ncy);
+      st[k] = G.off[c];
+      ln[k] = G.off[c + 1] - st[k];
+    }
+    total += ln[k];
+  }
+  // most segments run through empty cells: nothing to do for the whole warp
+  if (!__any_sync(0xffffffffu, total > 0 || wide)) return false;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { ws->start[lane][k] = st[k]; ws->len[lane][k] = ln[k]; }
+  double dx = p1x - p0x, dy = p1y - p0y;
+  double far = (radius + sqrt(dx * dx + dy * dy)) * (1.0 + 1e-9) + 1e-9;
+  ws->seg[lane][0] = p0x; ws->seg[lane][1] = p0y; ws->seg[lane][2] = p1x; ws->seg[lane][3] = p1y;
+  ws->seg[lane][4] = far * far;
+  int inc = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  ws->pre[lane + 1] = inc;
+  if (lane == 0) { ws->pre[0] = 0; ws->hit = 0; }
+  __syncwarp();
+  const int all = ws->pre[32];
+  for (int p = lane; p < all; p += 32) {
+    int lo = 0, hi = 32;  // owner = last lane with pre[owner] <= p
+#pragma unroll
+    for (int step = 0; step < 5; step++) {
+      int mid = (lo + hi) >> 1;
+      if (ws->pre[mid] <= p) lo = mid; else hi = mid;
+    }
+    int q = p - ws->pre[lo], k = 0;
+    while (q >= ws->len[lo][k]) { q -= ws->len[lo][k]; k++; }
+    if (entry_hits(O, G, G.idx[ws->start[lo][k] + q], ws->seg[lo], radius)) atomicOr(&ws->hit, 1u << lo);
+  }
+  // segments spanning many cells: one at a time, the warp sweeps its cells
+  unsigned wmask = __ballot_sync(0xffffffffu, wide);
+  while (wmask) {
+    int L = __ffs(wmask) - 1;
+    wmask &= wmask - 1;
+    int wx0 = __shfl_sync(0xffffffffu, cx0, L), wy0 = __shfl_sync(0xffffffffu, cy0, L);
+    int wny = __shfl_sync(0xffffffffu, ncy, L), wn = __shfl_sync(0xffffffffu, ncells, L);
+    bool h = false;
+    for (int k = lane; k < wn && !h; k += 32) {
+      int c = (wx0 + k / wny) * G.ny + (wy0 + k % wny);
+      for (int e = G.off[c]; e < G.off[c + 1] && !h; e++) h = entry_hits(O, G, G.idx[e], ws->seg[L], radius);
+    }
+    if (__any_sync(0xffffffffu, h) && lane == 0) atomicOr(&ws->hit, 1u << L);
+  }
+  __syncwarp();
+  bool mine = (ws->hit >> lane) & 1u;
+  __syncwarp();  // the scratch is reused by the next call
+  return mine;
+}
+
 struct EdgeArgs {
   int64_t n;
   const double *start, *end;        // n x 3, or null when ids are given
@@ -166,6 +271,20 @@ __device__ __forceinline__ void stage_obstacles(ObsView &O, unsigned char *smem)
   O.kind = s_kind; O.voff = s_voff;
 }
 
+// no grid entry (polygon edge or ball within the robot radius) in any cell touching the box
+__device__ __forceinline__ bool region_empty(const ObstacleGrid &G, double lox, double loy,
+                                             double hix, double hiy) {
+  if (G.nx == 0 || !(lox <= hix) || !(loy <= hiy)) return false;
+  double fx0 = floor((lox - G.x0) * G.inv_cell), fx1 = floor((hix - G.x0) * G.inv_cell);
+  double fy0 = floor((loy - G.y0) * G.inv_cell), fy1 = floor((hiy - G.y0) * G.inv_cell);
+  if (fx1 < 0.0 || fy1 < 0.0 || fx0 > (double)(G.nx - 1) || fy0 > (double)(G.ny - 1)) return true;
+  int cx0 = (int)fmax(fx0, 0.0), cx1 = (int)fmin(fx1, (double)(G.nx - 1));
+  int cy0 = (int)fmax(fy0, 0.0), cy1 = (int)fmin(fy1, (double)(G.ny - 1));
+  for (int cx = cx0; cx <= cx1; cx++)  // a row's cells are consecutive in the CSR
+    if (G.off[cx * G.ny + cy1 + 1] != G.off[cx * G.ny + cy0]) return false;
+  return true;
+}
+
 // K4a: Edge::NewEdge + the candidate solve of CalculateTrajectory, one thread per edge
 __global__ void __launch_bounds__(EDGE_T)
 dubins_solve_kernel(EdgeArgs A, DubinsPath *paths) {
@@ -177,6 +296,23 @@ dubins_solve_kernel(EdgeArgs A, DubinsPath *paths) {
   DubinsPath P;
   double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
   dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
+  if (A.obs.n > 0 && A.grid.nx > 0) {
+    // parts whose whole circle (or straight piece) lies where no obstacle comes within the
+    // robot radius need no per-segment test; a path made only of such parts is free
+    int idle = 0, parts = 0;
+    const double rr = fabs(A.r_min) * (1.0 + 1e-9) + 1e-9;
+    for (int k = 0; k < 3; k++) {
+      int kind = P.kind(k);
+      if (kind == PART_NONE) continue;
+      parts++;
+      const DubinsPart &p = P.part[k];
+      bool empty = (kind == PART_LINE)
+                       ? region_empty(A.grid, fmin(p.cx, p.a), fmin(p.cy, p.b), fmax(p.cx, p.a), fmax(p.cy, p.b))
+                       : region_empty(A.grid, p.cx - rr, p.cy - rr, p.cx + rr, p.cy + rr);
+      if (empty) { idle++; P.kinds |= 1 << (8 + k); }
+    }
+    if (idle == parts) P.kinds = 0;  // the walk kernel reports it free without walking
+  }
   paths[e] = P;
   if (A.length) A.length[e] = P.dist;
 }
@@ -188,6 +324,8 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
   ObsView O = A.obs;
   if (A.obs_smem && O.n > 0) stage_obstacles(O, smem_raw);
   const int lane = threadIdx.x & 31;
+  __shared__ WarpScratch s_ws[EDGE_T / 32];
+  WarpScratch *ws = &s_ws[threadIdx.x >> 5];
   PolylineWalker W;
   W.part = 3;
   long long e = -1;       // edge this lane is walking
@@ -208,29 +346,29 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
           exhausted = true;
         } else {
           e = mine;
-          W.start(paths + e, A.r_min);
+          W.start(paths + e, A.r_min, true);
           have_prev = false;
         }
       }
     }
     if (__all_sync(0xffffffffu, e < 0)) break;
+    // every lane advances its polyline by one point; the new segments are tested together
+    double cx = 0.0, cy = 0.0;
+    bool ended = false, test = false;
     if (e >= 0) {
-      double cx, cy;
-      bool decided = false, hit = false;
-      if (!W.next(&cx, &cy)) {
-        decided = true;  // end of path, no segment collided (dubinsedge.cpp:897)
+      bool connects = false;
+      if (!W.next(&cx, &cy, &connects)) ended = true;  // end of path, nothing collided (dubinsedge.cpp:897)
+      else test = have_prev && connects;
+    }
+    bool hit = warp_segments_vs_obstacles(O, A.grid, test, px, py, cx, cy, A.robot_radius, ws, lane);
+    if (e >= 0) {
+      if (ended || hit) {  // :878-889 first hit decides the edge
+        A.verdict[e] = hit ? 1 : 0;
+        e = -1;
       } else {
-        if (have_prev && segment_vs_obstacles(O, A.grid, px, py, cx, cy, A.robot_radius)) {
-          decided = true;  // :878-889 first hit
-          hit = true;
-        }
         px = cx;
         py = cy;
         have_prev = true;
-      }
-      if (decided) {
-        A.verdict[e] = hit ? 1 : 0;
-        e = -1;
       }
     }
   }
@@ -242,11 +380,16 @@ linecheck_kernel(EdgeArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ObsView O = A.obs;
   if (A.obs_smem && O.n > 0) stage_obstacles(O, smem_raw);
+  __shared__ WarpScratch s_ws[EDGE_T / 32];
+  WarpScratch *ws = &s_ws[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
-  if (e >= A.n) return;
-  double sx, sy, st, ex, ey, et;
-  load_pose(A, e, false, sx, sy, st);
-  load_pose(A, e, true, ex, ey, et);
+  const bool live = e < A.n;
+  double sx = 0, sy = 0, st = 0, ex = 0, ey = 0, et = 0;
+  if (live) {
+    load_pose(A, e, false, sx, sy, st);
+    load_pose(A, e, true, ex, ey, et);
+  }
   bool hit = false;
   double th = atan2(ey - sy, ex - sx);
   double dist = metric_dist(A.metric, sx, sy, th, ex, ey, th);
@@ -258,13 +401,18 @@ linecheck_kernel(EdgeArgs A) {
     for (int i = 0; i < 50; i++) {
       if (ex > sx) x_val += x_dist / traj_length; else x_val -= x_dist / traj_length;
       if (ey > sy) y_val += y_dist / traj_length; else y_val -= y_dist / traj_length;
-      if (segment_vs_obstacles(O, A.grid, px, py, x_val, y_val, A.robot_radius)) { hit = true; break; }
+      bool h = warp_segments_vs_obstacles(O, A.grid, live && !hit, px, py, x_val, y_val,
+                                          A.robot_radius, ws, lane);
+      hit = hit || h;
+      if (__all_sync(0xffffffffu, hit || !live)) break;
       px = x_val;
       py = y_val;
     }
   }
-  A.verdict[e] = hit ? 1 : 0;
-  if (A.length) A.length[e] = dist;
+  if (live) {
+    A.verdict[e] = hit ? 1 : 0;
+    if (A.length) A.length[e] = dist;
+  }
 }
 
 // distance from an axis-aligned rectangle to a segment (0 when they touch)

@@ -132,6 +132,8 @@ struct __align__(16) DubinsPath {
   int kinds;    // part kinds, 2 bits each
   DubinsPart part[3];
   __host__ __device__ __forceinline__ int kind(int k) const { return (kinds >> (2 * k)) & 3; }
+  // bit 8+k set: no obstacle comes near part k (edge check only); its segments need no test
+  __host__ __device__ __forceinline__ bool idle(int k) const { return (kinds >> (8 + k)) & 1; }
 };
 
 __device__ __forceinline__ double len2(double dx, double dy) { return sqrt(dx * dx + dy * dy); }
@@ -314,6 +316,8 @@ struct PolylineWalker {
   double cx, cy, a, b;
   double val, phi_end;
   bool ended, equal;
+  bool skip_idle;  // fast-forward parts flagged idle to their last point
+  bool fresh;      // the next point does not continue a tested polyline segment
 
   __device__ __forceinline__ void begin_part() {
     while (part < 3) {
@@ -337,13 +341,16 @@ struct PolylineWalker {
       part++;
     }
   }
-  __device__ __forceinline__ void start(const DubinsPath *p, double r) {
-    path = p; r_min = r; part = 0; i = 0; n = 0; kind = PART_NONE;
+  __device__ __forceinline__ void start(const DubinsPath *p, double r, bool skip = false) {
+    path = p; r_min = r; part = 0; i = 0; n = 0; kind = PART_NONE; fresh = true; skip_idle = skip;
     begin_part();
   }
   __device__ __forceinline__ bool done() const { return part >= 3; }
-  __device__ __forceinline__ bool next(double *x, double *y) {
+  // *connects: the segment from the previous point to this one is part of the polyline to test
+  __device__ __forceinline__ bool next(double *x, double *y, bool *connects = nullptr) {
     if (part >= 3) return false;
+    if (connects) *connects = !fresh;
+    fresh = false;
     if (kind == PART_LINE) {
       if (i == 0) { *x = cx; *y = cy; } else { *x = a; *y = b; }
     } else {
@@ -363,6 +370,20 @@ struct PolylineWalker {
       *y = cy + r_min * sn;
     }
     i++;
+    if (i == 1 && skip_idle && n > 2 && kind != PART_LINE && path->idle(part)) {
+      // nothing can collide inside this arc's circle: after its first point (whose
+      // segment from the previous part is still tested) run the angle recurrence
+      // without sin/cos up to the last point, which starts the next junction segment
+      if (equal) i = n - 1;
+      else
+        for (; i < n - 1; i++) {
+          if (ended) continue;
+          bool in = (kind == PART_ARC_R) ? (val >= phi_end) : (val <= phi_end);
+          if (in) { if (kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
+          else ended = true;
+        }
+      fresh = true;
+    }
     if (i >= n) { part++; begin_part(); }
     return true;
   }
