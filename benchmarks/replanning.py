@@ -25,19 +25,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--nodes", type=int, default=2_000_000)
-    ap.add_argument("--batch", type=int, default=4096)
-    args = ap.parse_args()
+def run(nodes=2_000_000, batch=4096, device=0):
+    """grows one store on `device`; returns the result dict (torch's current stream is used)"""
+    class args:  # noqa: N801
+        pass
+    args.nodes, args.batch = nodes, batch
     import torch
     import drrt_b200
     from drrt_b200 import capi, synth
     from drrt_b200.kdtree import KDTree
 
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
-    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+    dev = torch.device("cuda", device)
+    if torch.cuda.current_stream().cuda_stream == 0:
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # the C ABI treats stream 0 as "its own"
     rng = np.random.default_rng(0xD2270004)
     pos = np.empty((args.nodes, 3))
     pos[:, 0] = rng.uniform(-50, 50, args.nodes)
@@ -45,7 +45,7 @@ def main():
     pos[:, 2] = rng.uniform(0, synth.TWO_PI, args.nodes)
     pos_t = torch.from_numpy(pos).to(dev)
     obs = synth.obstacles(256, 0xD2270003, lo=-48.0, hi=48.0)
-    tree = KDTree(device=0, capacity=args.nodes)
+    tree = KDTree(device=device, capacity=args.nodes)
     tree.SetObstacles(**obs)
     delta, gamma = 10.0, 100.0
 
@@ -77,6 +77,8 @@ def main():
                                    r_min=synth.R_MIN, length_out=length)
         e3.record()
         torch.cuda.synchronize()
+        if os.environ.get('REPLAN_DEBUG') and (b % 40 == 0 or e1.elapsed_time(e2) > 2.0):
+            print(b, 'insert %.3f range %.3f edge %.3f edges %d' % (e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), start.shape[0]), file=sys.stderr, flush=True)
         t_insert += e0.elapsed_time(e1)
         t_range += e1.elapsed_time(e2)
         t_edge += e2.elapsed_time(e3)
@@ -114,7 +116,18 @@ def main():
             "collision_rate": tot_coll / max(tot_edges, 1),
             "conflict_queries": tot_conf_q, "conflict_hits_per_query": tot_conf_hits / max(tot_conf_q, 1),
             "gpu_launches": capi.launches() - l0}
-    print(json.dumps(line), flush=True)
+    tree.close()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nodes", type=int, default=2_000_000)
+    ap.add_argument("--batch", type=int, default=4096)
+    a = ap.parse_args()
+    import torch
+    torch.cuda.set_device(0)
+    print(json.dumps(run(a.nodes, a.batch)), flush=True)
 
 
 if __name__ == "__main__":

@@ -190,8 +190,16 @@ int drrt_store_create(int device, int dims, int n_wraps, const int *wrap_dims,
     return set_error(DRRT_ERR_CUDA, "create: %s", cudaGetErrorString(e));
   }
   if (capacity_hint > 0) {
+    // everything that scales with the node count, so a store grown to the hint never
+    // reallocates (cudaMalloc/cudaFree stall the device for milliseconds)
     int rc = store_reserve_nodes(S, capacity_hint);
-    if (rc != DRRT_OK) { delete S; return rc; }
+    cudaStream_t st = S->stream;
+    if (rc == DRRT_OK) rc = S->rec.reserve(capacity_hint, st);
+    if (rc == DRRT_OK) rc = S->cell_of.reserve(capacity_hint, st);
+    if (rc == DRRT_OK) rc = S->rank_in_cell.reserve(capacity_hint, st);
+    if (rc == DRRT_OK) rc = S->cell_start.reserve(capacity_hint + 4096, st);
+    if (rc == DRRT_OK) rc = S->scan_tmp.reserve(capacity_hint / 1024 + 4096, st);
+    if (rc != DRRT_OK) { drrt_store_destroy(reinterpret_cast<drrt_store *>(S)); return rc; }
   }
   *out = reinterpret_cast<drrt_store *>(S);
   return DRRT_OK;

@@ -131,7 +131,7 @@ template <typename T>
 int DevBuf<T>::reserve(size_t n, cudaStream_t s, bool keep, size_t keep_n) {
   if (n <= cap) return DRRT_OK;
   size_t ncap = cap ? cap : 256;
-  while (ncap < n) ncap = ncap + ncap / 2 + 256;
+  while (ncap < n) ncap = 2 * ncap + 256;
   T *np = nullptr;
   cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
   if (e != cudaSuccess)
