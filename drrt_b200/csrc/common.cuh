@@ -54,6 +54,7 @@ struct __align__(32) NodeRec {
 // (ix,iy) column's theta range is one contiguous run of records.
 struct GridParams {
   double x0, y0, inv_hx, inv_hy;  // cell = floor((x - x0) * inv_h), clamped
+  double hx, hy, ht;              // cell edge lengths (1 / inv_h)
   double t0, inv_ht;              // theta key origin / inverse cell size
   double period;                  // > 0: theta key = theta mod period
   int nx, ny, nt;
@@ -135,6 +136,7 @@ __host__ __device__ __forceinline__ double metric_dist(int metric, double ax, do
 // theta bucketing key in [0, period): exact fmod, one rounded add at most
 __host__ __device__ __forceinline__ double theta_key(double th, double period) {
   if (!(period > 0.0)) return th;
+  if (th >= 0.0 && th < period) return th;  // the usual case; fmod is exact but slow
   double k = fmod(th, period);
   if (k < 0.0) k += period;
   if (k >= period) k = 0.0;

@@ -54,7 +54,7 @@ __device__ __forceinline__ int cell_floor(double v, double v0, double inv_h) {
 // periodic wrap run b = [tb0,tb1] (empty when tb0 > tb1).
 __device__ __forceinline__ void theta_runs(const GridParams &g, double key, double half, int &ta0,
                                            int &ta1, int &tb0, int &tb1) {
-  const double slack = 1e-6 / g.inv_ht;
+  const double slack = 1e-6 * g.ht;
   tb0 = 1; tb1 = 0;
   if (g.periodic) {
     if (!(2.0 * (half + slack) < g.period * (1.0 - 1e-9)) || !(key == key)) {
@@ -108,10 +108,10 @@ __device__ __forceinline__ void setup_query(const GridView &A, double qx, double
   Q.key = g.periodic ? theta_key(Q.t, g.period) : Q.t;
   theta_runs(g, Q.key, rr, Q.ta0, Q.ta1, Q.tb0, Q.tb1);
   // the ball swallows the whole indexed box: every column gets its full theta range
-  double ex = fmax(fabs(Q.x - g.x0), fabs(Q.x - (g.x0 + g.nx / g.inv_hx)));
-  double ey = fmax(fabs(Q.y - g.y0), fabs(Q.y - (g.y0 + g.ny / g.inv_hy)));
+  double ex = fmax(fabs(Q.x - g.x0), fabs(Q.x - (g.x0 + g.nx * g.hx)));
+  double ey = fmax(fabs(Q.y - g.y0), fabs(Q.y - (g.y0 + g.ny * g.hy)));
   double et = g.periodic ? 0.5 * g.period
-                         : fmax(fabs(Q.t - g.t0), fabs(Q.t - (g.t0 + g.nt / g.inv_ht)));
+                         : fmax(fabs(Q.t - g.t0), fabs(Q.t - (g.t0 + g.nt * g.ht)));
   Q.all = (ex * ex + ey * ey + et * et <= Q.r * Q.r) || !(Q.key == Q.key);
   // a narrower per-column range can wrap even when the query-wide one is the full circle
   Q.may_wrap = g.periodic && !Q.all && (Q.tb0 <= Q.tb1 || (Q.ta0 == 0 && Q.ta1 == g.nt - 1));
@@ -133,8 +133,8 @@ __device__ __forceinline__ void column_runs(const GridView &A, const Query &Q, i
   if (col >= ncol) return;
   int ix = Q.ix0 + col / ncy, iy = Q.iy0 + col % ncy;
   // closest approach of the column's footprint (edge columns are open-ended)
-  double xlo = g.x0 + ((double)ix - 1e-6) / g.inv_hx, xhi = g.x0 + ((double)ix + 1.000001) / g.inv_hx;
-  double ylo = g.y0 + ((double)iy - 1e-6) / g.inv_hy, yhi = g.y0 + ((double)iy + 1.000001) / g.inv_hy;
+  double xlo = g.x0 + ((double)ix - 1e-6) * g.hx, xhi = g.x0 + ((double)ix + 1.000001) * g.hx;
+  double ylo = g.y0 + ((double)iy - 1e-6) * g.hy, yhi = g.y0 + ((double)iy + 1.000001) * g.hy;
   double dx = 0.0, dy = 0.0;
   if (ix > 0 && Q.x < xlo) dx = xlo - Q.x;
   if (ix < g.nx - 1 && Q.x > xhi) dx = Q.x - xhi;

@@ -300,6 +300,9 @@ int rebuild_index(Store *S, cudaStream_t st) {
   gp.inv_hx = gp.nx / Lx;
   gp.inv_hy = gp.ny / Ly;
   gp.inv_ht = gp.nt / Lt;
+  gp.hx = Lx / gp.nx;
+  gp.hy = Ly / gp.ny;
+  gp.ht = Lt / gp.nt;
   const int64_t ncell = (int64_t)gp.nx * gp.ny * gp.nt;
 
   DRRT_CHECK(S->rec.reserve(n, st));
