@@ -329,6 +329,22 @@ def main():
         extra["nearest"] = {"queries_per_s": world * N_QUERIES / (ms * 1e-3), "ms_per_step": ms,
                             "roofline_frac": 60.0 * N_QUERIES / (ms * 1e-3) / 1e9 / peak}
 
+        # fused Extend (range + both Dubins edges per neighbour + best parent) on the 2b batch
+        lmc_t = torch.rand(N_NODES, dtype=torch.float64, device=dev) * 80.0
+        bp = torch.empty(N_QUERIES, dtype=torch.int32, device=dev)
+        bc = torch.empty(N_QUERIES, dtype=torch.float64, device=dev)
+
+        def step_extend():
+            state["ext"] = tree.Extend_dev(r2b, q_dev, lmc=lmc_t, best_parent=bp, best_cost=bc,
+                                           robot_radius=synth.ROBOT_RADIUS, r_min=synth.R_MIN)
+
+        ms = timed(step_extend, esteps, 3) / esteps
+        n_pairs = int(state["ext"][0].total)
+        extra["extend_2b"] = {"new_nodes_per_s": world * N_QUERIES / (ms * 1e-3), "ms_per_step": ms,
+                              "edge_checks_per_step": 2 * n_pairs,
+                              "edge_checks_per_s": world * 2 * n_pairs / (ms * 1e-3),
+                              "with_parent": float((bp >= 0).float().mean().item())}
+        del lmc_t, bp, bc
         # config 4: replanning scenario (2 M nodes grown by 4096-node batches), one store per rank
         del ids_k, dist_k, ids_1, dist_1
         from benchmarks import replanning

@@ -67,6 +67,13 @@ SIGNATURES = {
     "drrt_edgecheck_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                            C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "drrt_extend_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_double,
+                                    C.c_double, C.c_int, c_dp, c_ip, c_i64p, c_ip, c_dp]),
+    "drrt_extend_fetch": (C.c_int, [C.c_void_p, c_ip, c_dp, c_u8p, c_dp]),
+    "drrt_extend_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
+                                        C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                        C.POINTER(RangeResult), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "drrt_dubins_trajectory_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double,
                                                c_dp, c_ip, C.c_char_p, c_dp]),
     "drrt_pointcheck_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, C.c_double, C.c_double,

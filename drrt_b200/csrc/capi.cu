@@ -227,6 +227,7 @@ int drrt_store_destroy(drrt_store *h) {
     if (S->d_pending) cudaFree(S->d_pending);
     if (S->d_ticket) cudaFree(S->d_ticket);
     if (S->d_edge_counter) cudaFree(S->d_edge_counter);
+    S->x_unsafe.release(); S->x_len.release(); S->x_lmc.release(); S->x_best.release(); S->x_best_cost.release();
     S->edge_paths.release(); S->og_off.release(); S->og_idx.release(); S->og_eobs.release();
     S->og_ball.release(); S->og_eax.release(); S->og_eay.release(); S->og_ebx.release(); S->og_eby.release();
     if (S->d_bounds) cudaFree(S->d_bounds);
@@ -470,6 +471,88 @@ int drrt_edgecheck_batch_dev(drrt_store *h, int64_t n, const double *start_dev,
   ENTER(h);
   return edgecheck_batch_dev(S, n, start_dev, end_dev, start_id_dev, end_id_dev, edge_kind,
                              robot_radius, r_min, verdict_dev, length_dev, pick(S, stream));
+}
+
+int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const double *radius,
+                      double radius_all, double robot_radius, double r_min, int in_warmup,
+                      const double *lmc, int32_t *counts, int64_t *total, int32_t *best_parent,
+                      double *best_cost) {
+  ENTER(h);
+  if (nq < 0 || (nq > 0 && (!q || !counts))) return set_error(DRRT_ERR_INVALID, "extend: arguments");
+  if (best_parent && !lmc) return set_error(DRRT_ERR_INVALID, "extend: best_parent needs lmc");
+  cudaStream_t st = S->stream;
+  S->last_extend_total = -1;
+  DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
+  DRRT_CHECK(upload(q, S->q_stage.p, 3 * nq * sizeof(double), st));
+  const double *rad_dev = nullptr;
+  if (radius) {
+    DRRT_CHECK(S->rad_stage.reserve(nq + 1, st));
+    DRRT_CHECK(upload(radius, S->rad_stage.p, nq * sizeof(double), st));
+    rad_dev = S->rad_stage.p;
+  }
+  const double *lmc_dev = nullptr;
+  if (lmc && best_parent) {
+    DRRT_CHECK(S->x_lmc.reserve(S->n + 1, st));
+    DRRT_CHECK(upload(lmc, S->x_lmc.p, S->n * sizeof(double), st));
+    DRRT_CHECK(S->x_best.reserve(nq + 1, st));
+    DRRT_CHECK(S->x_best_cost.reserve(nq + 1, st));
+    lmc_dev = S->x_lmc.p;
+  }
+  drrt_range_result res{};
+  uint8_t *unsafe_dev = nullptr;
+  double *len_dev = nullptr;
+  bool saved = S->has_obstacles;
+  if (in_warmup) S->has_obstacles = false;  // obstacle.cpp:883
+  int rc = extend_batch_dev(S, nq, S->q_stage.p, rad_dev, radius_all, robot_radius, r_min, lmc_dev, st,
+                            &res, &unsafe_dev, &len_dev, lmc_dev ? S->x_best.p : nullptr,
+                            lmc_dev ? S->x_best_cost.p : nullptr);
+  S->has_obstacles = saved;
+  DRRT_CHECK(rc);
+  if (nq > 0) {
+    DRRT_CHECK(S->i_stage.reserve(nq, st));
+    counts_from_offsets<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(res.offsets_dev, nq, S->i_stage.p);
+    DRRT_LAUNCHED();
+    DRRT_CHECK(download(counts, S->i_stage.p, nq * sizeof(int32_t), st));
+    if (lmc_dev) {
+      DRRT_CHECK(download(best_parent, S->x_best.p, nq * sizeof(int32_t), st));
+      if (best_cost) DRRT_CHECK(download(best_cost, S->x_best_cost.p, nq * sizeof(double), st));
+    }
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  if (total) *total = res.total;
+  S->last_extend_total = res.total;
+  return DRRT_OK;
+}
+
+int drrt_extend_fetch(drrt_store *h, int32_t *ids, double *dist, uint8_t *unsafe, double *length) {
+  ENTER(h);
+  if (S->last_extend_total < 0) return set_error(DRRT_ERR_STATE, "fetch: no extend batch on this handle");
+  cudaStream_t st = S->stream;
+  const int64_t t = S->last_extend_total;
+  if (t > 0) {
+    if (ids) DRRT_CHECK(download(ids, S->r_ids.p, t * sizeof(int32_t), st));
+    if (dist) DRRT_CHECK(download(dist, S->r_dist.p, t * sizeof(double), st));
+    if (unsafe) DRRT_CHECK(download(unsafe, S->x_unsafe.p, 2 * t, st));
+    if (length) DRRT_CHECK(download(length, S->x_len.p, 2 * t * sizeof(double), st));
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+int drrt_extend_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, const double *radius_dev,
+                          double radius_all, double robot_radius, double r_min,
+                          const double *lmc_dev, void *stream, drrt_range_result *rows,
+                          const uint8_t **unsafe_dev, const double **length_dev,
+                          int32_t *best_parent_dev, double *best_cost_dev) {
+  ENTER(h);
+  if (nq < 0 || (nq > 0 && !q_dev) || !rows) return set_error(DRRT_ERR_INVALID, "extend: arguments");
+  uint8_t *u = nullptr;
+  double *l = nullptr;
+  DRRT_CHECK(extend_batch_dev(S, nq, q_dev, radius_dev, radius_all, robot_radius, r_min, lmc_dev,
+                              pick(S, stream), rows, &u, &l, best_parent_dev, best_cost_dev));
+  if (unsafe_dev) *unsafe_dev = u;
+  if (length_dev) *length_dev = l;
+  return DRRT_OK;
 }
 
 int drrt_dubins_trajectory_batch(drrt_store *h, int64_t n, const double *start, const double *end,

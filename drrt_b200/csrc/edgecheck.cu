@@ -231,6 +231,12 @@ struct EdgeArgs {
   const double *start, *end;        // n x 3, or null when ids are given
   const int32_t *sid, *eid;
   const double *sx, *sy, *sth;      // store SoA (ids mode)
+  // neighbour-list mode (drrt_extend_batch): edge e = 2*t + dir over the CSR rows of a range
+  // result; dir 0 = query -> neighbour (FindBestParent), dir 1 = neighbour -> query (Extend)
+  const int64_t *csr_off;
+  const int32_t *csr_ids;
+  const double *csr_q;
+  int64_t csr_nq;
   int metric;
   int edge_kind;
   double robot_radius, r_min;
@@ -243,6 +249,22 @@ struct EdgeArgs {
 
 __device__ __forceinline__ void load_pose(const EdgeArgs &A, int64_t e, bool end, double &x,
                                           double &y, double &t) {
+  if (A.csr_off) {
+    const int64_t pair = e >> 1;
+    const bool node_side = ((e & 1) != 0) != end;  // dir 0: start = query; dir 1: start = neighbour
+    if (node_side) {
+      int32_t id = A.csr_ids[pair];
+      x = A.sx[id]; y = A.sy[id]; t = A.sth[id];
+    } else {
+      int64_t lo = 0, hi = A.csr_nq;  // row with csr_off[row] <= pair < csr_off[row + 1]
+      while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (A.csr_off[mid] <= pair) lo = mid; else hi = mid;
+      }
+      x = A.csr_q[3 * lo]; y = A.csr_q[3 * lo + 1]; t = A.csr_q[3 * lo + 2];
+    }
+    return;
+  }
   const int32_t *ids = end ? A.eid : A.sid;
   if (ids) {
     int32_t id = ids[e];
@@ -568,13 +590,17 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   if (edge_kind != DRRT_EDGE_DUBINS && edge_kind != DRRT_EDGE_STRAIGHT)
     return set_error(DRRT_ERR_INVALID, "edgecheck: edge_kind");
   bool by_id = sid_dev && eid_dev;
-  if (!by_id && !(start_dev && end_dev)) return set_error(DRRT_ERR_INVALID, "edgecheck: endpoints");
+  const bool csr = S->csr_q != nullptr;  // neighbour-list mode, set by extend_batch_dev
+  if (!csr && !by_id && !(start_dev && end_dev)) return set_error(DRRT_ERR_INVALID, "edgecheck: endpoints");
   if (!verdict_dev) return set_error(DRRT_ERR_INVALID, "edgecheck: verdict");
   if (n == 0) return DRRT_OK;
   EdgeArgs A{};
   A.n = n; A.start = by_id ? nullptr : start_dev; A.end = by_id ? nullptr : end_dev;
   A.sid = by_id ? sid_dev : nullptr; A.eid = by_id ? eid_dev : nullptr;
   A.sx = S->x.p; A.sy = S->y.p; A.sth = S->th.p;
+  if (csr) {
+    A.csr_off = S->r_offsets.p; A.csr_ids = S->r_ids.p; A.csr_q = S->csr_q; A.csr_nq = S->csr_nq;
+  }
   A.metric = S->metric; A.edge_kind = edge_kind;
   A.robot_radius = robot_radius; A.r_min = r_min;
   A.obs.n = S->has_obstacles ? S->obs.n_active : 0;
@@ -621,6 +647,64 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
     }
   }
   DRRT_CUDA(cudaGetLastError());
+  return DRRT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Fused Extend step: for every neighbour of every new node both Dubins
+// edges are checked straight off the range result, and FindBestParent's argmin
+// (src/drrt.cpp:388-459: the safe new->near edge minimising near.rrt_LMC_ + edge.dist_) is
+// reduced per row on the device.
+__global__ void best_parent_kernel(int64_t nq, const int64_t *off, const int32_t *ids,
+                                   const uint8_t *unsafe, const double *len, const double *lmc,
+                                   int32_t *best, double *best_cost) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= nq) return;
+  double c = DRRT_INF;  // new_node->rrt_LMC_ = INF (drrt.cpp:391)
+  long long at = -1;
+  for (int64_t p = off[row] + lane; p < off[row + 1]; p += 32) {
+    if (unsafe[2 * p]) continue;               // :422-431
+    double v = lmc[ids[p]] + len[2 * p];       // :444-446
+    if (c > v) { c = v; at = p; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {  // ties: the neighbour listed first (smallest id)
+    double oc = __shfl_xor_sync(0xffffffffu, c, o);
+    long long oa = __shfl_xor_sync(0xffffffffu, at, o);
+    if (oa >= 0 && (at < 0 || oc < c || (oc == c && oa < at))) { c = oc; at = oa; }
+  }
+  if (lane == 0) {
+    best[row] = at >= 0 ? ids[at] : -1;
+    best_cost[row] = c;
+  }
+}
+
+int extend_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *radius_dev,
+                     double radius_all, double robot_radius, double r_min, const double *lmc_dev,
+                     cudaStream_t st, drrt_range_result *rr, uint8_t **unsafe_dev, double **len_dev,
+                     int32_t *best_dev, double *best_cost_dev) {
+  DRRT_CHECK(range_batch_dev(S, nq, q_dev, radius_dev, radius_all, st, rr));
+  const int64_t total = rr->total;
+  DRRT_CHECK(S->x_unsafe.reserve((size_t)(2 * total + 1), st));
+  DRRT_CHECK(S->x_len.reserve((size_t)(2 * total + 1), st));
+  *unsafe_dev = S->x_unsafe.p;
+  *len_dev = S->x_len.p;
+  if (total > 0) {
+    S->csr_q = q_dev;
+    S->csr_nq = nq;
+    int rc = edgecheck_batch_dev(S, 2 * total, nullptr, nullptr, nullptr, nullptr, DRRT_EDGE_DUBINS,
+                                 robot_radius, r_min, S->x_unsafe.p, S->x_len.p, st);
+    S->csr_q = nullptr;
+    DRRT_CHECK(rc);
+  }
+  if (best_dev && nq > 0) {
+    if (!lmc_dev) return set_error(DRRT_ERR_INVALID, "extend: best parent needs the lmc array");
+    best_parent_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(nq, rr->offsets_dev, rr->ids_dev,
+                                                                 S->x_unsafe.p, S->x_len.p, lmc_dev,
+                                                                 best_dev, best_cost_dev);
+    DRRT_LAUNCHED();
+    DRRT_CUDA(cudaGetLastError());
+  }
   return DRRT_OK;
 }
 

@@ -94,6 +94,14 @@ struct Store {
   double ogrid_radius = -1.0;
   DevBuf<int32_t> og_off, og_idx, og_eobs, og_ball;
   DevBuf<double> og_eax, og_eay, og_ebx, og_eby;
+  // fused Extend: per-neighbour verdicts / lengths (2 per pair), query poses of the CSR rows
+  DevBuf<uint8_t> x_unsafe;
+  DevBuf<double> x_len, x_lmc;
+  DevBuf<int32_t> x_best;
+  DevBuf<double> x_best_cost;
+  const double *csr_q = nullptr;
+  int64_t csr_nq = 0;
+  int64_t last_extend_total = -1;
   // solved Dubins paths handed from the solve kernel to the walk kernel
   DevBuf<unsigned char> edge_paths;
   unsigned long long *d_edge_counter = nullptr;
@@ -121,6 +129,10 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
                         const int32_t *sid_dev, const int32_t *eid_dev, int edge_kind,
                         double robot_radius, double r_min, uint8_t *verdict_dev,
                         double *length_dev, cudaStream_t st);
+int extend_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *radius_dev,
+                     double radius_all, double robot_radius, double r_min, const double *lmc_dev,
+                     cudaStream_t st, drrt_range_result *rr, uint8_t **unsafe_dev, double **len_dev,
+                     int32_t *best_dev, double *best_cost_dev);
 int trajectory_batch_dev(Store *S, int64_t n, const double *start_dev, const double *end_dev,
                          double r_min, double *xy_dev, int32_t *npts_dev, char *type_dev,
                          double *length_dev, cudaStream_t st);

@@ -42,7 +42,8 @@ def dev_tensor(ptr, n, typestr):
     """torch view (no copy) of n items at device pointer ptr; typestr e.g. '<i4', '<i8', '<f8'"""
     import torch
     if n == 0:
-        return torch.empty(0, dtype={"<i4": torch.int32, "<i8": torch.int64, "<f8": torch.float64}[typestr],
+        return torch.empty(0, dtype={"<i4": torch.int32, "<i8": torch.int64, "<f8": torch.float64,
+                                  "|u1": torch.uint8}[typestr],
                            device="cuda")
     return torch.as_tensor(_DevView(ptr, n, typestr), device="cuda")
 
@@ -240,6 +241,52 @@ class KDTree:
                                                  float(robot_radius), float(r_min),
                                                  _dev_ptr(verdict_out), _dev_ptr(length_out),
                                                  _torch_stream()))
+
+    # -- Extend's hot path fused (drrt.cpp:194-362): neighbours, both edges, best parent
+    def Extend(self, range_, new_points, lmc=None, robot_radius=0.5, r_min=1.0, in_warmup=False):
+        """-> dict(offsets, ids, dist, unsafe[total,2], length[total,2], best_parent, best_cost);
+        column 0 = new->near (FindBestParent), column 1 = near->new (Extend's second pass)."""
+        q = _f64(new_points, (-1, 3))
+        nq = q.shape[0]
+        rad, r_all = (None, float(range_)) if np.ndim(range_) == 0 else (_f64(range_, (nq,)), 0.0)
+        counts = np.zeros(nq, dtype=np.int32)
+        total = C.c_int64()
+        best = np.full(nq, -1, dtype=np.int32) if lmc is not None else None
+        cost = np.zeros(nq, dtype=np.float64) if lmc is not None else None
+        lm = _f64(lmc) if lmc is not None else None
+        check(self._lib.drrt_extend_batch(self._h, nq, _ptr(q, c_dp),
+                                          _ptr(rad, c_dp) if rad is not None else None, r_all,
+                                          float(robot_radius), float(r_min), int(in_warmup),
+                                          _ptr(lm, c_dp) if lm is not None else None, _ptr(counts, c_ip),
+                                          C.byref(total), _ptr(best, c_ip) if best is not None else None,
+                                          _ptr(cost, c_dp) if cost is not None else None))
+        t = total.value
+        ids = np.empty(t, dtype=np.int32)
+        dist = np.empty(t, dtype=np.float64)
+        unsafe = np.empty((t, 2), dtype=np.uint8)
+        length = np.empty((t, 2), dtype=np.float64)
+        check(self._lib.drrt_extend_fetch(self._h, _ptr(ids, c_ip), _ptr(dist, c_dp),
+                                          _ptr(unsafe, c_u8p), _ptr(length, c_dp)))
+        off = np.zeros(nq + 1, dtype=np.int64)
+        np.cumsum(counts, out=off[1:])
+        return dict(offsets=off, ids=ids, dist=dist, unsafe=unsafe, length=length, best_parent=best,
+                    best_cost=cost)
+
+    def Extend_dev(self, range_, new_points, lmc=None, best_parent=None, best_cost=None,
+                   robot_radius=0.5, r_min=1.0):
+        """device-resident Extend: torch tensors in; returns (RangeResult rows, unsafe u8[2*total],
+        length f64[2*total]) as views of library-owned buffers (valid until the next call)."""
+        import torch
+        q = new_points
+        rad_t, r_all = (range_, 0.0) if torch.is_tensor(range_) else (None, float(range_))
+        res = capi.RangeResult()
+        u = C.c_void_p()
+        ln = C.c_void_p()
+        check(self._lib.drrt_extend_batch_dev(self._h, q.shape[0], _dev_ptr(q), _dev_ptr(rad_t), r_all,
+                                              float(robot_radius), float(r_min), _dev_ptr(lmc),
+                                              _torch_stream(), C.byref(res), C.byref(u), C.byref(ln),
+                                              _dev_ptr(best_parent), _dev_ptr(best_cost)))
+        return res, dev_tensor(u.value, 2 * res.total, "|u1"), dev_tensor(ln.value, 2 * res.total, "<f8")
 
     # -- LineCheck obstacle.cpp:1092-1143
     def LineCheck(self, node1, node2, robot_radius=0.5):

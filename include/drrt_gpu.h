@@ -173,6 +173,33 @@ DRRT_API int drrt_edgecheck_batch_dev(drrt_store *h, int64_t n, const double *st
                              uint8_t *verdict_dev, double *length_dev,
                              void *stream);
 
+/* ---- fused Extend step (the step after the edge check) ----------
+ * What Extend does around the hot path for one new node (src/drrt.cpp:194-362):
+ * KDFindWithinRange (:213-216), then for every neighbour the new->near edge
+ * (FindBestParent :367-460) and the near->new edge (:284-293), each solved and
+ * collision-checked, and the parent chosen as the safe new->near edge that
+ * minimises near.rrt_LMC_ + edge.dist_ (:444-449).  Here for nq new nodes at
+ * once, the neighbour lists never leaving the device between the two stages.
+ *   lmc          rrt_LMC_ of every node in the store (host array, store-size
+ *                entries) or NULL to skip the parent reduction
+ *   counts/total as drrt_range_batch
+ *   best_parent  node id per query (-1: no safe neighbour), best_cost its
+ *                near.lmc + length (INF = 1e12 when none); ties: smaller id
+ * drrt_extend_fetch returns the rows (ids, dist as drrt_range_fetch) and, per
+ * neighbour t, unsafe[2t], length[2t] for new->near and [2t+1] for near->new. */
+DRRT_API int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const double *radius,
+                      double radius_all, double robot_radius, double r_min, int in_warmup,
+                      const double *lmc, int32_t *counts, int64_t *total,
+                      int32_t *best_parent, double *best_cost);
+DRRT_API int drrt_extend_fetch(drrt_store *h, int32_t *ids, double *dist, uint8_t *unsafe,
+                      double *length);
+DRRT_API int drrt_extend_batch_dev(drrt_store *h, int64_t nq, const double *q_dev,
+                          const double *radius_dev, double radius_all, double robot_radius,
+                          double r_min, const double *lmc_dev, void *stream,
+                          drrt_range_result *rows, const uint8_t **unsafe_dev,
+                          const double **length_dev, int32_t *best_parent_dev,
+                          double *best_cost_dev);
+
 /* DubinsEdge::CalculateTrajectory polyline (edge->trajectory_, read by
  * src/moverobot.cpp:107,158): up to DRRT_TRAJ_MAX (x,y) points per edge.
  * xy: n x DRRT_TRAJ_MAX x 2 f64; npts: n; type: n x 4 chars ("rsl\0"...) */

@@ -1,0 +1,74 @@
+"""Fused Extend step (drrt_extend_batch) against the oracle:
+KDFindWithinRange (kdtree.cpp:794-820), both Dubins edges per neighbour through
+CalculateTrajectory + ExplicitEdgeCheck, and FindBestParent's reduction
+(drrt.cpp:388-459): the safe new->near edge minimising near.rrt_LMC_ + dist_."""
+import numpy as np
+import pytest
+
+from drrt_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_extend_matches_oracle(drrt, po):
+    pos = synth.box_points(120_000, 401)
+    obstacles = synth.obstacles(128, 402)
+    tree = drrt.KDTree()
+    tree.KDInsert(pos)
+    tree.SetObstacles(**obstacles)
+    ref = po.RefTree()
+    ref.insert(pos)
+    robs = po.RefObstacles(**obstacles)
+    rng = np.random.default_rng(403)
+    lmc = rng.uniform(0.0, 80.0, len(pos))
+    lmc[rng.integers(0, len(pos), 500)] = 1e12              # nodes not yet connected: rrt_LMC_ = INF
+    new = synth.box_points(700, 404)
+    radius = 1.3
+    out = tree.Extend(radius, new, lmc=lmc)
+    off, ids, dist = ref.range_batch(new, radius)
+    assert np.array_equal(out["offsets"], off) and np.array_equal(out["ids"], ids)
+    assert np.array_equal(out["dist"], dist)
+    rows = np.repeat(np.arange(len(new)), np.diff(off))
+    a, b = new[rows], pos[ids]
+    v_out, l_out, c_out = robs.edge_check_batch(a, b, want_clearance=True)   # new -> near
+    v_in, l_in, c_in = robs.edge_check_batch(b, a, want_clearance=True)      # near -> new
+    for col, (v, ln, clr) in enumerate(((v_out, l_out, c_out), (v_in, l_in, c_in))):
+        bad = np.nonzero(out["unsafe"][:, col] != v)[0]
+        assert (clr[bad] < 1e-6).all() and len(bad) <= 3
+        assert np.allclose(out["length"][:, col], ln, rtol=1e-9)
+    # FindBestParent on the DEVICE's own verdicts/lengths must be the exact argmin;
+    # against the oracle's it may differ only where a verdict differed
+    cost_dev = np.where(out["unsafe"][:, 0] == 0, lmc[ids] + out["length"][:, 0], np.inf)
+    for i in range(len(new)):
+        sl = slice(off[i], off[i + 1])
+        c = cost_dev[sl]
+        ok = c < 1e12                                          # rrt_LMC_ starts at INF, strict `>`
+        if ok.any():
+            j = int(np.argmin(np.where(ok, c, np.inf)))
+            assert out["best_parent"][i] == ids[sl][j]
+            assert out["best_cost"][i] == c[j]
+        else:
+            assert out["best_parent"][i] == -1 and out["best_cost"][i] == 1e12
+    cost_ref = np.where(v_out == 0, lmc[ids] + l_out, np.inf)
+    agree = 0
+    for i in range(len(new)):
+        sl = slice(off[i], off[i + 1])
+        c = cost_ref[sl]
+        want = ids[sl][int(np.argmin(c))] if (c < 1e12).any() else -1
+        agree += int(want == out["best_parent"][i])
+    assert agree >= len(new) - 3
+    assert (out["best_parent"] >= 0).mean() > 0.5
+
+
+def test_extend_warmup_and_empty(drrt, po):
+    pos = synth.box_points(5000, 405)
+    tree = drrt.KDTree()
+    tree.KDInsert(pos)
+    tree.SetObstacles(**synth.obstacles(64, 406))
+    new = synth.box_points(50, 407)
+    out = tree.Extend(2.0, new, lmc=np.zeros(len(pos)), in_warmup=True)
+    assert not out["unsafe"].any()                            # in_warmup_time_: nothing collides
+    out = tree.Extend(1e-9, new, lmc=np.zeros(len(pos)))
+    assert out["offsets"][-1] == 0 and (out["best_parent"] == -1).all()
+    out = tree.Extend(2.0, new)                               # no lmc: rows only
+    assert out["best_parent"] is None and len(out["ids"]) == out["offsets"][-1]
