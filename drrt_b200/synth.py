@@ -108,3 +108,21 @@ def random_edges(n, seed, max_len=0.66, lo=0.0, hi=50.0):
     e[:, 1] = s[:, 1] + ln * np.sin(ang)
     e[:, 2] = rng.uniform(0.0, TWO_PI, n)
     return s, e
+
+
+def write_obstacle_file(path, table):
+    """Writes a polygon table in the grammar of Obstacle::ReadObstaclesFromFile
+    (src/obstacle.cpp:25-155): polygon count; per polygon a delimiter line, `ox,oy`, the number
+    of moves (0 here: static), the vertex count and one `x,y` line per vertex.  Vertices are
+    written as the analytic checker reads them back (world frame)."""
+    with open(path, "w") as fh:
+        n = len(table["kind"])
+        fh.write("%d\n" % n)
+        for i in range(n):
+            fh.write("----\n")
+            fh.write("%.17g,%.17g\n" % (table["origin"][i][0], table["origin"][i][1]))
+            fh.write("0\n")
+            v0, v1 = table["vert_off"][i], table["vert_off"][i + 1]
+            fh.write("%d\n" % (v1 - v0))
+            for v in range(v0, v1):
+                fh.write("%.17g,%.17g\n" % (table["verts"][v][0], table["verts"][v][1]))

@@ -130,3 +130,17 @@ def geom(pa, pb, qa, qb):
     raw = _run("geom", struct.pack("<q", n) + _f64(v))
     return (np.frombuffer(raw, dtype=np.float64, count=n).copy(),
             np.frombuffer(raw, dtype=np.float64, count=n, offset=8 * n).copy())
+
+
+def obstacle_file_edges(path, start, end, r_min=1.0, robot_radius=0.5, metric=0):
+    """reads `path` with the reference's Obstacle::ReadObstaclesFromFile, then checks the edges"""
+    s = np.ascontiguousarray(start, dtype=np.float64).reshape(-1, 3)
+    e = np.ascontiguousarray(end, dtype=np.float64).reshape(-1, 3)
+    pb = os.path.abspath(path).encode()
+    payload = (struct.pack("<iddi", metric, r_min, robot_radius, len(pb)) + pb
+               + struct.pack("<q", len(s)) + _f64(s) + _f64(e))
+    raw = _run("obsfile", payload)
+    n_obs = struct.unpack_from("<i", raw, 0)[0]
+    verdict = np.frombuffer(raw, dtype=np.uint8, count=len(s), offset=4).copy()
+    dist = np.frombuffer(raw, dtype=np.float64, count=len(s), offset=4 + len(s)).copy()
+    return n_obs, verdict, dist

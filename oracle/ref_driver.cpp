@@ -284,6 +284,53 @@ static int cmd_edges(const char *cmd, Reader &in, Writer &out) {
   return 0;
 }
 
+// ---- obstacle file -> list -> edge checks -------------------
+// Obstacle::ReadObstaclesFromFile (obstacle.cpp:25-155) fills ConfigSpace::obstacles_; the
+// obstacle thread later switches obstacles on (obstacle_used_), done here directly.
+static int cmd_obsfile(const char *cmd, Reader &in, Writer &out) {
+  int metric = in.get<int32_t>();
+  double r_min = in.get<double>(), robot_radius = in.get<double>();
+  int32_t plen = in.get<int32_t>();
+  std::vector<char> pbuf = in.arr<char>(plen);
+  std::string path(pbuf.begin(), pbuf.end());
+  int64_t n = in.get<int64_t>();
+  std::vector<double> s = in.arr<double>(3 * n), e = in.arr<double>(3 * n);
+  shared_ptr<ConfigSpace> C = make_cspace(metric, r_min, robot_radius, 0.1);
+  shared_ptr<KDTree> T = make_tree(metric, 1);
+  Obstacle::ReadObstaclesFromFile(path, C);
+  {
+    shared_ptr<ListNode> ln = C->obstacles_->front_;
+    for (int i = 0; i < C->obstacles_->length_; i++, ln = ln->child_) ln->obstacle_->obstacle_used_ = true;
+  }
+#ifdef DRRT_SHIM
+  DrrtGpuUploadObstacles(T.get(), C);
+#endif
+  std::vector<uint8_t> verdict(n, 0);
+  std::vector<double> dist(n);
+  for (int64_t i = 0; i < n; i++) {
+    shared_ptr<KDTreeNode> a = make_shared<KDTreeNode>(vec3(&s[3 * i]));
+    shared_ptr<KDTreeNode> b = make_shared<KDTreeNode>(vec3(&e[3 * i]));
+    shared_ptr<Edge> edge = Edge::NewEdge(C, T, a, b);
+    bool hit = false;
+#ifdef DRRT_SHIM
+    hit = ExplicitEdgeCheckGpu(C, T.get(), edge);
+#else
+    edge->CalculateTrajectory();
+    shared_ptr<ListNode> ln = C->obstacles_->front_;  // obstacle.cpp:897-916
+    for (int o = 0; o < C->obstacles_->length_ && !hit; o++, ln = ln->child_)
+      for (int k = 1; k < edge->trajectory_.rows() && !hit; k++)
+        hit = ExplicitEdgeCheck2D(ln->obstacle_, edge->trajectory_.row(k - 1), edge->trajectory_.row(k),
+                                  C->robot_radius_);
+#endif
+    verdict[i] = hit ? 1 : 0;
+    dist[i] = edge->dist_;
+  }
+  out.put<int32_t>(C->obstacles_->length_);
+  out.arr(verdict); out.arr(dist);
+  (void)cmd;
+  return 0;
+}
+
 // ---- node validity ------------------------------------------------------------
 static int cmd_points(Reader &in, Writer &out) {
   int metric = in.get<int32_t>();
@@ -332,6 +379,7 @@ int main(int argc, char **argv) {
   if (!strcmp(cmd, "traj") || !strcmp(cmd, "edgecheck") || !strcmp(cmd, "edgecheck_gpu"))
     return cmd_edges(cmd, in, out);
   if (!strcmp(cmd, "points")) return cmd_points(in, out);
+  if (!strcmp(cmd, "obsfile")) return cmd_obsfile(cmd, in, out);
   if (!strcmp(cmd, "geom")) return cmd_geom(in, out);
   fprintf(stderr, "unknown command %s\n", cmd);
   return 2;

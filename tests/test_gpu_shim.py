@@ -58,3 +58,21 @@ def test_reference_edges_over_gpu_checker(shim, po, gold):
         _, _, clr = po.RefObstacles(**I["o"]).edge_check_batch(I["s"], I["e"], want_clearance=True)
         assert (clr[diff] < 1e-6).all()
     assert np.allclose(r["dist"], unhex(gold["edges"]["dist"]), rtol=1e-9)
+
+
+def test_obstacle_file_to_device_table(shim, po, tmp_path):
+    """SURVEY 8f rank 4: the reference's own Obstacle::ReadObstaclesFromFile (obstacle.cpp:25-155)
+    fills ConfigSpace::obstacles_; DrrtGpuUploadObstacles flattens that list into the device table;
+    ExplicitEdgeCheckGpu then answers as the analytic checker does on the same list."""
+    from drrt_b200 import synth
+    o = synth.obstacles(40, 0xE1)
+    path = str(tmp_path / "obstacles.txt")
+    synth.write_obstacle_file(path, o)
+    s, e = synth.random_edges(1500, 0xE2, max_len=2.5)
+    n_obs, v, d = shim.obstacle_file_edges(path, s, e)
+    rv, rl, clr = po.RefObstacles(**o).edge_check_batch(s, e, want_clearance=True)
+    assert n_obs == 40
+    bad = np.nonzero(v != rv)[0]
+    assert (clr[bad] < 1e-6).all() and len(bad) <= 2
+    assert np.allclose(d, rl, rtol=1e-9)
+    assert 0.05 < v.mean() < 0.9
