@@ -31,7 +31,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_NODES = 1_000_000
+N_NODES = 1_000_000   # --nodes overrides (config 5 uses 8 M)
 N_QUERIES = 65_536
 N_EDGES = 10_000_000
 K_NN = 16
@@ -153,8 +153,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the kNN / edge-check extras")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--nodes", type=int, default=N_NODES,
+                    help="nodes in the replicated store (BASELINE config 5: 8000000)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global N_NODES
+    N_NODES = args.nodes
 
     if args.impl == "reference":
         run_reference(args)
@@ -353,6 +357,19 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         _, cpu = cpu_range_baseline(r2a, 0)
+        if "dubins_edge_check" in extra:
+            # the oracle's CalculateTrajectory + ExplicitEdgeCheck on a bounded sample of config-3 edges
+            from oracle import pyoracle as po
+            off_h, ids_h, _ = tree.KDFindWithinRange(r2b, q_host[:2048])
+            s_h, e_h = synth.edges_from_neighbours(synth.nodes(N_NODES), q_host[:2048], off_h, ids_h, 200_000)
+            robs = po.RefObstacles(**synth.obstacles())
+            t0 = time.perf_counter()
+            robs.edge_check_batch(s_h, e_h, nthreads=0)
+            dt = time.perf_counter() - t0
+            extra["dubins_edge_check"]["cpu_baseline"] = {
+                "value": len(s_h) / dt, "unit": "edges/s", "cores": po.num_threads(), "kind": "port",
+                "sample": "%d config-3 edges, oracle Dubins solve + polyline + ExplicitEdgeCheck2D with "
+                          "first-hit exit, %.1f s" % (len(s_h), dt)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
