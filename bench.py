@@ -146,6 +146,7 @@ def run_reference(args):
 
 
 def main():
+    global N_NODES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -157,7 +158,6 @@ def main():
                     help="nodes in the replicated store (BASELINE config 5: 8000000)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    global N_NODES
     N_NODES = args.nodes
 
     if args.impl == "reference":
