@@ -376,9 +376,9 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "config2a batched range-ball: 1M nodes (x,y,theta), ghost "
+                "config": {"workload": "config2a batched range-ball: %d nodes (x,y,theta), ghost "
                                        "wraparound, 64K queries/GPU, r=%.6f (RRTx shrinking radius, "
-                                       "gamma=100)" % r2a,
+                                       "gamma=100)" % (N_NODES, r2a),
                            "nodes": N_NODES, "queries_per_gpu": N_QUERIES,
                            "hits_per_query": hits_2a / N_QUERIES,
                            "l2": "flushed between timed steps (512 MiB memset, untimed)",

@@ -60,3 +60,32 @@ def test_create_rejects_unsupported(drrt):
         drrt.KDTree(wraps=(0,), wrap_points=(50.0,))
     with pytest.raises(drrt.DrrtError):
         drrt.KDTree(wraps=(2,), wrap_points=(6.0,))   # R2S1 metric wraps at 2*pi' only
+
+
+def test_one_handle_many_host_threads(drrt, po):
+    # the reference enters the tree from 5 planner threads + robot + obstacle threads under
+    # tree_mutex_ (mainloop.cpp:99-113); calls on one handle are serialised inside the library
+    import threading
+    pos = synth.box_points(40_000, 7)
+    t = drrt.KDTree(); t.KDInsert(pos)
+    r = po.RefTree(); r.insert(pos)
+    q = synth.box_points(4 * 300, 8).reshape(4, 300, 3)
+    want = [r.range_batch(q[k], 1.5) for k in range(4)]
+    got = [None] * 4
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(5):
+                got[k] = t.KDFindWithinRange(1.5, q[k])
+                nid, _ = t.KDFindNearest(q[k][:50])
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs
+    for k in range(4):
+        for a, b in zip(got[k], want[k]):
+            assert np.array_equal(a, b)
