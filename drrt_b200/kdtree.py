@@ -7,6 +7,7 @@ to the C ABI (include/drrt_gpu.h).  Results come back as numpy arrays; the
 device.  There is no CPU path here.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -70,6 +71,9 @@ class KDTree:
         check(self._lib.drrt_store_create(device, dims, len(w), w.ctypes.data_as(C.POINTER(C.c_int)),
                                           _ptr(wp, c_dp), metric, int(capacity), C.byref(h)))
         self._h = h
+        # batch + fetch is a two-call protocol on the handle: keep the pair together when several
+        # host threads share one tree (the reference's callers hold tree_mutex_ for the same reason)
+        self._lock = threading.Lock()
 
     def close(self):
         if getattr(self, "_h", None):
@@ -131,12 +135,13 @@ class KDTree:
             rad = _f64(range_, (nq,))
         counts = np.zeros(nq, dtype=np.int32)
         total = C.c_int64()
-        check(self._lib.drrt_range_batch(self._h, nq, _ptr(q, c_dp),
-                                         _ptr(rad, c_dp) if rad is not None else None, r_all,
-                                         _ptr(counts, c_ip), C.byref(total)))
-        ids = np.empty(total.value, dtype=np.int32)
-        dist = np.empty(total.value, dtype=np.float64)
-        check(self._lib.drrt_range_fetch(self._h, _ptr(ids, c_ip), _ptr(dist, c_dp)))
+        with self._lock:
+            check(self._lib.drrt_range_batch(self._h, nq, _ptr(q, c_dp),
+                                             _ptr(rad, c_dp) if rad is not None else None, r_all,
+                                             _ptr(counts, c_ip), C.byref(total)))
+            ids = np.empty(total.value, dtype=np.int32)
+            dist = np.empty(total.value, dtype=np.float64)
+            check(self._lib.drrt_range_fetch(self._h, _ptr(ids, c_ip), _ptr(dist, c_dp)))
         off = np.zeros(nq + 1, dtype=np.int64)
         np.cumsum(counts, out=off[1:])
         return off, ids, dist
@@ -254,19 +259,20 @@ class KDTree:
         best = np.full(nq, -1, dtype=np.int32) if lmc is not None else None
         cost = np.zeros(nq, dtype=np.float64) if lmc is not None else None
         lm = _f64(lmc) if lmc is not None else None
-        check(self._lib.drrt_extend_batch(self._h, nq, _ptr(q, c_dp),
-                                          _ptr(rad, c_dp) if rad is not None else None, r_all,
-                                          float(robot_radius), float(r_min), int(in_warmup),
-                                          _ptr(lm, c_dp) if lm is not None else None, _ptr(counts, c_ip),
-                                          C.byref(total), _ptr(best, c_ip) if best is not None else None,
-                                          _ptr(cost, c_dp) if cost is not None else None))
-        t = total.value
-        ids = np.empty(t, dtype=np.int32)
-        dist = np.empty(t, dtype=np.float64)
-        unsafe = np.empty((t, 2), dtype=np.uint8)
-        length = np.empty((t, 2), dtype=np.float64)
-        check(self._lib.drrt_extend_fetch(self._h, _ptr(ids, c_ip), _ptr(dist, c_dp),
-                                          _ptr(unsafe, c_u8p), _ptr(length, c_dp)))
+        with self._lock:
+            check(self._lib.drrt_extend_batch(self._h, nq, _ptr(q, c_dp),
+                                              _ptr(rad, c_dp) if rad is not None else None, r_all,
+                                              float(robot_radius), float(r_min), int(in_warmup),
+                                              _ptr(lm, c_dp) if lm is not None else None, _ptr(counts, c_ip),
+                                              C.byref(total), _ptr(best, c_ip) if best is not None else None,
+                                              _ptr(cost, c_dp) if cost is not None else None))
+            t = total.value
+            ids = np.empty(t, dtype=np.int32)
+            dist = np.empty(t, dtype=np.float64)
+            unsafe = np.empty((t, 2), dtype=np.uint8)
+            length = np.empty((t, 2), dtype=np.float64)
+            check(self._lib.drrt_extend_fetch(self._h, _ptr(ids, c_ip), _ptr(dist, c_dp),
+                                              _ptr(unsafe, c_u8p), _ptr(length, c_dp)))
         off = np.zeros(nq + 1, dtype=np.int64)
         np.cumsum(counts, out=off[1:])
         return dict(offsets=off, ids=ids, dist=dist, unsafe=unsafe, length=length, best_parent=best,

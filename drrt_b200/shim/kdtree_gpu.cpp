@@ -31,6 +31,7 @@ struct ShimState {
   drrt_store *h = nullptr;
   std::vector<std::shared_ptr<KDTreeNode>> by_id;  // device id -> host node
   bool failed = false;
+  std::mutex pair_mu;  // drrt_range_batch + drrt_range_fetch travel together
 };
 
 std::mutex g_mu;
@@ -277,6 +278,7 @@ void KDTree::KDFindWithinRange(std::shared_ptr<JList> &S, double range, Eigen::V
   ShimState &s = state_of(this);
   if (s.failed) return;
   double q[3] = {queryPoint(0), queryPoint(1), queryPoint(2)};
+  std::lock_guard<std::mutex> pair(s.pair_mu);
   int32_t count = 0;
   int64_t total = 0;
   if (!ok(drrt_range_batch(s.h, 1, q, nullptr, range, &count, &total), "KDFindWithinRange")) return;
