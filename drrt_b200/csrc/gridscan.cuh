@@ -214,45 +214,44 @@ __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, 
 // thread resolves one column's runs, a CTA-wide prefix sum flattens them, and
 // each warp takes an equal, contiguous slice of the candidates (consecutive
 // lanes read consecutive 32-byte records).  run_start/run_pref hold 2*T and
-// 2*T+1 ints, tmp holds NWARPS ints.  f as in scan_columns.
+// 2*T+1 ints, tmp64 holds NWARPS 64-bit words.  f as in scan_columns.
 template <int NWARPS, class F>
 __device__ __forceinline__ void scan_columns_block(const GridView &A, const Query &Q,
-                                                   int *run_start, int *run_pref, int *tmp, F f) {
+                                                   int *run_start, int *run_pref, long long *tmp64,
+                                                   F f) {
   constexpr int T = NWARPS * 32;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int ncy = Q.iy1 - Q.iy0 + 1;
   const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
   const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
-  const bool two = Q.may_wrap;  // a second (wrapped) theta run per column
-  const int nent = two ? 2 * T : T;
   for (int cb = 0; cb < ncol; cb += T) {
     int s0, l0, s1, l1;
     column_runs(A, Q, cb + tid, ncol, ncy, cull, s0, l0, s1, l1);
-    int tot = l0 + l1, inc = tot;
+    // one prefix sum carries both the record count (low half) and the number of NON-EMPTY
+    // runs (high half): only those are listed, so walking the list never steps over culled
+    // columns or absent wrap runs
+    const int nrun = (l0 > 0) + (l1 > 0);
+    const long long mine = ((long long)nrun << 32) | (unsigned)(l0 + l1);
+    long long inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      long long t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    if (lane == 31) tmp[w] = inc;
+    if (lane == 31) tmp64[w] = inc;
     __syncthreads();
-    int wbase = 0, total = 0;
+    long long wbase = 0, all = 0;
 #pragma unroll
     for (int ww = 0; ww < NWARPS; ww++) {
-      int v = tmp[ww];
+      long long v = tmp64[ww];
       if (ww < w) wbase += v;
-      total += v;
+      all += v;
     }
-    int excl = wbase + inc - tot;
-    if (two) {
-      run_start[2 * tid] = s0;
-      run_start[2 * tid + 1] = s1;
-      run_pref[2 * tid] = excl;
-      run_pref[2 * tid + 1] = excl + l0;
-    } else {
-      run_start[tid] = s0;
-      run_pref[tid] = excl;
-    }
+    const long long excl64 = wbase + inc - mine;
+    const int excl = (int)(excl64 & 0xffffffffll), slot = (int)(excl64 >> 32);
+    const int total = (int)(all & 0xffffffffll), nent = (int)(all >> 32);
+    if (l0 > 0) { run_start[slot] = s0; run_pref[slot] = excl; }
+    if (l1 > 0) { run_start[slot + (l0 > 0)] = s1; run_pref[slot + (l0 > 0)] = excl + l0; }
     if (tid == T - 1) run_pref[nent] = total;
     __syncthreads();
     int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;

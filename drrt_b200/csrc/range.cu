@@ -337,7 +337,7 @@ range_kernel(RangeArgs A) {
   __shared__ long long s_base;
   __shared__ int s_runs[RUN_SLOTS];
   __shared__ int s_pref[RUN_SLOTS + WARPS];
-  __shared__ int s_tmp[WARPS];
+  __shared__ long long s_tmp[WARPS];
   __shared__ Query s_query;
   __shared__ int s_hist[NSTAGE][NB + 1];
   __shared__ int s_misc[NSTAGE][4 + WARPS];
