@@ -374,14 +374,26 @@ struct PolylineWalker {
       // nothing can collide inside this arc's circle: after its first point (whose
       // segment from the previous part is still tested) run the angle recurrence
       // without sin/cos up to the last point, which starts the next junction segment
-      if (equal) i = n - 1;
-      else
-        for (; i < n - 1; i++) {
-          if (ended) continue;
-          bool in = (kind == PART_ARC_R) ? (val >= phi_end) : (val <= phi_end);
-          if (in) { if (kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
-          else ended = true;
+      if (equal) {
+        i = n - 1;
+      } else {
+        // Unless |dphi|/0.1 sits on an integer (to within the rounding the recurrence can
+        // accumulate) the loop provably runs n-1 times and the last entry is phi_end.
+        double steps = fabs(phi_end - a) / 0.1;
+        double frac = steps - floor(steps);
+        if (frac > 1e-9 && frac < 1.0 - 1e-9) {
+          i = n - 1;
+          ended = false;
+          val = (kind == PART_ARC_R) ? phi_end - 1.0 : phi_end + 1.0;  // next() emits phi_end
+        } else {
+          for (; i < n - 1; i++) {
+            if (ended) continue;
+            bool in = (kind == PART_ARC_R) ? (val >= phi_end) : (val <= phi_end);
+            if (in) { if (kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
+            else ended = true;
+          }
         }
+      }
       fresh = true;
     }
     if (i >= n) { part++; begin_part(); }
