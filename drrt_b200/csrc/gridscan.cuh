@@ -285,6 +285,105 @@ __device__ __forceinline__ void scan_columns_block(const GridView &A, const Quer
   }
 }
 
+// Flattened candidate list of a CTA-wide scan: run j covers candidate numbers
+// [runs[j-1].x, runs[j].x) and candidate i of it is record i + runs[j].y.
+// A whole CTA of NWARPS warps visits ALL candidate columns of query Q: every
+// thread resolves one column, a CTA-wide prefix sum lists the non-empty runs,
+// each warp takes an equal contiguous slice of the candidate numbers and every
+// lane handles UNR candidates per trip (i, i+32, ...), walking the run list
+// monotonically.  runs holds 2*T+1 entries, tmp64 NWARPS words.
+// f(valid[UNR], x[UNR], y[UNR], theta[UNR], id[UNR]) is called converged.
+template <int NWARPS, int UNR, class F>
+__device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query &Q, int2 *runs,
+                                                 long long *tmp64, F f) {
+  constexpr int T = NWARPS * 32;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int ncy = Q.iy1 - Q.iy0 + 1;
+  const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
+  const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
+  for (int cb = 0; cb < ncol; cb += T) {
+    int s0, l0, s1, l1;
+    column_runs(A, Q, cb + tid, ncol, ncy, cull, s0, l0, s1, l1);
+    const int nrun = (l0 > 0) + (l1 > 0);
+    const long long mine = ((long long)nrun << 32) | (unsigned)(l0 + l1);
+    long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) tmp64[w] = inc;
+    __syncthreads();
+    long long wbase = 0, all = 0;
+#pragma unroll
+    for (int ww = 0; ww < NWARPS; ww++) {
+      long long v = tmp64[ww];
+      if (ww < w) wbase += v;
+      all += v;
+    }
+    const long long excl64 = wbase + inc - mine;
+    const int excl = (int)(excl64 & 0xffffffffll), slot = (int)(excl64 >> 32);
+    const int total = (int)(all & 0xffffffffll), nent = (int)(all >> 32);
+    if (l0 > 0) runs[slot] = make_int2(excl + l0, s0 - excl);
+    if (l1 > 0) runs[slot + (l0 > 0)] = make_int2(excl + l0 + l1, s1 - (excl + l0));
+    if (tid == T - 1) runs[nent] = make_int2(0x7fffffff, 0);
+    __syncthreads();
+    const int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;
+    const int c0 = w * per, c1 = min(total, c0 + per);
+    if (c0 < c1) {
+      int lo = -1, hi = nent;  // smallest j with runs[j].x > c0
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (runs[mid].x > c0) hi = mid; else lo = mid;
+      }
+      int jl = hi;
+      int2 cur = runs[jl];
+      for (int base = c0; base < c1; base += 32 * UNR) {
+        bool valid[UNR];
+        double nx[UNR], ny[UNR], nt[UNR];
+        int32_t id[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          const int i = base + u * 32 + lane;
+          valid[u] = i < c1;
+          nx[u] = ny[u] = nt[u] = 0.0;
+          id[u] = 0;
+          if (valid[u]) {
+            while (i >= cur.x) cur = runs[++jl];
+            const NodeRec *r = A.rec + (i + cur.y);
+            double2 xy = *reinterpret_cast<const double2 *>(&r->x);
+            double2 ti = *reinterpret_cast<const double2 *>(&r->th);
+            nx[u] = xy.x; ny[u] = xy.y; nt[u] = ti.x;
+            id[u] = (int32_t)(__double_as_longlong(ti.y) & 0xffffffffll);
+          }
+        }
+        f(valid, nx, ny, nt, id);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// tail scan of a whole CTA, UNR candidates per lane per trip
+template <int NWARPS, int UNR, class F>
+__device__ __forceinline__ void scan_tail_cta(const GridView &A, F f) {
+  const int tid = threadIdx.x;
+  for (int64_t b = A.n_indexed; b < A.n; b += (int64_t)NWARPS * 32 * UNR) {
+    bool valid[UNR];
+    double nx[UNR], ny[UNR], nt[UNR];
+    int32_t id[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      int64_t i = b + (int64_t)u * NWARPS * 32 + tid;
+      valid[u] = i < A.n;
+      nx[u] = ny[u] = nt[u] = 0.0;
+      id[u] = (int32_t)i;
+      if (valid[u]) { nx[u] = A.x[i]; ny[u] = A.y[i]; nt[u] = A.th[i]; }
+    }
+    f(valid, nx, ny, nt, id);
+  }
+}
+
 // nodes inserted after the last index build: straight from the SoA store
 template <class F>
 __device__ __forceinline__ void scan_tail(const GridView &A, int first, int stride, int lane, F f) {

@@ -449,17 +449,309 @@ range_kernel(RangeArgs A) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// CTA-per-query kernel (large neighbourhoods, config 2a).
+//
+// Differences from the generic kernel above, all aimed at the instruction
+// count (the kernel is issue-bound, profiles/README.md):
+//  * the id sort is fused into the scan: a staged hit bumps a BYTE counter of
+//    its id bucket (id >> shift, 16384 buckets, four per shared-memory word) and
+//    keeps the old value as its arrival rank; after the scan one prefix sum over
+//    the 4096 words gives every bucket's start, a hit's provisional position is
+//    start + rank, and only hits sharing a bucket (~20 %) count their smaller
+//    mates.  Two passes over the hits instead of six;
+//  * the ghost probe (kdtree.cpp:807-819) is evaluated only when it can matter:
+//    for the wrap-aware metric metric(ghost,n) >= metric(q,n) up to rounding
+//    (the ghost's theta term is the unwrapped distance), so a candidate the
+//    first probe rejected by more than a rounding band cannot be admitted by
+//    the ghost; candidates the first probe reaches in range but the signed
+//    theta prune hides (walk_reaches) still take the ghost pass;
+//  * two candidates per lane per trip, one shared counter update for both.
+static constexpr int CTA_WARPS = 16;
+static constexpr int CTA_T = CTA_WARPS * 32;
+static constexpr int CTA_STAGE = 4608;  // hits staged per query
+static constexpr int CTA_NB = 16384;    // id buckets
+static constexpr int CTA_NW = CTA_NB / 4;
+static constexpr int CTA_UNR = 2;
+static constexpr int CTA_CROWDED = 128;  // a byte counter must never wrap
+// dynamic shared memory layout (bytes)
+static constexpr int CTA_OFF_DIST = 0;
+static constexpr int CTA_OFF_ID = CTA_OFF_DIST + CTA_STAGE * 8;
+static constexpr int CTA_OFF_HIST = CTA_OFF_ID + CTA_STAGE * 4;
+static constexpr int CTA_OFF_WSTART = CTA_OFF_HIST + CTA_NW * 4;
+static constexpr int CTA_OFF_TMP = CTA_OFF_WSTART + CTA_NW * 2;
+static constexpr int CTA_OFF_RANK = CTA_OFF_TMP + CTA_STAGE * 2;
+static constexpr int CTA_OFF_RUNS = CTA_OFF_RANK + CTA_STAGE;
+static constexpr int CTA_SMEM = CTA_OFF_RUNS + (2 * CTA_T + 1) * 8 + 8;
+static_assert(CTA_OFF_HIST + CTA_STAGE * 8 <= CTA_SMEM, "fallback sort keys alias the sort scratch");
+static_assert(CTA_OFF_RUNS % 8 == 0 && CTA_OFF_HIST % 16 == 0 && CTA_OFF_WSTART % 16 == 0, "alignment");
+
+// candidate test with the ghost probe taken only when it can change the answer
+//
+// Why the ghost can be skipped (wrap-aware metric, wrap point == the metric's period W):
+// with a = |q.theta - n.theta| the first probe's theta term is min(a, W - a), whose square is
+// the squared distance of a to the nearer of {0, W}; the ghost q.theta +- W sees
+// a' = |q.theta +- W - n.theta| instead.  For a <= 1.5 W that distance never shrinks
+// (it stays equal on the far side of the seam and grows on the near side), so
+// metric(ghost, n) >= metric(q, n) in exact arithmetic; in IEEE double each theta term
+// carries at most a few roundings of magnitudes <= |q.theta| + |n.theta| + 2W, which the
+// band (2^-46 relative to that magnitude, against 2^-52 roundings) covers.  Candidates
+// outside |n.theta - q.theta| <= 1.45 W or |n.theta| <= 64 always take the ghost pass.
+struct GhostBand {
+  double s_band;    // first-probe squared sums at or above this cannot be rescued by the ghost
+  double nlo, nhi;  // n.theta interval in which that holds
+};
+
+template <int METRIC>
+__device__ __forceinline__ GhostBand ghost_band(const Query &Q) {
+  GhostBand B;
+  const double band = Q.r + 1.4210854715202004e-14 * (fabs(Q.t) + 64.0 + 2.0 * DRRT_TWO_PI + fabs(Q.r));
+  B.s_band = band * band * (1.0 + 1.4210854715202004e-14);
+  B.nlo = fmax(-64.0, Q.t - 1.45 * DRRT_TWO_PI);
+  B.nhi = fmin(64.0, Q.t + 1.45 * DRRT_TWO_PI);
+  if (METRIC == DRRT_METRIC_EUCLID || !(fabs(Q.t) <= 64.0) || !(B.s_band == B.s_band)) {
+    B.s_band = 1.0e308;  // every rejected candidate takes the ghost pass
+    B.nlo = 1.0;
+    B.nhi = -1.0;
+  }
+  return B;
+}
+
+template <int METRIC>
+__device__ __forceinline__ bool eval_candidate2(const Query &Q, const GhostBand &B, double nx,
+                                                double ny, double nt, int32_t id,
+                                                const double *gate, double *dout) {
+  double s = metric_sum<METRIC>(Q.x, Q.y, Q.t, nx, ny, nt);
+  if (s < Q.s_hi) {
+    double d = sqrt(s);
+    if (id == 0) {
+      if (d <= Q.r) { *dout = d; return true; }  // kdtree.cpp:800-802
+    } else if (d < Q.r) {                         // kdtree.cpp:733, :765
+      if (METRIC == DRRT_METRIC_EUCLID || walk_reaches(Q.t, nt, Q.r, id, gate)) {
+        *dout = d;
+        return true;
+      }
+    }
+  }
+  if (Q.has_ghost && (s < B.s_band || !(nt >= B.nlo && nt <= B.nhi))) {
+    double s2 = metric_sum<METRIC>(Q.x, Q.y, Q.gt, nx, ny, nt);
+    if (s2 < Q.s_hi) {
+      double d = sqrt(s2);
+      if (d < Q.r && (METRIC == DRRT_METRIC_EUCLID || walk_reaches(Q.gt, nt, Q.r, id, gate))) {
+        *dout = d;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
+  constexpr int T = CTA_T, WARPS = CTA_WARPS, STAGE = CTA_STAGE, UNR = CTA_UNR;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sdist = reinterpret_cast<double *>(smem_raw + CTA_OFF_DIST);
+  int32_t *sid = reinterpret_cast<int32_t *>(smem_raw + CTA_OFF_ID);
+  unsigned *hist = reinterpret_cast<unsigned *>(smem_raw + CTA_OFF_HIST);
+  uint16_t *wstart = reinterpret_cast<uint16_t *>(smem_raw + CTA_OFF_WSTART);
+  uint16_t *tmp = reinterpret_cast<uint16_t *>(smem_raw + CTA_OFF_TMP);
+  uint8_t *srank = reinterpret_cast<uint8_t *>(smem_raw + CTA_OFF_RANK);
+  int2 *runs = reinterpret_cast<int2 *>(smem_raw + CTA_OFF_RUNS);
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + CTA_OFF_HIST);
+  __shared__ int s_vb, s_count, s_crowded;
+  __shared__ long long s_base;
+  __shared__ long long s_tmp[WARPS];
+  __shared__ int s_wsum[WARPS];
+  __shared__ Query s_query;
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) {
+    s_vb = atomicAdd(A.ticket, 1);
+    s_count = 0;
+    s_crowded = 0;
+  }
+  for (int i = tid; i < CTA_NW / 4; i += T) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  const int vb = s_vb;
+  const int64_t qi = vb;
+  if (qi >= A.nq) return;  // uniform
+  const GridView &V = A.V;
+  if (w == 0) {
+    Query Q0;
+    setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
+                        A.radius ? A.radius[qi] : A.radius_all, Q0);
+    if (lane == 0) s_query = Q0;
+  }
+  __syncthreads();
+  const Query Q = s_query;
+  const GhostBand GB = ghost_band<METRIC>(Q);
+  // id bucket = id >> shift, at most CTA_NB buckets over the ids of the store
+  int shift = 0;
+  {
+    unsigned top = (unsigned)(V.n > 0 ? V.n - 1 : 0);
+    int bits = 32 - __clz(top | 1u);
+    shift = max(0, bits - 14);
+  }
+  const unsigned ltmask = (1u << lane) - 1u;
+  int32_t *gids = nullptr;
+  double *gdist = nullptr;
+
+  auto visit = [&](const bool *valid, const double *nx, const double *ny, const double *nt,
+                   const int32_t *id) {
+    bool hit[UNR];
+    double d[UNR];
+    unsigned m[UNR];
+    int tot = 0;
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      d[u] = 0.0;
+      hit[u] = valid[u] && eval_candidate2<METRIC>(Q, GB, nx[u], ny[u], nt[u], id[u], V.gate, &d[u]);
+      m[u] = __ballot_sync(0xffffffffu, hit[u]);
+      tot += __popc(m[u]);
+    }
+    if (tot == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_count, tot);
+    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      if (hit[u]) {
+        const int slot = base + __popc(m[u] & ltmask);
+        if (gids) {
+          gids[slot] = id[u];
+          gdist[slot] = d[u];
+        } else if (slot < STAGE) {
+          sid[slot] = id[u];
+          sdist[slot] = d[u];
+          const unsigned b = (unsigned)id[u] >> shift;
+          const int sh = (b & 3u) * 8;
+          const unsigned old = atomicAdd(&hist[b >> 2], 1u << sh);
+          const unsigned rank = (old >> sh) & 0xffu;
+          srank[slot] = (uint8_t)rank;
+          if (rank >= CTA_CROWDED) s_crowded = 1;
+        }
+      }
+      base += __popc(m[u]);
+    }
+  };
+  auto scan_all = [&]() {
+    if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit);
+    scan_tail_cta<WARPS, UNR>(V, visit);
+  };
+  scan_all();
+  __syncthreads();
+
+  const int n = s_count;
+  if (tid == 0) lookback_publish(A.desc, vb, (long long)n);
+  const bool staged = n > 0 && n <= STAGE;
+  const bool crowded = s_crowded != 0;
+  if (staged && !crowded) {
+    // bucket starts: prefix sum over the byte counters, eight words per thread
+    uint4 a = reinterpret_cast<const uint4 *>(hist)[2 * tid], b4 = reinterpret_cast<const uint4 *>(hist)[2 * tid + 1];
+    unsigned wv[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+    int cnt[8], sum = 0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) { cnt[e] = (int)__dp4a(wv[e], 0x01010101u, 0u); sum += cnt[e]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wsum[w] = inc;
+    __syncthreads();
+    int excl = inc - sum;
+#pragma unroll
+    for (int ww = 0; ww < WARPS; ww++) excl += (ww < w) ? s_wsum[ww] : 0;
+    unsigned pk[4];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+      unsigned lo16 = (unsigned)excl; excl += cnt[e];
+      unsigned hi16 = (unsigned)excl; excl += cnt[e + 1];
+      pk[e >> 1] = lo16 | (hi16 << 16);
+    }
+    reinterpret_cast<uint4 *>(wstart)[tid] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    __syncthreads();
+    // provisional position = bucket start + arrival rank
+    for (int i = tid; i < n; i += T) {
+      const unsigned b = (unsigned)sid[i] >> shift;
+      const unsigned wd = hist[b >> 2];
+      const int sh = (b & 3u) * 8;
+      const int s0 = wstart[b >> 2] + (int)__dp4a(wd & ((1u << sh) - 1u), 0x01010101u, 0u);
+      tmp[s0 + srank[i]] = (uint16_t)i;
+    }
+  } else if (staged) {
+    // ids bunched in a few buckets: network sort of (id, slot) keys
+    int32_t mine[STAGE / T];
+    int c = 0;
+    for (int i = tid; i < n; i += T) mine[c++] = sid[i];
+    __syncthreads();
+    c = 0;
+    for (int i = tid; i < n; i += T) keys[i] = ((unsigned long long)(unsigned)mine[c++] << 32) | (unsigned)i;
+    __syncthreads();
+    sort_keys_shared<true>(keys, n, tid, T);
+  }
+  if (w == 0) {
+    long long excl = lookback_resolve(A.desc, vb, (long long)n, lane);
+    if (lane == 0) s_base = excl;
+  }
+  __syncthreads();
+  const long long my_off = s_base;
+  if (tid == 0) {
+    A.offsets[qi] = my_off;
+    if (qi == A.nq - 1) A.offsets[A.nq] = my_off + n;
+  }
+  if (n == 0) return;
+  if (my_off + n > A.cap) return;  // arena too small: the host grows it and reruns
+  int32_t *oid = A.ids + my_off;
+  double *od = A.dist + my_off;
+  if (staged && !crowded) {
+    // final position: bucket mates with a smaller id go first
+    for (int p = tid; p < n; p += T) {
+      const int slot = tmp[p];
+      const int32_t id = sid[slot];
+      const unsigned b = (unsigned)id >> shift;
+      const unsigned wd = hist[b >> 2];
+      const int sh = (b & 3u) * 8;
+      const int c = (int)((wd >> sh) & 0xffu);
+      int fin = p;
+      if (c > 1) {
+        const int s0 = wstart[b >> 2] + (int)__dp4a(wd & ((1u << sh) - 1u), 0x01010101u, 0u);
+        fin = s0;
+        for (int m = 0; m < c; m++) fin += (sid[tmp[s0 + m]] < id) ? 1 : 0;
+      }
+      oid[fin] = id;
+      od[fin] = sdist[slot];
+    }
+  } else if (staged) {
+    for (int p = tid; p < n; p += T) {
+      const unsigned long long k = keys[p];
+      oid[p] = (int32_t)(k >> 32);
+      od[p] = sdist[(unsigned)(k & 0xffffu)];
+    }
+  } else {
+    // more hits than the staging area: second pass straight into the arena
+    __syncthreads();
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    gids = oid;
+    gdist = od;
+    scan_all();
+    __syncthreads();
+    sort_pairs_global<true>(oid, od, n, tid, T);
+  }
+}
+
 template <int METRIC>
 static int launch_range(const RangeArgs &A, bool block_mode, cudaStream_t st) {
   if (block_mode) {
-    size_t smem = (size_t)BLOCK_STAGE * 18;
     static bool attr_done = false;
     if (!attr_done) {
-      DRRT_CUDA(cudaFuncSetAttribute(range_kernel<METRIC, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<METRIC>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
       attr_done = true;
     }
-    range_kernel<METRIC, true><<<(unsigned)A.nq, BLOCK_MODE_WARPS * 32, smem, st>>>(A);
+    range_cta_kernel<METRIC><<<(unsigned)A.nq, CTA_T, CTA_SMEM, st>>>(A);
   } else {
     size_t smem = (size_t)WARP_STAGE * WARP_MODE_WARPS * 18;
     unsigned nb = (unsigned)((A.nq + WARP_MODE_WARPS - 1) / WARP_MODE_WARPS);
