@@ -65,6 +65,7 @@ def run(nodes=2_000_000, batch=4096, device=0):
         e1.record()
         r = synth.shrinking_radius(hi, gamma, delta)
         res = tree.KDFindWithinRange_dev(r, batch)
+        res = tree.range_pack()  # the edge list below is built from a plain CSR
         e2.record()
         off, ids, _ = KDTree.range_result_tensors(res)
         counts = off[1:] - off[:-1]

@@ -25,7 +25,8 @@ c_i64p = C.POINTER(C.c_int64)
 
 class RangeResult(C.Structure):
     _fields_ = [("nq", C.c_int64), ("total", C.c_int64), ("offsets_dev", C.c_void_p),
-                ("ids_dev", C.c_void_p), ("dist_dev", C.c_void_p)]
+                ("ids_dev", C.c_void_p), ("dist_dev", C.c_void_p), ("counts_dev", C.c_void_p),
+                ("extent", C.c_int64), ("packed", C.c_int32)]
 
 
 class DrrtError(RuntimeError):
@@ -52,6 +53,7 @@ SIGNATURES = {
     "drrt_range_fetch": (C.c_int, [C.c_void_p, c_ip, c_dp]),
     "drrt_range_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_void_p, C.POINTER(RangeResult)]),
+    "drrt_range_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RangeResult)]),
     "drrt_nearest_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_ip, c_dp]),
     "drrt_nearest_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
@@ -98,7 +100,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.drrt_abi_version() != 1:
+        if lib.drrt_abi_version() != 2:
             raise ImportError("drrt_b200: ABI version mismatch")
         _lib = lib
     return _lib

@@ -60,11 +60,6 @@ static int download(void *dst, const void *src, size_t bytes, cudaStream_t st) {
   return DRRT_OK;
 }
 
-__global__ void counts_from_offsets(const int64_t *off, int64_t nq, int32_t *counts) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < nq) counts[i] = (int32_t)(off[i + 1] - off[i]);
-}
-
 static int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist,
                     bool nearest = false) {
   if (nq < 0 || k < 1 || (nq > 0 && (!q || !ids)))
@@ -180,6 +175,7 @@ int drrt_store_create(int device, int dims, int n_wraps, const int *wrap_dims,
   cudaError_t e = cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&S->d_pending, 64);
   if (e == cudaSuccess) e = cudaMalloc(&S->d_ticket, 64);
+  if (e == cudaSuccess) S->d_totals = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(S->d_ticket) + 16);
   if (e == cudaSuccess) e = cudaMalloc(&S->d_edge_counter, 64);
   if (e == cudaSuccess) e = cudaMalloc(&S->d_bounds, 6 * sizeof(double));
   if (e == cudaSuccess) e = cudaMallocHost(&S->h_pending, 64);
@@ -217,6 +213,8 @@ int drrt_store_destroy(drrt_store *h) {
     S->rec.release(); S->cell_start.release(); S->cell_of.release(); S->rank_in_cell.release();
     S->scan_tmp.release();
     S->r_offsets.release(); S->r_ids.release(); S->r_dist.release(); S->r_desc.release();
+    S->r_counts.release(); S->r_chunk_total.release(); S->r_chunk_base.release();
+    S->r_offsets2.release(); S->r_ids2.release(); S->r_dist2.release();
     S->q_stage.release(); S->rad_stage.release();
     S->i_stage.release(); S->i_stage2.release(); S->d_stage.release(); S->d_stage2.release();
     S->d_stage3.release(); S->b_stage.release();
@@ -329,13 +327,7 @@ int drrt_range_batch(drrt_store *h, int64_t nq, const double *q, const double *r
   }
   drrt_range_result res{};
   DRRT_CHECK(range_batch_dev(S, nq, S->q_stage.p, rad_dev, radius_all, st, &res));
-  if (nq > 0) {
-    DRRT_CHECK(S->i_stage.reserve(nq, st));
-    counts_from_offsets<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(res.offsets_dev, nq,
-                                                                      S->i_stage.p);
-    DRRT_LAUNCHED();
-    DRRT_CHECK(download(counts, S->i_stage.p, nq * sizeof(int32_t), st));
-  }
+  if (nq > 0) DRRT_CHECK(download(counts, res.counts_dev, nq * sizeof(int32_t), st));
   DRRT_CUDA(cudaStreamSynchronize(st));
   if (total) *total = res.total;
   return DRRT_OK;
@@ -346,11 +338,20 @@ int drrt_range_fetch(drrt_store *h, int32_t *ids, double *dist) {
   if (S->last_nq < 0) return set_error(DRRT_ERR_STATE, "fetch: no range batch on this handle");
   cudaStream_t st = S->stream;
   if (S->last_total > 0) {
-    if (ids) DRRT_CHECK(download(ids, S->r_ids.p, S->last_total * sizeof(int32_t), st));
-    if (dist) DRRT_CHECK(download(dist, S->r_dist.p, S->last_total * sizeof(double), st));
+    // the caller's layout is the plain CSR given by the counts
+    drrt_range_result res{};
+    DRRT_CHECK(range_pack_dev(S, st, &res));
+    if (ids) DRRT_CHECK(download(ids, res.ids_dev, S->last_total * sizeof(int32_t), st));
+    if (dist) DRRT_CHECK(download(dist, res.dist_dev, S->last_total * sizeof(double), st));
   }
   DRRT_CUDA(cudaStreamSynchronize(st));
   return DRRT_OK;
+}
+
+int drrt_range_pack(drrt_store *h, void *stream, drrt_range_result *out) {
+  ENTER(h);
+  if (!out) return set_error(DRRT_ERR_INVALID, "pack: arguments");
+  return range_pack_dev(S, pick(S, stream), out);
 }
 
 int drrt_range_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, const double *radius_dev,
@@ -509,10 +510,7 @@ int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const double *
   S->has_obstacles = saved;
   DRRT_CHECK(rc);
   if (nq > 0) {
-    DRRT_CHECK(S->i_stage.reserve(nq, st));
-    counts_from_offsets<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(res.offsets_dev, nq, S->i_stage.p);
-    DRRT_LAUNCHED();
-    DRRT_CHECK(download(counts, S->i_stage.p, nq * sizeof(int32_t), st));
+    DRRT_CHECK(download(counts, res.counts_dev, nq * sizeof(int32_t), st));
     if (lmc_dev) {
       DRRT_CHECK(download(best_parent, S->x_best.p, nq * sizeof(int32_t), st));
       if (best_cost) DRRT_CHECK(download(best_cost, S->x_best_cost.p, nq * sizeof(double), st));
@@ -530,8 +528,8 @@ int drrt_extend_fetch(drrt_store *h, int32_t *ids, double *dist, uint8_t *unsafe
   cudaStream_t st = S->stream;
   const int64_t t = S->last_extend_total;
   if (t > 0) {
-    if (ids) DRRT_CHECK(download(ids, S->r_ids.p, t * sizeof(int32_t), st));
-    if (dist) DRRT_CHECK(download(dist, S->r_dist.p, t * sizeof(double), st));
+    if (ids) DRRT_CHECK(download(ids, S->csr_ids, t * sizeof(int32_t), st));
+    if (dist) DRRT_CHECK(download(dist, S->csr_dist, t * sizeof(double), st));
     if (unsafe) DRRT_CHECK(download(unsafe, S->x_unsafe.p, 2 * t, st));
     if (length) DRRT_CHECK(download(length, S->x_len.p, 2 * t * sizeof(double), st));
   }

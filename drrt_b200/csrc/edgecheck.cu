@@ -599,7 +599,7 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   A.sid = by_id ? sid_dev : nullptr; A.eid = by_id ? eid_dev : nullptr;
   A.sx = S->x.p; A.sy = S->y.p; A.sth = S->th.p;
   if (csr) {
-    A.csr_off = S->r_offsets.p; A.csr_ids = S->r_ids.p; A.csr_q = S->csr_q; A.csr_nq = S->csr_nq;
+    A.csr_off = S->csr_off; A.csr_ids = S->csr_ids; A.csr_q = S->csr_q; A.csr_nq = S->csr_nq;
   }
   A.metric = S->metric; A.edge_kind = edge_kind;
   A.robot_radius = robot_radius; A.r_min = r_min;
@@ -684,6 +684,11 @@ int extend_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *ra
                      cudaStream_t st, drrt_range_result *rr, uint8_t **unsafe_dev, double **len_dev,
                      int32_t *best_dev, double *best_cost_dev) {
   DRRT_CHECK(range_batch_dev(S, nq, q_dev, radius_dev, radius_all, st, rr));
+  // the pair numbering below (2 edges per neighbour) runs over a plain CSR
+  DRRT_CHECK(range_pack_dev(S, st, rr));
+  S->csr_off = rr->offsets_dev;
+  S->csr_ids = rr->ids_dev;
+  S->csr_dist = rr->dist_dev;
   const int64_t total = rr->total;
   DRRT_CHECK(S->x_unsafe.reserve((size_t)(2 * total + 1), st));
   DRRT_CHECK(S->x_len.reserve((size_t)(2 * total + 1), st));

@@ -314,13 +314,16 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
     }
     if (lane == 31) tmp64[w] = inc;
     __syncthreads();
-    long long wbase = 0, all = 0;
+    // every warp scans the NWARPS warp totals with its first lanes
+    static_assert(NWARPS <= 32, "one lane per warp total");
+    long long wt = (lane < NWARPS) ? tmp64[lane] : 0, winc = wt;
 #pragma unroll
-    for (int ww = 0; ww < NWARPS; ww++) {
-      long long v = tmp64[ww];
-      if (ww < w) wbase += v;
-      all += v;
+    for (int o = 1; o < NWARPS; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
     }
+    const long long all = __shfl_sync(0xffffffffu, winc, NWARPS - 1);
+    const long long wbase = __shfl_sync(0xffffffffu, winc - wt, w);
     const long long excl64 = wbase + inc - mine;
     const int excl = (int)(excl64 & 0xffffffffll), slot = (int)(excl64 >> 32);
     const int total = (int)(all & 0xffffffffll), nent = (int)(all >> 32);

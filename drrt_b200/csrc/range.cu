@@ -27,6 +27,8 @@
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
+#include <vector>
 
 #include "gridscan.cuh"
 
@@ -49,6 +51,12 @@ struct RangeArgs {
   int64_t cap;
   unsigned long long *desc;
   int32_t *ticket;
+  int32_t *counts;
+  // CTA kernel: arena slices of CTA_CHUNK rows
+  int64_t nchunks, chunk_cap;
+  const int64_t *chunk_base;  // exact slices (rerun) or null: slice c starts at c * chunk_cap
+  int64_t *chunk_total;
+  unsigned long long *totals;  // [0] hits, [1] slices that overflowed
 };
 
 // does the reference's walk from probe theta `pt` ever evaluate node n?
@@ -423,6 +431,7 @@ range_kernel(RangeArgs A) {
     for (int i = 0; i < w; i++) my_off += s_count[i];
   if (active && tid == 0) {
     A.offsets[qi] = my_off;
+    A.counts[qi] = my_cnt;
     if (qi == A.nq - 1) A.offsets[A.nq] = my_off + my_cnt;
   }
   if (!active || my_cnt == 0) return;   // uniform per group
@@ -452,20 +461,22 @@ range_kernel(RangeArgs A) {
 // ---------------------------------------------------------------------------
 // CTA-per-query kernel (large neighbourhoods, config 2a).
 //
-// Differences from the generic kernel above, all aimed at the instruction
-// count (the kernel is issue-bound, profiles/README.md):
+// The kernel is issue- and latency-bound, not HBM-bound (profiles/README.md), so
+// everything here is about instructions and barriers per query:
+//  * persistent CTAs take CHUNKS of CTA_CHUNK consecutive queries from a ticket
+//    and write the chunk's rows back to back into the chunk's own slice of the
+//    result arena -- no ordered allocation across CTAs, hence no CTA ever waits
+//    for a predecessor (the look-back of the generic kernel cost ~15 % here).
+//    Rows are addressed by offsets[q] / counts[q]; slices are sized from the
+//    expected neighbourhood and leave unused slots between chunks.  If a chunk
+//    overflows its slice the host reruns with exact slice sizes;
 //  * the id sort is fused into the scan: a staged hit bumps a BYTE counter of
 //    its id bucket (id >> shift, 16384 buckets, four per shared-memory word) and
-//    keeps the old value as its arrival rank; after the scan one prefix sum over
-//    the 4096 words gives every bucket's start, a hit's provisional position is
-//    start + rank, and only hits sharing a bucket (~20 %) count their smaller
-//    mates.  Two passes over the hits instead of six;
-//  * the ghost probe (kdtree.cpp:807-819) is evaluated only when it can matter:
-//    for the wrap-aware metric metric(ghost,n) >= metric(q,n) up to rounding
-//    (the ghost's theta term is the unwrapped distance), so a candidate the
-//    first probe rejected by more than a rounding band cannot be admitted by
-//    the ghost; candidates the first probe reaches in range but the signed
-//    theta prune hides (walk_reaches) still take the ghost pass;
+//    keeps the old value as its arrival rank; one prefix sum over the 4096 words
+//    gives every bucket's start, a hit's position is start + rank, and the few
+//    buckets holding several hits (~20 % of the hits) are insertion-sorted;
+//  * the ghost probe (kdtree.cpp:807-819) is evaluated only when it can matter
+//    (ghost_band below);
 //  * two candidates per lane per trip, one shared counter update for both.
 static constexpr int CTA_WARPS = 16;
 static constexpr int CTA_T = CTA_WARPS * 32;
@@ -473,7 +484,8 @@ static constexpr int CTA_STAGE = 4608;  // hits staged per query
 static constexpr int CTA_NB = 16384;    // id buckets
 static constexpr int CTA_NW = CTA_NB / 4;
 static constexpr int CTA_UNR = 2;
-static constexpr int CTA_CROWDED = 128;  // a byte counter must never wrap
+static constexpr int CTA_CROWDED = 32;  // larger buckets are not insertion-sorted (bytes must not wrap)
+static constexpr int CTA_CHUNK = 8;     // consecutive queries per arena slice
 // dynamic shared memory layout (bytes)
 static constexpr int CTA_OFF_DIST = 0;
 static constexpr int CTA_OFF_ID = CTA_OFF_DIST + CTA_STAGE * 8;
@@ -482,12 +494,13 @@ static constexpr int CTA_OFF_WSTART = CTA_OFF_HIST + CTA_NW * 4;
 static constexpr int CTA_OFF_TMP = CTA_OFF_WSTART + CTA_NW * 2;
 static constexpr int CTA_OFF_RANK = CTA_OFF_TMP + CTA_STAGE * 2;
 static constexpr int CTA_OFF_RUNS = CTA_OFF_RANK + CTA_STAGE;
-static constexpr int CTA_SMEM = CTA_OFF_RUNS + (2 * CTA_T + 1) * 8 + 8;
+static constexpr int CTA_RUNS_BYTES = (2 * CTA_T + 1) * 8 + 8;
+static constexpr int CTA_CLIST_BYTES = (CTA_STAGE / 2) * 4;  // shared buckets: at most STAGE / 2
+static constexpr int CTA_SMEM = CTA_OFF_RUNS + (CTA_RUNS_BYTES > CTA_CLIST_BYTES ? CTA_RUNS_BYTES : CTA_CLIST_BYTES);
 static_assert(CTA_OFF_HIST + CTA_STAGE * 8 <= CTA_SMEM, "fallback sort keys alias the sort scratch");
 static_assert(CTA_OFF_RUNS % 8 == 0 && CTA_OFF_HIST % 16 == 0 && CTA_OFF_WSTART % 16 == 0, "alignment");
+static_assert(CTA_STAGE % CTA_T == 0, "stage is a whole number of CTA trips");
 
-// candidate test with the ghost probe taken only when it can change the answer
-//
 // Why the ghost can be skipped (wrap-aware metric, wrap point == the metric's period W):
 // with a = |q.theta - n.theta| the first probe's theta term is min(a, W - a), whose square is
 // the squared distance of a to the nearer of {0, W}; the ghost q.theta +- W sees
@@ -496,7 +509,8 @@ static_assert(CTA_OFF_RUNS % 8 == 0 && CTA_OFF_HIST % 16 == 0 && CTA_OFF_WSTART 
 // metric(ghost, n) >= metric(q, n) in exact arithmetic; in IEEE double each theta term
 // carries at most a few roundings of magnitudes <= |q.theta| + |n.theta| + 2W, which the
 // band (2^-46 relative to that magnitude, against 2^-52 roundings) covers.  Candidates
-// outside |n.theta - q.theta| <= 1.45 W or |n.theta| <= 64 always take the ghost pass.
+// outside |n.theta - q.theta| <= 1.45 W or |n.theta| <= 64 always take the ghost pass, and
+// so does a candidate the first probe finds in range but the signed prune hides.
 struct GhostBand {
   double s_band;    // first-probe squared sums at or above this cannot be rescued by the ghost
   double nlo, nhi;  // n.theta interval in which that holds
@@ -557,34 +571,17 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
   uint16_t *tmp = reinterpret_cast<uint16_t *>(smem_raw + CTA_OFF_TMP);
   uint8_t *srank = reinterpret_cast<uint8_t *>(smem_raw + CTA_OFF_RANK);
   int2 *runs = reinterpret_cast<int2 *>(smem_raw + CTA_OFF_RUNS);
+  unsigned *clist = reinterpret_cast<unsigned *>(smem_raw + CTA_OFF_RUNS);  // after the scan
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + CTA_OFF_HIST);
-  __shared__ int s_vb, s_count, s_crowded;
-  __shared__ long long s_base;
+  __shared__ long long s_chunk;
+  __shared__ int s_count, s_crowded, s_nlist;
   __shared__ long long s_tmp[WARPS];
   __shared__ int s_wsum[WARPS];
   __shared__ Query s_query;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) {
-    s_vb = atomicAdd(A.ticket, 1);
-    s_count = 0;
-    s_crowded = 0;
-  }
-  for (int i = tid; i < CTA_NW / 4; i += T) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
-  const int vb = s_vb;
-  const int64_t qi = vb;
-  if (qi >= A.nq) return;  // uniform
   const GridView &V = A.V;
-  if (w == 0) {
-    Query Q0;
-    setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
-                        A.radius ? A.radius[qi] : A.radius_all, Q0);
-    if (lane == 0) s_query = Q0;
-  }
-  __syncthreads();
-  const Query Q = s_query;
-  const GhostBand GB = ghost_band<METRIC>(Q);
+  const unsigned ltmask = (1u << lane) - 1u;
   // id bucket = id >> shift, at most CTA_NB buckets over the ids of the store
   int shift = 0;
   {
@@ -592,173 +589,233 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
     int bits = 32 - __clz(top | 1u);
     shift = max(0, bits - 14);
   }
-  const unsigned ltmask = (1u << lane) - 1u;
-  int32_t *gids = nullptr;
-  double *gdist = nullptr;
 
-  auto visit = [&](const bool *valid, const double *nx, const double *ny, const double *nt,
-                   const int32_t *id) {
-    bool hit[UNR];
-    double d[UNR];
-    unsigned m[UNR];
-    int tot = 0;
+  for (;;) {
+    __syncthreads();  // everyone is done with the previous chunk (and its s_chunk)
+    if (tid == 0) s_chunk = (long long)atomicAdd(A.ticket, 1);
+    __syncthreads();
+    const int64_t ck = s_chunk;
+    if (ck >= A.nchunks) break;
+    const int64_t base = A.chunk_base ? A.chunk_base[ck] : ck * A.chunk_cap;
+    const int64_t cap = A.chunk_base ? A.chunk_base[ck + 1] - base : A.chunk_cap;
+    const int64_t q0 = ck * CTA_CHUNK, q1 = min(A.nq, q0 + (int64_t)CTA_CHUNK);
+    int64_t run = 0;    // hits of the chunk's earlier rows
+    bool over = false;  // some row did not fit the slice
+
+    for (int64_t qi = q0; qi < q1; qi++) {
+      if (tid == 0) { s_count = 0; s_crowded = 0; s_nlist = 0; }
+      for (int i = tid; i < CTA_NW / 4; i += T) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
+      if (w == 0) {
+        Query Q0;
+        setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
+                            A.radius ? A.radius[qi] : A.radius_all, Q0);
+        if (lane == 0) s_query = Q0;
+      }
+      __syncthreads();
+      const Query Q = s_query;
+      const GhostBand GB = ghost_band<METRIC>(Q);
+      int32_t *gids = nullptr;
+      double *gdist = nullptr;
+
+      auto visit_impl = [&](auto direct_tag, const bool *valid, const double *nx, const double *ny,
+                            const double *nt, const int32_t *id) {
+        constexpr bool DIRECT = decltype(direct_tag)::value;
+        bool hit[UNR];
+        double d[UNR];
+        unsigned m[UNR];
+        int tot = 0;
 #pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      d[u] = 0.0;
-      hit[u] = valid[u] && eval_candidate2<METRIC>(Q, GB, nx[u], ny[u], nt[u], id[u], V.gate, &d[u]);
-      m[u] = __ballot_sync(0xffffffffu, hit[u]);
-      tot += __popc(m[u]);
-    }
-    if (tot == 0) return;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&s_count, tot);
-    base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      if (hit[u]) {
-        const int slot = base + __popc(m[u] & ltmask);
-        if (gids) {
-          gids[slot] = id[u];
-          gdist[slot] = d[u];
-        } else if (slot < STAGE) {
-          sid[slot] = id[u];
-          sdist[slot] = d[u];
-          const unsigned b = (unsigned)id[u] >> shift;
-          const int sh = (b & 3u) * 8;
-          const unsigned old = atomicAdd(&hist[b >> 2], 1u << sh);
-          const unsigned rank = (old >> sh) & 0xffu;
-          srank[slot] = (uint8_t)rank;
-          if (rank >= CTA_CROWDED) s_crowded = 1;
+        for (int u = 0; u < UNR; u++) {
+          d[u] = 0.0;
+          hit[u] = valid[u] && eval_candidate2<METRIC>(Q, GB, nx[u], ny[u], nt[u], id[u], V.gate, &d[u]);
+          m[u] = __ballot_sync(0xffffffffu, hit[u]);
+          tot += __popc(m[u]);
         }
-      }
-      base += __popc(m[u]);
-    }
-  };
-  auto scan_all = [&]() {
-    if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit);
-    scan_tail_cta<WARPS, UNR>(V, visit);
-  };
-  scan_all();
-  __syncthreads();
+        if (tot == 0) return;
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(&s_count, tot);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          if (hit[u]) {
+            const int slot = pos + __popc(m[u] & ltmask);
+            if (DIRECT) {
+              gids[slot] = id[u];
+              gdist[slot] = d[u];
+            } else if (slot < STAGE) {
+              sid[slot] = id[u];
+              sdist[slot] = d[u];
+              const unsigned b = (unsigned)id[u] >> shift;
+              const int sh = (b & 3u) * 8;
+              const unsigned old = atomicAdd(&hist[b >> 2], 1u << sh);
+              const unsigned rank = (old >> sh) & 0xffu;
+              srank[slot] = (uint8_t)rank;
+              if (rank >= CTA_CROWDED) s_crowded = 1;
+            }
+          }
+          pos += __popc(m[u]);
+        }
+      };
+      auto visit = [&](const bool *valid, const double *nx, const double *ny, const double *nt,
+                       const int32_t *id) { visit_impl(std::false_type{}, valid, nx, ny, nt, id); };
+      auto visit_direct = [&](const bool *valid, const double *nx, const double *ny,
+                              const double *nt, const int32_t *id) {
+        visit_impl(std::true_type{}, valid, nx, ny, nt, id);
+      };
 
-  const int n = s_count;
-  if (tid == 0) lookback_publish(A.desc, vb, (long long)n);
-  const bool staged = n > 0 && n <= STAGE;
-  const bool crowded = s_crowded != 0;
-  if (staged && !crowded) {
-    // bucket starts: prefix sum over the byte counters, eight words per thread
-    uint4 a = reinterpret_cast<const uint4 *>(hist)[2 * tid], b4 = reinterpret_cast<const uint4 *>(hist)[2 * tid + 1];
-    unsigned wv[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
-    int cnt[8], sum = 0;
-#pragma unroll
-    for (int e = 0; e < 8; e++) { cnt[e] = (int)__dp4a(wv[e], 0x01010101u, 0u); sum += cnt[e]; }
-    int inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_wsum[w] = inc;
-    __syncthreads();
-    int excl = inc - sum;
-#pragma unroll
-    for (int ww = 0; ww < WARPS; ww++) excl += (ww < w) ? s_wsum[ww] : 0;
-    unsigned pk[4];
-#pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      unsigned lo16 = (unsigned)excl; excl += cnt[e];
-      unsigned hi16 = (unsigned)excl; excl += cnt[e + 1];
-      pk[e >> 1] = lo16 | (hi16 << 16);
-    }
-    reinterpret_cast<uint4 *>(wstart)[tid] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    __syncthreads();
-    // provisional position = bucket start + arrival rank
-    for (int i = tid; i < n; i += T) {
-      const unsigned b = (unsigned)sid[i] >> shift;
-      const unsigned wd = hist[b >> 2];
-      const int sh = (b & 3u) * 8;
-      const int s0 = wstart[b >> 2] + (int)__dp4a(wd & ((1u << sh) - 1u), 0x01010101u, 0u);
-      tmp[s0 + srank[i]] = (uint16_t)i;
-    }
-  } else if (staged) {
-    // ids bunched in a few buckets: network sort of (id, slot) keys
-    int32_t mine[STAGE / T];
-    int c = 0;
-    for (int i = tid; i < n; i += T) mine[c++] = sid[i];
-    __syncthreads();
-    c = 0;
-    for (int i = tid; i < n; i += T) keys[i] = ((unsigned long long)(unsigned)mine[c++] << 32) | (unsigned)i;
-    __syncthreads();
-    sort_keys_shared<true>(keys, n, tid, T);
-  }
-  if (w == 0) {
-    long long excl = lookback_resolve(A.desc, vb, (long long)n, lane);
-    if (lane == 0) s_base = excl;
-  }
-  __syncthreads();
-  const long long my_off = s_base;
-  if (tid == 0) {
-    A.offsets[qi] = my_off;
-    if (qi == A.nq - 1) A.offsets[A.nq] = my_off + n;
-  }
-  if (n == 0) return;
-  if (my_off + n > A.cap) return;  // arena too small: the host grows it and reruns
-  int32_t *oid = A.ids + my_off;
-  double *od = A.dist + my_off;
-  if (staged && !crowded) {
-    // final position: bucket mates with a smaller id go first
-    for (int p = tid; p < n; p += T) {
-      const int slot = tmp[p];
-      const int32_t id = sid[slot];
-      const unsigned b = (unsigned)id >> shift;
-      const unsigned wd = hist[b >> 2];
-      const int sh = (b & 3u) * 8;
-      const int c = (int)((wd >> sh) & 0xffu);
-      int fin = p;
-      if (c > 1) {
-        const int s0 = wstart[b >> 2] + (int)__dp4a(wd & ((1u << sh) - 1u), 0x01010101u, 0u);
-        fin = s0;
-        for (int m = 0; m < c; m++) fin += (sid[tmp[s0 + m]] < id) ? 1 : 0;
+      if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit);
+      scan_tail_cta<WARPS, UNR>(V, visit);
+      __syncthreads();
+
+      const int n = s_count;
+      const bool staged = n > 0 && n <= STAGE;
+      const bool crowded = s_crowded != 0;
+      const bool fits = run + n <= cap;
+      if (tid == 0) {
+        A.offsets[qi] = base + run;
+        A.counts[qi] = n;
+        if (qi == A.nq - 1) A.offsets[A.nq] = base + run + n;
       }
-      oid[fin] = id;
-      od[fin] = sdist[slot];
+      int32_t *oid = A.ids + base + run;
+      double *od = A.dist + base + run;
+      if (!fits) {
+        over = true;  // counted, not written: the host reruns with exact slices
+      } else if (staged && !crowded) {
+        // bucket starts: prefix sum over the byte counters, eight words per thread
+        uint4 a = reinterpret_cast<const uint4 *>(hist)[2 * tid];
+        uint4 b4 = reinterpret_cast<const uint4 *>(hist)[2 * tid + 1];
+        unsigned wv[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+        int cnt[8], sum = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) { cnt[e] = (int)__dp4a(wv[e], 0x01010101u, 0u); sum += cnt[e]; }
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_wsum[w] = inc;
+        __syncthreads();
+        int wsv = (lane < WARPS) ? s_wsum[lane] : 0, wsi = wsv;
+#pragma unroll
+        for (int o = 1; o < WARPS; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, wsi, o);
+          if (lane >= o) wsi += t;
+        }
+        int excl = inc - sum + __shfl_sync(0xffffffffu, wsi - wsv, w);
+        unsigned pk[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          unsigned lo16 = (unsigned)excl; excl += cnt[e];
+          unsigned hi16 = (unsigned)excl; excl += cnt[e + 1];
+          pk[e >> 1] = lo16 | (hi16 << 16);
+        }
+        reinterpret_cast<uint4 *>(wstart)[tid] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        __syncthreads();
+        // position = bucket start + arrival rank; buckets holding several hits are listed
+        // (by their first arrival) and put in id order below
+        for (int i0 = 0; i0 < n; i0 += T) {
+          const int i = i0 + tid;
+          bool listed = false;
+          unsigned ent = 0;
+          if (i < n) {
+            const unsigned b = (unsigned)sid[i] >> shift;
+            const unsigned wd = hist[b >> 2];
+            const int sh = (b & 3u) * 8;
+            const int s0 = wstart[b >> 2] + (int)__dp4a(wd & ((1u << sh) - 1u), 0x01010101u, 0u);
+            const unsigned r = srank[i];
+            tmp[s0 + r] = (uint16_t)i;
+            const unsigned c = (wd >> sh) & 0xffu;
+            listed = c > 1 && r == 0;
+            ent = (unsigned)s0 | (c << 16);
+          }
+          const unsigned lm = __ballot_sync(0xffffffffu, listed);
+          if (lm) {
+            int lb = 0;
+            if (lane == 0) lb = atomicAdd(&s_nlist, __popc(lm));
+            lb = __shfl_sync(0xffffffffu, lb, 0);
+            if (listed) clist[lb + __popc(lm & ltmask)] = ent;
+          }
+        }
+        __syncthreads();
+        const int nl = s_nlist;
+        for (int e = tid; e < nl; e += T) {
+          const unsigned ent = clist[e];
+          const int s0 = (int)(ent & 0xffffu), c = (int)(ent >> 16);
+          for (int a2 = 1; a2 < c; a2++) {
+            const uint16_t slot = tmp[s0 + a2];
+            const int32_t kid = sid[slot];
+            int j = a2 - 1;
+            while (j >= 0) {
+              const uint16_t sj = tmp[s0 + j];
+              if (sid[sj] <= kid) break;
+              tmp[s0 + j + 1] = sj;
+              j--;
+            }
+            tmp[s0 + j + 1] = slot;
+          }
+        }
+        __syncthreads();
+        for (int p = tid; p < n; p += T) {
+          const int slot = tmp[p];
+          oid[p] = sid[slot];
+          od[p] = sdist[slot];
+        }
+      } else if (staged) {
+        // ids bunched in a few buckets: network sort of (id, slot) keys
+        for (int i = tid; i < n; i += T) keys[i] = ((unsigned long long)(unsigned)sid[i] << 32) | (unsigned)i;
+        __syncthreads();
+        sort_keys_shared<true>(keys, n, tid, T);
+        for (int p = tid; p < n; p += T) {
+          const unsigned long long k = keys[p];
+          oid[p] = (int32_t)(k >> 32);
+          od[p] = sdist[(unsigned)(k & 0xffffu)];
+        }
+      } else if (n > 0) {
+        // more hits than the staging area: second pass straight into the arena
+        __syncthreads();
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        gids = oid;
+        gdist = od;
+        if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit_direct);
+        scan_tail_cta<WARPS, UNR>(V, visit_direct);
+        __syncthreads();
+        sort_pairs_global<true>(oid, od, n, tid, T);
+      }
+      run += n;
+      __syncthreads();  // staging and scratch are free for the next query
     }
-  } else if (staged) {
-    for (int p = tid; p < n; p += T) {
-      const unsigned long long k = keys[p];
-      oid[p] = (int32_t)(k >> 32);
-      od[p] = sdist[(unsigned)(k & 0xffffu)];
+    if (tid == 0) {
+      A.chunk_total[ck] = run;
+      atomicAdd(&A.totals[0], (unsigned long long)run);
+      if (over) atomicAdd(&A.totals[1], 1ull);
     }
-  } else {
-    // more hits than the staging area: second pass straight into the arena
-    __syncthreads();
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-    gids = oid;
-    gdist = od;
-    scan_all();
-    __syncthreads();
-    sort_pairs_global<true>(oid, od, n, tid, T);
   }
 }
 
-template <int METRIC>
-static int launch_range(const RangeArgs &A, bool block_mode, cudaStream_t st) {
-  if (block_mode) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<METRIC>,
+static int cta_kernel_grid(int metric, int *grid) {
+  static int per_sm[2] = {0, 0}, sms = 0;
+  const int mi = metric == DRRT_METRIC_EUCLID ? 1 : 0;
+  if (!per_sm[mi]) {
+    int dev = 0, v = 0;
+    DRRT_CUDA(cudaGetDevice(&dev));
+    DRRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (mi) {
+      DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<DRRT_METRIC_EUCLID>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
-      attr_done = true;
+      DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &v, range_cta_kernel<DRRT_METRIC_EUCLID>, CTA_T, CTA_SMEM));
+    } else {
+      DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<DRRT_METRIC_R2S1_WRAP>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
+      DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &v, range_cta_kernel<DRRT_METRIC_R2S1_WRAP>, CTA_T, CTA_SMEM));
     }
-    range_cta_kernel<METRIC><<<(unsigned)A.nq, CTA_T, CTA_SMEM, st>>>(A);
-  } else {
-    size_t smem = (size_t)WARP_STAGE * WARP_MODE_WARPS * 18;
-    unsigned nb = (unsigned)((A.nq + WARP_MODE_WARPS - 1) / WARP_MODE_WARPS);
-    range_kernel<METRIC, false><<<nb, WARP_MODE_WARPS * 32, smem, st>>>(A);
+    if (v < 1) return set_error(DRRT_ERR_CUDA, "range: CTA kernel does not fit an SM");
+    per_sm[mi] = v;
   }
-  DRRT_LAUNCHED();
-  DRRT_CUDA(cudaGetLastError());
+  *grid = per_sm[mi] * sms;
   return DRRT_OK;
 }
 
@@ -773,17 +830,105 @@ __global__ void max_radius_kernel(const double *r, int64_t n, unsigned long long
   if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
+// ---------------------------------------------------------------------------
+// packing: rows of a sliced result -> plain CSR (exclusive prefix sum of counts)
+
+// single CTA; out[0..n] = exclusive prefix sums of counts (out[n] = total)
+__global__ void scan_counts_kernel(const int32_t *counts, int64_t n, int64_t *out) {
+  constexpr int T = 1024;
+  __shared__ long long s_w[32];
+  __shared__ long long s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t b = 0; b < n; b += T) {
+    const int64_t i = b + tid;
+    long long v = i < n ? (long long)counts[i] : 0, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    long long wv = s_w[lane], wi = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    const long long carry = s_carry;
+    const long long excl = carry + __shfl_sync(0xffffffffu, wi - wv, w) + inc - v;
+    if (i < n) out[i] = excl;
+    __syncthreads();
+    if (tid == T - 1) s_carry = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) out[n] = s_carry;
+}
+
+__global__ void pack_rows_kernel(int64_t nq, const int64_t *src_off, const int32_t *counts,
+                                 const int64_t *dst_off, const int32_t *ids, const double *dist,
+                                 int32_t *ids_out, double *dist_out) {
+  for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+    const int64_t s = src_off[q], d = dst_off[q];
+    const int c = counts[q];
+    for (int i = threadIdx.x; i < c; i += blockDim.x) {
+      ids_out[d + i] = ids[s + i];
+      dist_out[d + i] = dist[s + i];
+    }
+  }
+}
+
+static void fill_result(Store *S, drrt_range_result *out) {
+  if (!out) return;
+  out->nq = S->last_nq;
+  out->total = S->last_total;
+  out->offsets_dev = S->last_packed_in_alt ? S->r_offsets2.p : S->r_offsets.p;
+  out->ids_dev = S->last_packed_in_alt ? S->r_ids2.p : S->r_ids.p;
+  out->dist_dev = S->last_packed_in_alt ? S->r_dist2.p : S->r_dist.p;
+  out->counts_dev = S->r_counts.p;
+  out->packed = (S->last_packed || S->last_packed_in_alt) ? 1 : 0;
+  out->extent = out->packed ? S->last_total : S->last_extent;
+}
+
+// Makes the last result a plain CSR (rows back to back in query order).
+int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out) {
+  if (S->last_nq < 0) return set_error(DRRT_ERR_STATE, "pack: no range batch on this handle");
+  if (!S->last_packed && !S->last_packed_in_alt && S->last_nq > 0) {
+    const int64_t nq = S->last_nq;
+    DRRT_CHECK(S->r_offsets2.reserve(nq + 1, st));
+    DRRT_CHECK(S->r_ids2.reserve(S->last_total + 1, st));
+    DRRT_CHECK(S->r_dist2.reserve(S->last_total + 1, st));
+    scan_counts_kernel<<<1, 1024, 0, st>>>(S->r_counts.p, nq, S->r_offsets2.p);
+    DRRT_LAUNCHED();
+    pack_rows_kernel<<<(unsigned)std::min<int64_t>(nq, 148 * 16), 256, 0, st>>>(
+        nq, S->r_offsets.p, S->r_counts.p, S->r_offsets2.p, S->r_ids.p, S->r_dist.p, S->r_ids2.p,
+        S->r_dist2.p);
+    DRRT_LAUNCHED();
+    DRRT_CUDA(cudaGetLastError());
+    S->last_packed_in_alt = true;
+  }
+  fill_result(S, out);
+  return DRRT_OK;
+}
+
 int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *radius_dev,
                     double radius_all, cudaStream_t st, drrt_range_result *out) {
   if (nq < 0) return set_error(DRRT_ERR_INVALID, "range: nq < 0");
   if (nq > 0x7ffffff0) return set_error(DRRT_ERR_INVALID, "range: nq too large");
   S->last_nq = -1;
+  S->last_packed = true;
+  S->last_packed_in_alt = false;
   DRRT_CHECK(S->r_offsets.reserve(nq + 1, st));
+  DRRT_CHECK(S->r_counts.reserve(nq + 1, st));
   if (nq == 0 || S->n == 0) {
     DRRT_CUDA(cudaMemsetAsync(S->r_offsets.p, 0, (nq + 1) * sizeof(int64_t), st));
+    DRRT_CUDA(cudaMemsetAsync(S->r_counts.p, 0, (nq + 1) * sizeof(int32_t), st));
     S->last_nq = nq;
     S->last_total = 0;
-    if (out) *out = drrt_range_result{nq, 0, S->r_offsets.p, S->r_ids.p, S->r_dist.p};
+    S->last_extent = 0;
+    fill_result(S, out);
     return DRRT_OK;
   }
   DRRT_CHECK(ensure_index(S, nq, st));
@@ -805,28 +950,91 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
     double ball = 4.18879 * rmax * rmax * rmax;
     expected = std::min((double)S->n, (double)S->n * ball / std::max(vol, 1e-300));
   }
-  bool block_mode = expected > WARP_STAGE / 2;
+  const bool block_mode = expected > WARP_STAGE / 2;
 
-  int64_t nvb = block_mode ? nq : (nq + WARP_MODE_WARPS - 1) / WARP_MODE_WARPS;
+  RangeArgs A{};
+  A.V = make_view(S);
+  A.q = q_dev; A.radius = radius_dev; A.radius_all = radius_all; A.nq = nq;
+  A.offsets = S->r_offsets.p; A.counts = S->r_counts.p; A.ticket = S->d_ticket;
+
+  if (block_mode) {
+    // slices of CTA_CHUNK rows, sized from the expected neighbourhood
+    const int64_t nchunks = (nq + CTA_CHUNK - 1) / CTA_CHUNK;
+    int64_t rowcap = (int64_t)(expected * 1.1 + 6.0 * sqrt(expected) + 64.0);
+    rowcap = std::min<int64_t>(rowcap, S->n);
+    DRRT_CHECK(S->r_chunk_total.reserve(nchunks + 1, st));
+    A.nchunks = nchunks;
+    A.chunk_cap = rowcap * CTA_CHUNK;
+    A.chunk_base = nullptr;
+    A.chunk_total = S->r_chunk_total.p;
+    A.totals = (unsigned long long *)S->d_totals;
+    int grid = 0;
+    DRRT_CHECK(cta_kernel_grid(S->metric, &grid));
+    grid = (int)std::min<int64_t>(grid, nchunks);
+    int64_t extent = nchunks * A.chunk_cap;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      DRRT_CHECK(S->r_ids.reserve(extent + 1, st));
+      DRRT_CHECK(S->r_dist.reserve(extent + 1, st));
+      A.ids = S->r_ids.p; A.dist = S->r_dist.p;
+      DRRT_CUDA(cudaMemsetAsync(S->d_ticket, 0, sizeof(int32_t), st));
+      DRRT_CUDA(cudaMemsetAsync(S->d_totals, 0, 2 * sizeof(unsigned long long), st));
+      if (S->metric == DRRT_METRIC_EUCLID)
+        range_cta_kernel<DRRT_METRIC_EUCLID><<<grid, CTA_T, CTA_SMEM, st>>>(A);
+      else
+        range_cta_kernel<DRRT_METRIC_R2S1_WRAP><<<grid, CTA_T, CTA_SMEM, st>>>(A);
+      DRRT_LAUNCHED();
+      DRRT_CUDA(cudaGetLastError());
+      DRRT_CUDA(cudaMemcpyAsync(S->h_scalar, S->d_totals, 2 * sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, st));
+      DRRT_CUDA(cudaStreamSynchronize(st));
+      const int64_t total = S->h_scalar[0], overflowed = S->h_scalar[1];
+      if (overflowed == 0) {
+        S->last_nq = nq;
+        S->last_total = total;
+        S->last_extent = extent;
+        S->last_packed = A.chunk_base != nullptr;
+        fill_result(S, out);
+        return DRRT_OK;
+      }
+      if (attempt == 1) break;
+      // some slice was too small: the counts are exact, rerun with exact slices
+      std::vector<int64_t> tot((size_t)nchunks), cb((size_t)nchunks + 1);
+      DRRT_CUDA(cudaMemcpyAsync(tot.data(), S->r_chunk_total.p, nchunks * sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, st));
+      DRRT_CUDA(cudaStreamSynchronize(st));
+      cb[0] = 0;
+      for (int64_t c = 0; c < nchunks; c++) cb[c + 1] = cb[c] + tot[c];
+      DRRT_CHECK(S->r_chunk_base.reserve(nchunks + 1, st));
+      DRRT_CUDA(cudaMemcpyAsync(S->r_chunk_base.p, cb.data(), (nchunks + 1) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, st));
+      DRRT_CUDA(cudaStreamSynchronize(st));
+      A.chunk_base = S->r_chunk_base.p;
+      extent = cb[nchunks];
+    }
+    return set_error(DRRT_ERR_STATE, "range: result slices did not converge");
+  }
+
+  // warp-per-query kernel: ordered allocation in the kernel, plain CSR
+  const int64_t nvb = (nq + WARP_MODE_WARPS - 1) / WARP_MODE_WARPS;
   DRRT_CHECK(S->r_desc.reserve(nvb, st));
   int64_t guess = (int64_t)std::min(1.0e12, expected * 1.3 * (double)nq) + 1024;
   if ((int64_t)S->r_ids.cap < guess) {
     DRRT_CHECK(S->r_ids.reserve(guess, st));
     DRRT_CHECK(S->r_dist.reserve(guess, st));
   }
-
-  RangeArgs A{};
-  A.V = make_view(S);
-  A.q = q_dev; A.radius = radius_dev; A.radius_all = radius_all; A.nq = nq;
-  A.offsets = S->r_offsets.p; A.desc = S->r_desc.p; A.ticket = S->d_ticket;
-
+  A.desc = S->r_desc.p;
   for (int attempt = 0; attempt < 3; attempt++) {
     A.ids = S->r_ids.p; A.dist = S->r_dist.p;
     A.cap = (int64_t)std::min(S->r_ids.cap, S->r_dist.cap);
     DRRT_CUDA(cudaMemsetAsync(S->r_desc.p, 0, nvb * sizeof(unsigned long long), st));
     DRRT_CUDA(cudaMemsetAsync(S->d_ticket, 0, sizeof(int32_t), st));
-    if (S->metric == DRRT_METRIC_EUCLID) DRRT_CHECK(launch_range<DRRT_METRIC_EUCLID>(A, block_mode, st));
-    else DRRT_CHECK(launch_range<DRRT_METRIC_R2S1_WRAP>(A, block_mode, st));
+    const size_t smem = (size_t)WARP_STAGE * WARP_MODE_WARPS * 18;
+    if (S->metric == DRRT_METRIC_EUCLID)
+      range_kernel<DRRT_METRIC_EUCLID, false><<<(unsigned)nvb, WARP_MODE_WARPS * 32, smem, st>>>(A);
+    else
+      range_kernel<DRRT_METRIC_R2S1_WRAP, false><<<(unsigned)nvb, WARP_MODE_WARPS * 32, smem, st>>>(A);
+    DRRT_LAUNCHED();
+    DRRT_CUDA(cudaGetLastError());
     DRRT_CUDA(cudaMemcpyAsync(S->h_scalar, S->r_offsets.p + nq, sizeof(int64_t),
                               cudaMemcpyDeviceToHost, st));
     DRRT_CUDA(cudaStreamSynchronize(st));
@@ -834,7 +1042,9 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
     if (total <= A.cap) {
       S->last_nq = nq;
       S->last_total = total;
-      if (out) *out = drrt_range_result{nq, total, S->r_offsets.p, S->r_ids.p, S->r_dist.p};
+      S->last_extent = total;
+      S->last_packed = true;
+      fill_result(S, out);
       return DRRT_OK;
     }
     DRRT_CHECK(S->r_ids.reserve(total + total / 8 + 1024, st));

@@ -68,10 +68,19 @@ struct Store {
   DevBuf<int64_t> r_offsets;  // nq+1
   DevBuf<int32_t> r_ids;
   DevBuf<double> r_dist;
-  DevBuf<unsigned long long> r_desc;  // look-back descriptors
+  DevBuf<unsigned long long> r_desc;  // look-back descriptors (warp-per-query kernel)
+  DevBuf<int32_t> r_counts;           // nq
+  DevBuf<int64_t> r_chunk_total, r_chunk_base;  // CTA kernel: per-slice hit totals / exact slice starts
+  // plain-CSR copy of a sliced result (range_pack_dev)
+  DevBuf<int64_t> r_offsets2;
+  DevBuf<int32_t> r_ids2;
+  DevBuf<double> r_dist2;
   DevBuf<double> q_stage, rad_stage;
   int32_t *d_ticket = nullptr;
-  int64_t last_nq = -1, last_total = 0;
+  unsigned long long *d_totals = nullptr;  // inside the d_ticket allocation
+  int64_t last_nq = -1, last_total = 0, last_extent = 0;
+  bool last_packed = true;          // the primary arena is a plain CSR
+  bool last_packed_in_alt = false;  // a packed copy exists in r_*2
   int64_t *h_scalar = nullptr;  // pinned scratch (8 x i64)
 
   // generic staging for host entry points
@@ -100,6 +109,9 @@ struct Store {
   DevBuf<int32_t> x_best;
   DevBuf<double> x_best_cost;
   const double *csr_q = nullptr;
+  const int64_t *csr_off = nullptr;
+  const int32_t *csr_ids = nullptr;
+  const double *csr_dist = nullptr;
   int64_t csr_nq = 0;
   int64_t last_extend_total = -1;
   // solved Dubins paths handed from the solve kernel to the walk kernel
@@ -121,6 +133,7 @@ int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, DevBuf<int32_
 // range.cu
 int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *radius_dev,
                     double radius_all, cudaStream_t st, drrt_range_result *out);
+int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out);
 // knn.cu
 int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
                   double *dist_dev, cudaStream_t st, bool nearest = false);

@@ -166,12 +166,26 @@ class KDTree:
                                              r_all, _torch_stream(), C.byref(res)))
         return res
 
+    def range_pack(self):
+        """Plain-CSR form of the last KDFindWithinRange_dev result (rows back to back,
+        offsets = exclusive prefix sum of the counts); a device-side copy when the
+        result was written in slices (res.packed == 0)."""
+        res = capi.RangeResult()
+        check(self._lib.drrt_range_pack(self._h, _torch_stream(), C.byref(res)))
+        return res
+
     @staticmethod
     def range_result_tensors(res):
-        """(offsets int64[nq+1], ids int32[total], dist f64[total]) as torch views of the
-        library-owned result of the last KDFindWithinRange_dev"""
-        return (dev_tensor(res.offsets_dev, res.nq + 1, "<i8"), dev_tensor(res.ids_dev, res.total, "<i4"),
-                dev_tensor(res.dist_dev, res.total, "<f8"))
+        """(offsets int64[nq+1], ids int32[extent], dist f64[extent]) as torch views of the
+        library-owned result of the last KDFindWithinRange_dev; row q is
+        [offsets[q], offsets[q] + counts[q]) -- see range_result_counts.  For a plain
+        CSR (extent == total) call range_pack() first."""
+        return (dev_tensor(res.offsets_dev, res.nq + 1, "<i8"), dev_tensor(res.ids_dev, res.extent, "<i4"),
+                dev_tensor(res.dist_dev, res.extent, "<f8"))
+
+    @staticmethod
+    def range_result_counts(res):
+        return dev_tensor(res.counts_dev, res.nq, "<i4")
 
     # -- KDTree::KDFindNearest kdtree.cpp:264-307
     def KDFindNearest(self, query_points):

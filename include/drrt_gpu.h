@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DRRT_ABI_VERSION 1
+#define DRRT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DRRT_API __attribute__((visibility("default")))
@@ -111,17 +111,26 @@ DRRT_API int drrt_range_fetch(drrt_store *h, int32_t *ids, double *dist);
 
 /* device-resident variant: queries/radii on the device; results stay in
  * library-owned device buffers valid until the next range call on h.
- * offsets_dev has nq+1 int64 entries. */
+ * Row q is ids_dev/dist_dev[offsets_dev[q] .. offsets_dev[q] + counts_dev[q]),
+ * rows in query order.  Large neighbourhoods are written in slices of a few
+ * consecutive rows with unused slots between slices (packed == 0); when
+ * packed == 1 the rows are back to back and offsets_dev (nq+1 entries) is the
+ * exclusive prefix sum of counts_dev, a plain CSR.  drrt_range_pack turns the
+ * last result of h into that form (one device-side copy) and returns it. */
 typedef struct {
   int64_t nq;
-  int64_t total;
-  const int64_t *offsets_dev;
+  int64_t total;               /* sum of counts */
+  const int64_t *offsets_dev;  /* nq + 1 */
   const int32_t *ids_dev;
   const double *dist_dev;
+  const int32_t *counts_dev;   /* nq */
+  int64_t extent;              /* elements of ids_dev / dist_dev the rows span */
+  int32_t packed;
 } drrt_range_result;
 DRRT_API int drrt_range_batch_dev(drrt_store *h, int64_t nq, const double *q_dev,
                          const double *radius_dev, double radius_all,
                          void *stream, drrt_range_result *out);
+DRRT_API int drrt_range_pack(drrt_store *h, void *stream, drrt_range_result *out);
 
 /* ---- nearest / k-nearest -------------------------------------------------
  * KDTree::KDFindNearest src/kdtree.cpp:264-307: id and distance of the

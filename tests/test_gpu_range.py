@@ -195,3 +195,56 @@ def test_range_signed_prune_without_wrap(drrt, po):
     t5, r5 = _pair(drrt, po, p4)
     _, ids, _ = t5.KDFindWithinRange(0.1, np.array([[10.0, 10.0, W - 0.02]]))
     assert list(ids) == [3]
+
+
+def _rows_dev(drrt, res):
+    """rows of a device-resident result as host arrays: offsets, counts, ids, dist"""
+    off, ids, dist = drrt.KDTree.range_result_tensors(res)
+    cnt = drrt.KDTree.range_result_counts(res)
+    return off.cpu().numpy(), cnt.cpu().numpy(), ids.cpu().numpy(), dist.cpu().numpy()
+
+
+def test_range_dev_sliced_rows_and_pack(drrt, po):
+    # large neighbourhoods are written in slices of consecutive rows (offsets + counts);
+    # drrt_range_pack turns the result into the plain CSR the host call returns
+    import torch
+    pos = synth.box_points(200_000, 71)
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(203, 72)           # not a multiple of the slice length
+    roff, rids, rdist = r.range_batch(q, 4.0)
+    res = t.KDFindWithinRange_dev(4.0, torch.from_numpy(q).cuda())
+    assert res.nq == len(q) and res.total == roff[-1]
+    off, cnt, ids, dist = _rows_dev(drrt, res)
+    assert np.array_equal(cnt, np.diff(roff))
+    assert (off[1:] >= off[:-1] + cnt).all() and off[-1] <= res.extent   # query order, no overlap
+    for i in range(len(q)):
+        assert np.array_equal(ids[off[i]:off[i] + cnt[i]], rids[roff[i]:roff[i + 1]])
+        assert np.array_equal(dist[off[i]:off[i] + cnt[i]], rdist[roff[i]:roff[i + 1]])
+    res2 = t.range_pack()
+    assert res2.packed == 1 and res2.extent == res2.total == roff[-1]
+    off2, cnt2, ids2, dist2 = _rows_dev(drrt, res2)
+    assert np.array_equal(off2, roff) and np.array_equal(ids2, rids) and np.array_equal(dist2, rdist)
+    # the small-neighbourhood kernel already answers with a plain CSR
+    res3 = t.KDFindWithinRange_dev(0.8, torch.from_numpy(q).cuda())
+    assert res3.packed == 1
+    off3, cnt3, ids3, _ = _rows_dev(drrt, res3)
+    soff, sids, _ = r.range_batch(q, 0.8)
+    assert np.array_equal(off3, soff) and np.array_equal(ids3, sids) and np.array_equal(cnt3, np.diff(soff))
+
+
+def test_range_slice_overflow_reruns_exact(drrt, po):
+    # a dense blob makes some slices outgrow their share of the arena: the batch is rerun
+    # with exact slice sizes and comes back as a plain CSR
+    import torch
+    pos = synth.box_points(150_000, 75)
+    rng = np.random.default_rng(76)
+    pos[20_000:26_000] = [30.0, 20.0, 1.0] + rng.normal(0, 0.25, (6000, 3))
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(120, 77)
+    q[40:80] = [30.0, 20.0, 1.0] + rng.normal(0, 0.2, (40, 3))
+    roff, rids, rdist = r.range_batch(q, 3.0)
+    res = t.KDFindWithinRange_dev(3.0, torch.from_numpy(q).cuda())
+    assert res.packed == 1 and res.total == roff[-1]
+    off, cnt, ids, dist = _rows_dev(drrt, res)
+    assert np.array_equal(off, roff) and np.array_equal(ids, rids) and np.array_equal(dist, rdist)
+    _check(t, r, q, 3.0)
