@@ -10,7 +10,6 @@
 // K1b index build: bounds -> cell id + rank (histogram) -> exclusive scan ->
 //   scatter of 32-byte NodeRec records in cell order.
 #include <math.h>
-#include <stdlib.h>
 
 #include <algorithm>
 
@@ -285,14 +284,13 @@ int rebuild_index(Store *S, cudaStream_t st) {
   double Lt = gp.periodic ? S->period : std::max(b[5] - b[4], 1e-9);
   // cubic cells holding ~2 nodes on average; the metric weighs x, y and theta
   // equally, so the neighbourhood is a ball in these units
-  const double occupancy = getenv("DRRT_EXP_OCC") ? atof(getenv("DRRT_EXP_OCC")) : 2.0;
+  const double occupancy = 2.0;
   double cells = std::max(1.0, (double)n / occupancy);
   double h = cbrt(Lx * Ly * Lt / cells);
-  const double fxy = getenv("DRRT_EXP_XYSCALE") ? atof(getenv("DRRT_EXP_XYSCALE")) : 1.0;
   for (;;) {
-    gp.nx = (int)std::min(4096.0, std::max(1.0, ceil(Lx / (h * fxy))));
-    gp.ny = (int)std::min(4096.0, std::max(1.0, ceil(Ly / (h * fxy))));
-    gp.nt = (int)std::min(1024.0, std::max(1.0, ceil(Lt / (h / (fxy * fxy)))));
+    gp.nx = (int)std::min(4096.0, std::max(1.0, ceil(Lx / h)));
+    gp.ny = (int)std::min(4096.0, std::max(1.0, ceil(Ly / h)));
+    gp.nt = (int)std::min(256.0, std::max(1.0, ceil(Lt / h)));
     if ((double)gp.nx * gp.ny * gp.nt <= 3.0e8) break;
     h *= 1.26;
   }
