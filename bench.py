@@ -382,14 +382,16 @@ def main():
                            "nodes": N_NODES, "queries_per_gpu": N_QUERIES,
                            "hits_per_query": hits_2a / N_QUERIES,
                            "l2": "flushed between timed steps (512 MiB memset, untimed)",
+                           "result": "rows in HBM, sorted by id, addressed by offsets+counts "
+                                     "(slices of 8 consecutive queries)",
                            "store": "replicated per GPU; NCCL broadcast of the insert batch"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak,
                              # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel
-                             # on this workload (ncu --set full, profiles/r01g_range_kernel.txt)
-                             "traffic": 3.556e9, "traffic_unit": "bytes/launch",
+                             # on this workload (ncu --set full, profiles/r01v3_range_cta_kernel.txt)
+                             "traffic": 3.451e9, "traffic_unit": "bytes/launch",
                              "peak_kind": peak_kind,
-                             "kernel": "range_kernel<R2S1, CTA-per-query>",
+                             "kernel": "range_cta_kernel<R2S1> (CTA per query)",
                              "algorithmic_bytes_per_launch": alg_bytes},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "extra": extra}

@@ -52,7 +52,8 @@ struct RangeArgs {
   unsigned long long *desc;
   int32_t *ticket;
   int32_t *counts;
-  // CTA kernel: arena slices of CTA_CHUNK rows
+  // CTA kernel: arena slices of chunk_len (<= CTA_CHUNK) rows
+  int chunk_len;
   int64_t nchunks, chunk_cap;
   const int64_t *chunk_base;  // exact slices (rerun) or null: slice c starts at c * chunk_cap
   int64_t *chunk_total;
@@ -485,7 +486,7 @@ static constexpr int CTA_NB = 16384;    // id buckets
 static constexpr int CTA_NW = CTA_NB / 4;
 static constexpr int CTA_UNR = 2;
 static constexpr int CTA_CROWDED = 32;  // larger buckets are not insertion-sorted (bytes must not wrap)
-static constexpr int CTA_CHUNK = 8;     // consecutive queries per arena slice
+static constexpr int CTA_CHUNK = 8;     // consecutive queries per arena slice (fewer when the batch is small)
 // dynamic shared memory layout (bytes)
 static constexpr int CTA_OFF_DIST = 0;
 static constexpr int CTA_OFF_ID = CTA_OFF_DIST + CTA_STAGE * 8;
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
     if (ck >= A.nchunks) break;
     const int64_t base = A.chunk_base ? A.chunk_base[ck] : ck * A.chunk_cap;
     const int64_t cap = A.chunk_base ? A.chunk_base[ck + 1] - base : A.chunk_cap;
-    const int64_t q0 = ck * CTA_CHUNK, q1 = min(A.nq, q0 + (int64_t)CTA_CHUNK);
+    const int64_t q0 = ck * A.chunk_len, q1 = min(A.nq, q0 + (int64_t)A.chunk_len);
     int64_t run = 0;    // hits of the chunk's earlier rows
     bool over = false;  // some row did not fit the slice
 
@@ -958,18 +959,21 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
   A.offsets = S->r_offsets.p; A.counts = S->r_counts.p; A.ticket = S->d_ticket;
 
   if (block_mode) {
-    // slices of CTA_CHUNK rows, sized from the expected neighbourhood
-    const int64_t nchunks = (nq + CTA_CHUNK - 1) / CTA_CHUNK;
+    // slices of chunk_len consecutive rows, sized from the expected neighbourhood; a small
+    // batch takes shorter slices so that every resident CTA still gets several of them
+    int grid = 0;
+    DRRT_CHECK(cta_kernel_grid(S->metric, &grid));
+    const int chunk_len = (int)std::max<int64_t>(1, std::min<int64_t>(CTA_CHUNK, nq / (4 * (int64_t)grid)));
+    const int64_t nchunks = (nq + chunk_len - 1) / chunk_len;
     int64_t rowcap = (int64_t)(expected * 1.1 + 6.0 * sqrt(expected) + 64.0);
     rowcap = std::min<int64_t>(rowcap, S->n);
     DRRT_CHECK(S->r_chunk_total.reserve(nchunks + 1, st));
+    A.chunk_len = chunk_len;
     A.nchunks = nchunks;
-    A.chunk_cap = rowcap * CTA_CHUNK;
+    A.chunk_cap = rowcap * chunk_len;
     A.chunk_base = nullptr;
     A.chunk_total = S->r_chunk_total.p;
     A.totals = (unsigned long long *)S->d_totals;
-    int grid = 0;
-    DRRT_CHECK(cta_kernel_grid(S->metric, &grid));
     grid = (int)std::min<int64_t>(grid, nchunks);
     int64_t extent = nchunks * A.chunk_cap;
     for (int attempt = 0; attempt < 2; attempt++) {
