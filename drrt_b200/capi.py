@@ -69,6 +69,13 @@ SIGNATURES = {
     "drrt_edgecheck_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                            C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "drrt_edgecheck_subset_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, c_ip, c_ip, C.c_int,
+                                              C.c_double, C.c_double, c_u8p, C.c_int32, c_u8p, c_dp]),
+    "drrt_edgecheck_subset_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                                  C.c_double, c_u8p, C.c_int32, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p]),
+    "drrt_obstacle_conflict_batch": (C.c_int, [C.c_void_p, C.c_int32, c_ip, C.c_double, c_ip, c_i64p]),
     "drrt_extend_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_double,
                                     C.c_double, C.c_int, c_dp, c_ip, c_i64p, c_ip, c_dp]),
     "drrt_extend_fetch": (C.c_int, [C.c_void_p, c_ip, c_dp, c_u8p, c_dp]),

@@ -221,7 +221,7 @@ int drrt_store_destroy(drrt_store *h) {
     S->o_kind.release(); S->o_voff.release(); S->oa_kind.release(); S->oa_voff.release();
     S->oa_live.release(); S->o_ox.release(); S->o_oy.release(); S->o_rad.release();
     S->o_vx.release(); S->o_vy.release(); S->oa_ox.release(); S->oa_oy.release();
-    S->oa_rad.release(); S->oa_vx.release(); S->oa_vy.release();
+    S->oa_rad.release(); S->oa_vx.release(); S->oa_vy.release(); S->o_mask.release();
     if (S->d_pending) cudaFree(S->d_pending);
     if (S->d_ticket) cudaFree(S->d_ticket);
     if (S->d_edge_counter) cudaFree(S->d_edge_counter);
@@ -405,6 +405,7 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
   std::vector<uint8_t> live(n_obs);
   std::vector<double> ox(n_obs), oy(n_obs), rad(radius, radius + n_obs), vx(nv_all), vy(nv_all);
   std::vector<double> aox, aoy, arad, avx, avy;
+  std::vector<int32_t> src_act;
   for (int i = 0; i <= n_obs; i++) vo_all[i] = n_obs ? vert_off[i] : 0;
   for (int v = 0; v < nv_all; v++) { vx[v] = verts_xy[2 * v]; vy[v] = verts_xy[2 * v + 1]; }
   for (int i = 0; i < n_obs; i++) {
@@ -413,6 +414,7 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
     live[i] = (used[i] && !(life_span[i] <= 0)) ? 1 : 0;  // obstacle.cpp:761
     // only a live ball or polygon can ever answer true (obstacle.cpp:781-804)
     if (live[i] && (kind[i] == 1 || kind[i] == 3)) {
+      src_act.push_back(i);
       k_act.push_back(kind[i]);
       aox.push_back(ox[i]); aoy.push_back(oy[i]); arad.push_back(rad[i]);
       for (int v = vert_off[i]; v < vert_off[i + 1]; v++) { avx.push_back(vx[v]); avy.push_back(vy[v]); }
@@ -440,7 +442,8 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
   T.a_kind = S->oa_kind.p; T.a_live = S->oa_live.p; T.a_ox = S->oa_ox.p; T.a_oy = S->oa_oy.p;
   T.a_rad = S->oa_rad.p; T.a_vert_off = S->oa_voff.p; T.a_vx = S->oa_vx.p; T.a_vy = S->oa_vy.p;
   S->h_o_ox = aox; S->h_o_oy = aoy; S->h_o_rad = arad; S->h_o_vx = avx; S->h_o_vy = avy;
-  S->h_o_kind = k_act; S->h_o_voff = vo_act;
+  S->h_o_kind = k_act; S->h_o_voff = vo_act; S->h_o_src = src_act;
+  S->h_all_ox = ox; S->h_all_oy = oy; S->h_all_rad = rad; S->h_all_kind = k_all;
   S->ogrid_radius = -1.0;  // broadphase grid is stale
   S->has_obstacles = true;
   return DRRT_OK;
@@ -472,6 +475,84 @@ int drrt_edgecheck_batch_dev(drrt_store *h, int64_t n, const double *start_dev,
   ENTER(h);
   return edgecheck_batch_dev(S, n, start_dev, end_dev, start_id_dev, end_id_dev, edge_kind,
                              robot_radius, r_min, verdict_dev, length_dev, pick(S, stream));
+}
+
+// ---- obstacle sweeps -----------------------------------
+
+// the caller's mask over the obstacle TABLE -> mask over the active (live ball / polygon) list
+static int stage_obstacle_mask(Store *S, const uint8_t *mask, int32_t n_obstacles, cudaStream_t st) {
+  if (!mask) return set_error(DRRT_ERR_INVALID, "subset check: obstacle_mask == NULL");
+  if (!S->has_obstacles || n_obstacles != S->obs.n_all)
+    return set_error(DRRT_ERR_INVALID, "subset check: mask has %d entries, the obstacle table %d",
+                     n_obstacles, S->has_obstacles ? S->obs.n_all : 0);
+  std::vector<uint8_t> act(S->h_o_src.size() + 1, 0);
+  for (size_t a = 0; a < S->h_o_src.size(); a++) act[a] = mask[S->h_o_src[a]] ? 1 : 0;
+  DRRT_CHECK(S->o_mask.reserve(act.size(), st));
+  DRRT_CUDA(cudaMemcpyAsync(S->o_mask.p, act.data(), act.size(), cudaMemcpyHostToDevice, st));
+  DRRT_CUDA(cudaStreamSynchronize(st));  // `act` dies at return
+  return DRRT_OK;
+}
+
+int drrt_edgecheck_subset_batch(drrt_store *h, int64_t n, const double *start, const double *end,
+                                const int32_t *start_id, const int32_t *end_id, int edge_kind,
+                                double robot_radius, double r_min, const uint8_t *obstacle_mask,
+                                int32_t n_obstacles, uint8_t *verdict, double *length) {
+  ENTER(h);
+  DRRT_CHECK(stage_obstacle_mask(S, obstacle_mask, n_obstacles, S->stream));
+  S->edge_mask = S->o_mask.p;
+  int rc = edge_host(S, n, start, end, start_id, end_id, edge_kind, robot_radius, r_min, 0, verdict,
+                     length);
+  S->edge_mask = nullptr;
+  return rc;
+}
+
+int drrt_edgecheck_subset_batch_dev(drrt_store *h, int64_t n, const double *start_dev,
+                                    const double *end_dev, const int32_t *start_id_dev,
+                                    const int32_t *end_id_dev, int edge_kind, double robot_radius,
+                                    double r_min, const uint8_t *obstacle_mask, int32_t n_obstacles,
+                                    uint8_t *verdict_dev, double *length_dev, void *stream) {
+  ENTER(h);
+  cudaStream_t st = pick(S, stream);
+  DRRT_CHECK(stage_obstacle_mask(S, obstacle_mask, n_obstacles, st));
+  S->edge_mask = S->o_mask.p;
+  int rc = edgecheck_batch_dev(S, n, start_dev, end_dev, start_id_dev, end_id_dev, edge_kind,
+                               robot_radius, r_min, verdict_dev, length_dev, st);
+  S->edge_mask = nullptr;
+  return rc;
+}
+
+int drrt_obstacle_conflict_batch(drrt_store *h, int32_t n_sel, const int32_t *obstacle_index,
+                                 double robot_radius, int32_t *counts, int64_t *total) {
+  ENTER(h);
+  if (n_sel < 0 || (n_sel > 0 && (!obstacle_index || !counts)))
+    return set_error(DRRT_ERR_INVALID, "conflict: arguments");
+  if (n_sel > 0 && !S->has_obstacles) return set_error(DRRT_ERR_STATE, "conflict: no obstacle table");
+  // FindPointsInConflictWithObstacle, Dubins space without time (obstacle.cpp:554-559):
+  // KDFindWithinRange(robot_radius_ + O->radius_ + PI, (O->origin_(0), O->origin_(1), PI))
+  std::vector<double> q(3 * (size_t)n_sel + 3), r((size_t)n_sel + 1);
+  for (int i = 0; i < n_sel; i++) {
+    const int o = obstacle_index[i];
+    if (o < 0 || o >= S->obs.n_all) return set_error(DRRT_ERR_INVALID, "conflict: obstacle %d", o);
+    const int kind = S->h_all_kind[o];
+    if (kind < 1 || kind > 5)  // :547, :608 "This case has not been coded yet."
+      return set_error(DRRT_ERR_UNSUPPORTED, "conflict: obstacle kind %d", kind);
+    q[3 * i] = S->h_all_ox[o];
+    q[3 * i + 1] = S->h_all_oy[o];
+    q[3 * i + 2] = DRRT_PI;
+    r[i] = robot_radius + S->h_all_rad[o] + DRRT_PI;
+  }
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(S->q_stage.reserve(3 * (size_t)n_sel + 3, st));
+  DRRT_CHECK(S->rad_stage.reserve((size_t)n_sel + 1, st));
+  DRRT_CHECK(upload(q.data(), S->q_stage.p, 3 * (size_t)n_sel * sizeof(double), st));
+  DRRT_CHECK(upload(r.data(), S->rad_stage.p, (size_t)n_sel * sizeof(double), st));
+  DRRT_CUDA(cudaStreamSynchronize(st));  // q, r die at return
+  drrt_range_result res{};
+  DRRT_CHECK(range_batch_dev(S, n_sel, S->q_stage.p, S->rad_stage.p, 0.0, st, &res));
+  if (n_sel > 0) DRRT_CHECK(download(counts, res.counts_dev, (size_t)n_sel * sizeof(int32_t), st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  if (total) *total = res.total;
+  return DRRT_OK;
 }
 
 int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const double *radius,

@@ -40,6 +40,7 @@ static constexpr int EDGE_T = 128;
 
 struct ObsView {
   int n;
+  const uint8_t *mask;  // null, or per obstacle: 0 = leave it out (subset checks of the sweeps)
   const int32_t *kind;
   const double *ox, *oy, *rad;
   const int32_t *voff;
@@ -51,6 +52,7 @@ struct ObsView {
 // from p0 are at more than `radius` from every point of the segment.
 __device__ __forceinline__ bool segment_hits(const ObsView &O, int o, double p0x, double p0y,
                                              double p1x, double p1y, double radius, double far2) {
+  if (O.mask && !O.mask[o]) return false;
   double d2 = dist_sqrd_point_segment(O.ox[o], O.oy[o], p0x, p0y, p1x, p1y);  // :769-779
   double reach = radius + O.rad[o];
   if (d2 > reach * reach) return false;
@@ -103,9 +105,12 @@ __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const Obs
         for (int e = G.off[c]; e < G.off[c + 1]; e++) {
           int j = G.idx[e];
           if (j >= G.n_edges) {  // ball: obstacle.cpp:781
-            if (within_reach(O, G.ball[j - G.n_edges], p0x, p0y, p1x, p1y, radius)) return true;
+            const int b = G.ball[j - G.n_edges];
+            if (O.mask && !O.mask[b]) continue;
+            if (within_reach(O, b, p0x, p0y, p1x, p1y, radius)) return true;
             continue;
           }
+          if (O.mask && !O.mask[G.eobs[j]]) continue;
           double ax = G.eax[j], ay = G.eay[j], bx = G.ebx[j], by = G.eby[j];
           // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
           if (dist_sqrd_point_segment(p0x, p0y, ax, ay, bx, by) > far2) continue;
@@ -133,8 +138,12 @@ struct WarpScratch {
 // one grid entry (polygon edge or ball) against one segment: the reference's tests verbatim
 __device__ __forceinline__ bool entry_hits(const ObsView &O, const ObstacleGrid &G, int j,
                                            const double *sg, double radius) {
-  if (j >= G.n_edges)  // ball: obstacle.cpp:781
-    return within_reach(O, G.ball[j - G.n_edges], sg[0], sg[1], sg[2], sg[3], radius);
+  if (j >= G.n_edges) {  // ball: obstacle.cpp:781
+    const int b = G.ball[j - G.n_edges];
+    if (O.mask && !O.mask[b]) return false;
+    return within_reach(O, b, sg[0], sg[1], sg[2], sg[3], radius);
+  }
+  if (O.mask && !O.mask[G.eobs[j]]) return false;
   double ax = G.eax[j], ay = G.eay[j], bx = G.ebx[j], by = G.eby[j];
   // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
   if (dist_sqrd_point_segment(sg[0], sg[1], ax, ay, bx, by) > sg[4]) return false;
@@ -604,6 +613,7 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   A.metric = S->metric; A.edge_kind = edge_kind;
   A.robot_radius = robot_radius; A.r_min = r_min;
   A.obs.n = S->has_obstacles ? S->obs.n_active : 0;
+  A.obs.mask = S->edge_mask;
   A.obs.kind = S->obs.kind; A.obs.ox = S->obs.ox; A.obs.oy = S->obs.oy; A.obs.rad = S->obs.rad;
   A.obs.voff = S->obs.vert_off; A.obs.vx = S->obs.vx; A.obs.vy = S->obs.vy;
   A.verdict = verdict_dev; A.length = length_dev;

@@ -99,6 +99,12 @@ struct Store {
   // table or the robot radius changes
   std::vector<double> h_o_ox, h_o_oy, h_o_rad, h_o_vx, h_o_vy;
   std::vector<int32_t> h_o_kind, h_o_voff;
+  std::vector<int32_t> h_o_src;  // table index of each active obstacle
+  // the whole table (obstacle sweeps: conflict queries, subset checks)
+  std::vector<double> h_all_ox, h_all_oy, h_all_rad;
+  std::vector<int32_t> h_all_kind;
+  DevBuf<uint8_t> o_mask;                // per ACTIVE obstacle: taking part in a subset check
+  const uint8_t *edge_mask = nullptr;    // set for the duration of a subset check
   ObstacleGrid ogrid{};
   double ogrid_radius = -1.0;
   DevBuf<int32_t> og_off, og_idx, og_eobs, og_ball;

@@ -251,6 +251,49 @@ class KDTree:
                                                  _ptr(length, c_dp)))
         return verdict, length
 
+    # -- edge->ExplicitEdgeCheck(O) for a subset of the obstacle table: the re-checks of
+    #    AddObstacle obstacle.cpp:612-667 / RemoveObstacle :669-754
+    def ExplicitEdgeCheckSubset(self, obstacle_mask, start=None, end=None, start_ids=None,
+                                end_ids=None, robot_radius=0.5, r_min=1.0, edge_kind=EDGE_DUBINS):
+        """obstacle_mask: one byte per obstacle of the table given to SetObstacles (non-zero =
+        takes part).  Edges by poses (start/end, n x 3) or by node ids."""
+        mask = np.ascontiguousarray(obstacle_mask, dtype=np.uint8)
+        s = e = si = ei = None
+        if start_ids is not None:
+            si = np.ascontiguousarray(start_ids, dtype=np.int32)
+            ei = np.ascontiguousarray(end_ids, dtype=np.int32)
+            n = si.shape[0]
+        else:
+            s = _f64(start, (-1, 3))
+            e = _f64(end, (-1, 3))
+            n = s.shape[0]
+        verdict = np.zeros(n, dtype=np.uint8)
+        length = np.zeros(n, dtype=np.float64)
+        p = lambda a, t: _ptr(a, t) if a is not None else None
+        check(self._lib.drrt_edgecheck_subset_batch(self._h, n, p(s, c_dp), p(e, c_dp), p(si, c_ip),
+                                                    p(ei, c_ip), edge_kind, float(robot_radius),
+                                                    float(r_min), _ptr(mask, c_u8p), len(mask),
+                                                    _ptr(verdict, c_u8p), _ptr(length, c_dp)))
+        return verdict, length
+
+    # -- FindPointsInConflictWithObstacle obstacle.cpp:540-610 (Dubins space, :554-559)
+    def FindPointsInConflictWithObstacle(self, obstacle_indices, robot_radius=0.5):
+        """-> (offsets int64[n+1], ids, dists): the nodes within robot_radius + O.radius_ + PI
+        of (O.origin_(0), O.origin_(1), PI), one row per listed obstacle."""
+        idx = np.ascontiguousarray(obstacle_indices, dtype=np.int32)
+        counts = np.zeros(len(idx), dtype=np.int32)
+        total = C.c_int64()
+        with self._lock:
+            check(self._lib.drrt_obstacle_conflict_batch(self._h, len(idx), _ptr(idx, c_ip),
+                                                         float(robot_radius), _ptr(counts, c_ip),
+                                                         C.byref(total)))
+            ids = np.empty(total.value, dtype=np.int32)
+            dist = np.empty(total.value, dtype=np.float64)
+            check(self._lib.drrt_range_fetch(self._h, _ptr(ids, c_ip), _ptr(dist, c_dp)))
+        off = np.zeros(len(idx) + 1, dtype=np.int64)
+        np.cumsum(counts, out=off[1:])
+        return off, ids, dist
+
     def ExplicitEdgeCheck_dev(self, verdict_out, start=None, end=None, start_ids=None,
                               end_ids=None, robot_radius=0.5, r_min=1.0, edge_kind=EDGE_DUBINS,
                               length_out=None):

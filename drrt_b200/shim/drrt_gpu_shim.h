@@ -31,6 +31,21 @@ bool ExplicitEdgeCheckBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
                                std::vector<std::shared_ptr<Edge>> &edges,
                                std::vector<unsigned char> &unsafe);
 
+// The re-checks of AddObstacle (obstacle.cpp:612-667) and RemoveObstacle (:669-754), for all
+// the edges of the nodes in conflict at once: against O alone (`edge->ExplicitEdgeCheck(O)`,
+// :643, :651, :712) and against every other used obstacle whose life window holds
+// time_elapsed (:717-734).  The obstacle table must be the current list
+// (DrrtGpuUploadObstacles after obstacle_used_ changes).  FindPointsInConflictWithObstacle
+// (:540-610) itself needs no shim: it calls Tree->KDFindWithinRange.
+bool ExplicitEdgeCheckObstacleBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
+                                       std::vector<std::shared_ptr<Edge>> &edges,
+                                       std::shared_ptr<Obstacle> &O,
+                                       std::vector<unsigned char> &unsafe);
+bool ExplicitEdgeCheckOtherObstaclesBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
+                                             std::vector<std::shared_ptr<Edge>> &edges,
+                                             std::shared_ptr<Obstacle> &O, double time_elapsed,
+                                             std::vector<unsigned char> &unsafe);
+
 // LineCheck obstacle.cpp:1092-1143 and ExplicitNodeCheck obstacle.cpp:1087-1090
 bool LineCheckGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t, std::shared_ptr<KDTreeNode> node1,
                   std::shared_ptr<KDTreeNode> node2);

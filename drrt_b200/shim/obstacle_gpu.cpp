@@ -70,6 +70,54 @@ bool ExplicitEdgeCheckBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
   return true;
 }
 
+// Subset re-checks of the obstacle sweeps.  `take(obstacle)` decides, in list order (the
+// order DrrtGpuUploadObstacles flattened), which obstacles an edge is tested against.
+template <class Take>
+static bool edge_check_subset(std::shared_ptr<ConfigSpace> &C, KDTree *t,
+                              std::vector<std::shared_ptr<Edge>> &edges,
+                              std::vector<unsigned char> &unsafe, Take take) {
+  drrt_store *h = DrrtGpuHandle(t);
+  const size_t n = edges.size();
+  unsafe.assign(n, 0);
+  if (!h || n == 0) return h != nullptr;
+  std::vector<uint8_t> mask;
+  {
+    std::shared_ptr<ListNode> node = C->obstacles_->front_;
+    for (int i = 0; i < C->obstacles_->length_; i++, node = node->child_)
+      mask.push_back(take(node->obstacle_) ? 1 : 0);
+  }
+  std::vector<double> s(3 * n), e(3 * n);
+  for (size_t i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) {
+      s[3 * i + k] = edges[i]->start_node_->position_(k);
+      e[3 * i + k] = edges[i]->end_node_->position_(k);
+    }
+  return ok(drrt_edgecheck_subset_batch(h, (int64_t)n, s.data(), e.data(), nullptr, nullptr,
+                                        DRRT_EDGE_DUBINS, C->robot_radius_, C->min_turn_radius_,
+                                        mask.data(), (int32_t)mask.size(), unsafe.data(), nullptr),
+            "ExplicitEdgeCheck(obstacle)");
+}
+
+bool ExplicitEdgeCheckObstacleBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
+                                       std::vector<std::shared_ptr<Edge>> &edges,
+                                       std::shared_ptr<Obstacle> &O,
+                                       std::vector<unsigned char> &unsafe) {
+  // neighbor_edge->ExplicitEdgeCheck(O), obstacle.cpp:643, 651, 712
+  return edge_check_subset(C, t, edges, unsafe,
+                           [&](const std::shared_ptr<Obstacle> &other) { return other == O; });
+}
+
+bool ExplicitEdgeCheckOtherObstaclesBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
+                                             std::vector<std::shared_ptr<Edge>> &edges,
+                                             std::shared_ptr<Obstacle> &O, double time_elapsed,
+                                             std::vector<unsigned char> &unsafe) {
+  // RemoveObstacle's inner loop, obstacle.cpp:717-734
+  return edge_check_subset(C, t, edges, unsafe, [&](const std::shared_ptr<Obstacle> &other) {
+    return other != O && other->obstacle_used_ && other->start_time_ <= time_elapsed &&
+           time_elapsed <= other->start_time_ + other->life_span_;
+  });
+}
+
 bool ExplicitEdgeCheckGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t, std::shared_ptr<Edge> &edge) {
   std::vector<std::shared_ptr<Edge>> one(1, edge);
   std::vector<unsigned char> unsafe;

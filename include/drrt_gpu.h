@@ -182,6 +182,37 @@ DRRT_API int drrt_edgecheck_batch_dev(drrt_store *h, int64_t n, const double *st
                              uint8_t *verdict_dev, double *length_dev,
                              void *stream);
 
+/* ---- obstacle add / remove sweeps ------------------------
+ * AddObstacle src/obstacle.cpp:612-667 and RemoveObstacle :669-754 re-check the
+ * stored edges of every node near an obstacle against THAT obstacle only
+ * (`edge->ExplicitEdgeCheck(O)`, i.e. DubinsEdge::ExplicitEdgeCheck
+ * src/dubinsedge.cpp:850-898 for one obstacle), and RemoveObstacle then against
+ * every OTHER obstacle that is used and inside its life window (:717-734).
+ * Both are the edge check above restricted to a subset of the table given to
+ * drrt_obstacles_set: obstacle_mask[o] != 0 for the obstacles taking part
+ * (n_obstacles must equal the table's length; the host decides the life-window
+ * part of the mask).  Edges are n x 3 poses (start/end) or node ids
+ * (start_id/end_id); pass the unused pair as NULL.
+ * drrt_obstacle_conflict_batch is FindPointsInConflictWithObstacle :540-610
+ * for the Dubins space without time (:554-559): one range query per listed
+ * obstacle, centre (origin_(0), origin_(1), PI), radius robot_radius +
+ * radius_ + PI; counts/total as drrt_range_batch, rows through
+ * drrt_range_fetch.  Kinds outside 1..5 -> DRRT_ERR_UNSUPPORTED. */
+DRRT_API int drrt_edgecheck_subset_batch(drrt_store *h, int64_t n, const double *start,
+                             const double *end, const int32_t *start_id,
+                             const int32_t *end_id, int edge_kind, double robot_radius,
+                             double r_min, const uint8_t *obstacle_mask,
+                             int32_t n_obstacles, uint8_t *verdict, double *length);
+DRRT_API int drrt_edgecheck_subset_batch_dev(drrt_store *h, int64_t n, const double *start_dev,
+                             const double *end_dev, const int32_t *start_id_dev,
+                             const int32_t *end_id_dev, int edge_kind,
+                             double robot_radius, double r_min,
+                             const uint8_t *obstacle_mask /* host */, int32_t n_obstacles,
+                             uint8_t *verdict_dev, double *length_dev, void *stream);
+DRRT_API int drrt_obstacle_conflict_batch(drrt_store *h, int32_t n_sel,
+                             const int32_t *obstacle_index, double robot_radius,
+                             int32_t *counts, int64_t *total);
+
 /* ---- fused Extend step (the step after the edge check) ----------
  * What Extend does around the hot path for one new node (src/drrt.cpp:194-362):
  * KDFindWithinRange (:213-216), then for every neighbour the new->near edge
