@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdrrt_b200.so")
+# DRRT_B200_LIB: another build of the same library (kernel A/B runs); still no CPU path
+LIB_PATH = os.environ.get("DRRT_B200_LIB") or os.path.join(_HERE, "libdrrt_b200.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_NO_DEVICE, ERR_STATE = range(7)
 METRIC_R2S1_WRAP, METRIC_EUCLID = 0, 1
