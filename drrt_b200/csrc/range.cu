@@ -484,7 +484,10 @@ static constexpr int CTA_T = CTA_WARPS * 32;
 static constexpr int CTA_STAGE = 4608;  // hits staged per query
 static constexpr int CTA_NB = 16384;    // id buckets
 static constexpr int CTA_NW = CTA_NB / 4;
-static constexpr int CTA_UNR = 2;
+#ifndef DRRT_CTA_UNR
+#define DRRT_CTA_UNR 2
+#endif
+static constexpr int CTA_UNR = DRRT_CTA_UNR;
 static constexpr int CTA_CROWDED = 32;  // larger buckets are not insertion-sorted (bytes must not wrap)
 static constexpr int CTA_CHUNK = 8;     // consecutive queries per arena slice (fewer when the batch is small)
 // dynamic shared memory layout (bytes)
@@ -532,33 +535,60 @@ __device__ __forceinline__ GhostBand ghost_band(const Query &Q) {
   return B;
 }
 
-template <int METRIC>
-__device__ __forceinline__ bool eval_candidate2(const Query &Q, const GhostBand &B, double nx,
-                                                double ny, double nt, int32_t id,
-                                                const double *gate, double *dout) {
-  double s = metric_sum<METRIC>(Q.x, Q.y, Q.t, nx, ny, nt);
-  if (s < Q.s_hi) {
-    double d = sqrt(s);
-    if (id == 0) {
-      if (d <= Q.r) { *dout = d; return true; }  // kdtree.cpp:800-802
-    } else if (d < Q.r) {                         // kdtree.cpp:733, :765
-      if (METRIC == DRRT_METRIC_EUCLID || walk_reaches(Q.t, nt, Q.r, id, gate)) {
-        *dout = d;
-        return true;
+// Candidate test of the CTA kernel: eval_candidate's predicate with the ghost probe behind ghost_band,
+// for UNR candidates at once, written straight-line (selects, no per-candidate
+// branches) so that the FP64 chains of the candidates overlap; the gate[] look-up and the ghost
+// pass stay behind warp-level branches because they are rare.
+template <int METRIC, int UNR>
+__device__ __forceinline__ void eval_candidates(const Query &Q, const GhostBand &B, const bool *valid,
+                                                const double *nx, const double *ny, const double *nt,
+                                                const int32_t *id, const double *gate, bool *hit,
+                                                double *dout) {
+  double s[UNR], d[UNR];
+  bool askgate[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; u++) s[u] = metric_sum<METRIC>(Q.x, Q.y, Q.t, nx[u], ny[u], nt[u]);
+#pragma unroll
+  for (int u = 0; u < UNR; u++) d[u] = sqrt(s[u]);
+  bool anygate = false;
+#pragma unroll
+  for (int u = 0; u < UNR; u++) {
+    const bool pre = valid[u] && s[u] < Q.s_hi;
+    const bool root = id[u] == 0;
+    const bool in = pre && (root ? d[u] <= Q.r : d[u] < Q.r);     // kdtree.cpp:800-802, :733, :765
+    const bool fast = METRIC == DRRT_METRIC_EUCLID || root || !(Q.t - nt[u] > Q.r);  // walk_reaches, first clause
+    hit[u] = in && fast;
+    askgate[u] = in && !fast;
+    anygate |= askgate[u];
+    dout[u] = d[u];
+  }
+  if (METRIC != DRRT_METRIC_EUCLID && __any_sync(0xffffffffu, anygate)) {
+#pragma unroll
+    for (int u = 0; u < UNR; u++)
+      if (askgate[u]) hit[u] = !(Q.t - gate[id[u]] > Q.r);
+  }
+  if (Q.has_ghost) {  // kdtree.cpp:807-819; uniform
+    bool needg[UNR], any = false;
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      needg[u] = valid[u] && !hit[u] && (s[u] < B.s_band || !(nt[u] >= B.nlo && nt[u] <= B.nhi));
+      any |= needg[u];
+    }
+    if (__any_sync(0xffffffffu, any)) {
+      double s2[UNR], d2[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) s2[u] = metric_sum<METRIC>(Q.x, Q.y, Q.gt, nx[u], ny[u], nt[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; u++) d2[u] = sqrt(s2[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const bool in = needg[u] && s2[u] < Q.s_hi && d2[u] < Q.r;
+        bool ok = in;
+        if (METRIC != DRRT_METRIC_EUCLID && in && (Q.gt - nt[u] > Q.r)) ok = !(Q.gt - gate[id[u]] > Q.r);
+        if (ok) { hit[u] = true; dout[u] = d2[u]; }
       }
     }
   }
-  if (Q.has_ghost && (s < B.s_band || !(nt >= B.nlo && nt <= B.nhi))) {
-    double s2 = metric_sum<METRIC>(Q.x, Q.y, Q.gt, nx, ny, nt);
-    if (s2 < Q.s_hi) {
-      double d = sqrt(s2);
-      if (d < Q.r && (METRIC == DRRT_METRIC_EUCLID || walk_reaches(Q.gt, nt, Q.r, id, gate))) {
-        *dout = d;
-        return true;
-      }
-    }
-  }
-  return false;
 }
 
 template <int METRIC>
@@ -625,10 +655,9 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         double d[UNR];
         unsigned m[UNR];
         int tot = 0;
+        eval_candidates<METRIC, UNR>(Q, GB, valid, nx, ny, nt, id, V.gate, hit, d);
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-          d[u] = 0.0;
-          hit[u] = valid[u] && eval_candidate2<METRIC>(Q, GB, nx[u], ny[u], nt[u], id[u], V.gate, &d[u]);
           m[u] = __ballot_sync(0xffffffffu, hit[u]);
           tot += __popc(m[u]);
         }
