@@ -37,6 +37,10 @@
 namespace drrt {
 
 static constexpr int EDGE_T = 128;
+#ifndef DRRT_PF_AHEAD
+#define DRRT_PF_AHEAD 8192
+#endif
+static constexpr long long PATH_PREFETCH_AHEAD = DRRT_PF_AHEAD;  // edges claimed ahead of the walk
 
 struct ObsView {
   int n;
@@ -377,6 +381,13 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
           exhausted = true;
         } else {
           e = mine;
+          // the records were written by the solve kernel and no longer sit in L2 (112 B x 10 M
+          // edges): pull the one that will be claimed a few trips from now out of DRAM early
+          if (mine + PATH_PREFETCH_AHEAD < A.n) {
+            const char *pf = reinterpret_cast<const char *>(paths + mine + PATH_PREFETCH_AHEAD);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + sizeof(DubinsPath) - 16));
+          }
           W.start(paths + e, A.r_min, true);
           have_prev = false;
         }
