@@ -54,9 +54,10 @@ struct ObsView {
 // ExplicitEdgeCheck2D for one active obstacle (kind 1 or 3).  far2 =
 // ((radius + |p1-p0|) * (1+1e-9) + 1e-9)^2 : polygon edges farther than that
 // from p0 are at more than `radius` from every point of the segment.
+template <bool MASKED>
 __device__ __forceinline__ bool segment_hits(const ObsView &O, int o, double p0x, double p0y,
                                              double p1x, double p1y, double radius, double far2) {
-  if (O.mask && !O.mask[o]) return false;
+  if (MASKED && !O.mask[o]) return false;
   double d2 = dist_sqrd_point_segment(O.ox[o], O.oy[o], p0x, p0y, p1x, p1y);  // :769-779
   double reach = radius + O.rad[o];
   if (d2 > reach * reach) return false;
@@ -88,6 +89,7 @@ __device__ __forceinline__ bool within_reach(const ObsView &O, int o, double p0x
 //   true  <=>  some live ball passes the bounding reject, or some polygon edge has
 //              SegmentDistSqrd < radius^2 and its obstacle passes the bounding reject
 // which is the OR over obstacles of obstacle.cpp:761-804.
+template <bool MASKED>
 __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const ObstacleGrid &G,
                                                      double p0x, double p0y, double p1x,
                                                      double p1y, double radius) {
@@ -110,11 +112,11 @@ __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const Obs
           int j = G.idx[e];
           if (j >= G.n_edges) {  // ball: obstacle.cpp:781
             const int b = G.ball[j - G.n_edges];
-            if (O.mask && !O.mask[b]) continue;
+            if (MASKED && !O.mask[b]) continue;
             if (within_reach(O, b, p0x, p0y, p1x, p1y, radius)) return true;
             continue;
           }
-          if (O.mask && !O.mask[G.eobs[j]]) continue;
+          if (MASKED && !O.mask[G.eobs[j]]) continue;
           double ax = G.eax[j], ay = G.eay[j], bx = G.ebx[j], by = G.eby[j];
           // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
           if (dist_sqrd_point_segment(p0x, p0y, ax, ay, bx, by) > far2) continue;
@@ -126,7 +128,7 @@ __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const Obs
     return false;
   }
   for (int o = 0; o < O.n; o++)
-    if (segment_hits(O, o, p0x, p0y, p1x, p1y, radius, far2)) return true;
+    if (segment_hits<MASKED>(O, o, p0x, p0y, p1x, p1y, radius, far2)) return true;
   return false;
 }
 
@@ -140,14 +142,15 @@ struct WarpScratch {
 };
 
 // one grid entry (polygon edge or ball) against one segment: the reference's tests verbatim
+template <bool MASKED>
 __device__ __forceinline__ bool entry_hits(const ObsView &O, const ObstacleGrid &G, int j,
                                            const double *sg, double radius) {
   if (j >= G.n_edges) {  // ball: obstacle.cpp:781
     const int b = G.ball[j - G.n_edges];
-    if (O.mask && !O.mask[b]) return false;
+    if (MASKED && !O.mask[b]) return false;
     return within_reach(O, b, sg[0], sg[1], sg[2], sg[3], radius);
   }
-  if (O.mask && !O.mask[G.eobs[j]]) return false;
+  if (MASKED && !O.mask[G.eobs[j]]) return false;
   double ax = G.eax[j], ay = G.eay[j], bx = G.ebx[j], by = G.eby[j];
   // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
   if (dist_sqrd_point_segment(sg[0], sg[1], ax, ay, bx, by) > sg[4]) return false;
@@ -161,11 +164,12 @@ __device__ __forceinline__ bool entry_hits(const ObsView &O, const ObstacleGrid 
 // segments meet no entry at all and a few meet several, so a per-lane loop runs
 // at ~2 active lanes; this keeps them all busy.  Returns whether the calling
 // lane's own segment collides.  All 32 lanes must call.
+template <bool MASKED>
 __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid &G, bool test,
                                            double p0x, double p0y, double p1x, double p1y,
                                            double radius, WarpScratch *ws, int lane) {
   if (G.nx == 0)  // no grid (degenerate table): per-lane loop over all obstacles
-    return test && segment_vs_obstacles(O, G, p0x, p0y, p1x, p1y, radius);
+    return test && segment_vs_obstacles<MASKED>(O, G, p0x, p0y, p1x, p1y, radius);
   double lox = fmin(p0x, p1x), hix = fmax(p0x, p1x), loy = fmin(p0y, p1y), hiy = fmax(p0y, p1y);
   int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;  // empty
   if (test && lox <= hix && loy <= hiy) {
@@ -217,7 +221,7 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
     }
     int q = p - ws->pre[lo], k = 0;
     while (q >= ws->len[lo][k]) { q -= ws->len[lo][k]; k++; }
-    if (entry_hits(O, G, G.idx[ws->start[lo][k] + q], ws->seg[lo], radius)) atomicOr(&ws->hit, 1u << lo);
+    if (entry_hits<MASKED>(O, G, G.idx[ws->start[lo][k] + q], ws->seg[lo], radius)) atomicOr(&ws->hit, 1u << lo);
   }
   // segments spanning many cells: one at a time, the warp sweeps its cells
   unsigned wmask = __ballot_sync(0xffffffffu, wide);
@@ -229,7 +233,7 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
     bool h = false;
     for (int k = lane; k < wn && !h; k += 32) {
       int c = (wx0 + k / wny) * G.ny + (wy0 + k % wny);
-      for (int e = G.off[c]; e < G.off[c + 1] && !h; e++) h = entry_hits(O, G, G.idx[e], ws->seg[L], radius);
+      for (int e = G.off[c]; e < G.off[c + 1] && !h; e++) h = entry_hits<MASKED>(O, G, G.idx[e], ws->seg[L], radius);
     }
     if (__any_sync(0xffffffffu, h) && lane == 0) atomicOr(&ws->hit, 1u << L);
   }
@@ -353,6 +357,7 @@ dubins_solve_kernel(EdgeArgs A, DubinsPath *paths) {
 }
 
 // K4b: polyline walk + ExplicitEdgeCheck2D per segment, lanes refill from a global counter
+template <bool MASKED>  // MASKED: only the obstacles of a subset take part (obstacle sweeps)
 __global__ void __launch_bounds__(EDGE_T)
 dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next_edge) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -402,7 +407,7 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
       if (!W.next(&cx, &cy, &connects)) ended = true;  // end of path, nothing collided (dubinsedge.cpp:897)
       else test = have_prev && connects;
     }
-    bool hit = warp_segments_vs_obstacles(O, A.grid, test, px, py, cx, cy, A.robot_radius, ws, lane);
+    bool hit = warp_segments_vs_obstacles<MASKED>(O, A.grid, test, px, py, cx, cy, A.robot_radius, ws, lane);
     if (e >= 0) {
       if (ended || hit) {  // :878-889 first hit decides the edge
         A.verdict[e] = hit ? 1 : 0;
@@ -417,6 +422,7 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
 }
 
 // K5: LineCheck (obstacle.cpp:1098-1133), one thread per edge
+template <bool MASKED>
 __global__ void __launch_bounds__(EDGE_T)
 linecheck_kernel(EdgeArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -443,7 +449,7 @@ linecheck_kernel(EdgeArgs A) {
     for (int i = 0; i < 50; i++) {
       if (ex > sx) x_val += x_dist / traj_length; else x_val -= x_dist / traj_length;
       if (ey > sy) y_val += y_dist / traj_length; else y_val -= y_dist / traj_length;
-      bool h = warp_segments_vs_obstacles(O, A.grid, live && !hit, px, py, x_val, y_val,
+      bool h = warp_segments_vs_obstacles<MASKED>(O, A.grid, live && !hit, px, py, x_val, y_val,
                                           A.robot_radius, ws, lane);
       hit = hit || h;
       if (__all_sync(0xffffffffu, hit || !live)) break;
@@ -637,15 +643,17 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   }
   static bool attr_done = false;
   if (!attr_done) {
-    DRRT_CUDA(cudaFuncSetAttribute(dubins_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   96 * 1024));
-    DRRT_CUDA(cudaFuncSetAttribute(linecheck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   96 * 1024));
+    DRRT_CUDA(cudaFuncSetAttribute(dubins_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DRRT_CUDA(cudaFuncSetAttribute(dubins_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DRRT_CUDA(cudaFuncSetAttribute(linecheck_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DRRT_CUDA(cudaFuncSetAttribute(linecheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_done = true;
   }
+  const bool masked = A.obs.mask != nullptr;
   unsigned nb = (unsigned)((n + EDGE_T - 1) / EDGE_T);
   if (edge_kind == DRRT_EDGE_STRAIGHT) {
-    linecheck_kernel<<<nb, EDGE_T, smem, st>>>(A);
+    if (masked) linecheck_kernel<true><<<nb, EDGE_T, smem, st>>>(A);
+    else linecheck_kernel<false><<<nb, EDGE_T, smem, st>>>(A);
     DRRT_LAUNCHED();
   } else {
     if (st != S->stream) DRRT_CUDA(cudaStreamSynchronize(S->stream));
@@ -659,11 +667,15 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
       DRRT_CUDA(cudaMemsetAsync(S->d_edge_counter, 0, sizeof(unsigned long long), st));
       // persistent grid: enough CTAs to fill the machine, lanes pull edges until none are left
       int per_sm = 0;
-      DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dubins_walk_kernel, EDGE_T, smem));
+      if (masked)
+        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dubins_walk_kernel<true>, EDGE_T, smem));
+      else
+        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dubins_walk_kernel<false>, EDGE_T, smem));
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
       unsigned grid = (unsigned)std::min<int64_t>(nb, (int64_t)std::max(per_sm, 1) * sms);
-      dubins_walk_kernel<<<grid, EDGE_T, smem, st>>>(A, paths, S->d_edge_counter);
+      if (masked) dubins_walk_kernel<true><<<grid, EDGE_T, smem, st>>>(A, paths, S->d_edge_counter);
+      else dubins_walk_kernel<false><<<grid, EDGE_T, smem, st>>>(A, paths, S->d_edge_counter);
       DRRT_LAUNCHED();
     }
   }
