@@ -212,7 +212,7 @@ int drrt_store_destroy(drrt_store *h) {
     S->ins_cur.release(); S->ins_split.release(); S->ins_gate.release(); S->stage_pos.release();
     S->rec.release(); S->cell_start.release(); S->cell_of.release(); S->rank_in_cell.release();
     S->scan_tmp.release();
-    S->r_offsets.release(); S->r_ids.release(); S->r_dist.release(); S->r_desc.release();
+    S->r_offsets.release(); S->r_ids.release(); S->r_dist.release();
     S->r_counts.release(); S->r_chunk_total.release(); S->r_chunk_base.release();
     S->r_offsets2.release(); S->r_ids2.release(); S->r_dist2.release();
     S->q_stage.release(); S->rad_stage.release();

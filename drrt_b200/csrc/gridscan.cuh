@@ -210,89 +210,10 @@ __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, 
           int mid = (lo + hi) >> 1;
           if (run_pref[mid] <= i) lo = mid; else hi = mid;
         }
-        const NodeRec *r = A.rec + (run_start[lo] + (i - run_pref[lo]));
-        double2 xy = *reinterpret_cast<const double2 *>(&r->x);
-        double2 ti = *reinterpret_cast<const double2 *>(&r->th);
-        nx = xy.x; ny = xy.y; nt = ti.x;
-        id = (int32_t)(__double_as_longlong(ti.y) & 0xffffffffll);
+        load_rec(A.rec + (run_start[lo] + (i - run_pref[lo])), nx, ny, nt, id);
       }
       f(valid, nx, ny, nt, id);
     }
-  }
-}
-
-// A whole CTA of NWARPS warps visits ALL candidate columns of query Q: every
-// thread resolves one column's runs, a CTA-wide prefix sum flattens them, and
-// each warp takes an equal, contiguous slice of the candidates (consecutive
-// lanes read consecutive 32-byte records).  run_start/run_pref hold 2*T and
-// 2*T+1 ints, tmp64 holds NWARPS 64-bit words.  f as in scan_columns.
-template <int NWARPS, class F>
-__device__ __forceinline__ void scan_columns_block(const GridView &A, const Query &Q,
-                                                   int *run_start, int *run_pref, long long *tmp64,
-                                                   F f) {
-  constexpr int T = NWARPS * 32;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int ncy = Q.iy1 - Q.iy0 + 1;
-  const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
-  const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
-  for (int cb = 0; cb < ncol; cb += T) {
-    int s0, l0, s1, l1;
-    column_runs(A, Q, cb + tid, ncol, ncy, cull, s0, l0, s1, l1);
-    // one prefix sum carries both the record count (low half) and the number of NON-EMPTY
-    // runs (high half): only those are listed, so walking the list never steps over culled
-    // columns or absent wrap runs
-    const int nrun = (l0 > 0) + (l1 > 0);
-    const long long mine = ((long long)nrun << 32) | (unsigned)(l0 + l1);
-    long long inc = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      long long t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) tmp64[w] = inc;
-    __syncthreads();
-    long long wbase = 0, all = 0;
-#pragma unroll
-    for (int ww = 0; ww < NWARPS; ww++) {
-      long long v = tmp64[ww];
-      if (ww < w) wbase += v;
-      all += v;
-    }
-    const long long excl64 = wbase + inc - mine;
-    const int excl = (int)(excl64 & 0xffffffffll), slot = (int)(excl64 >> 32);
-    const int total = (int)(all & 0xffffffffll), nent = (int)(all >> 32);
-    if (l0 > 0) { run_start[slot] = s0; run_pref[slot] = excl; }
-    if (l1 > 0) { run_start[slot + (l0 > 0)] = s1; run_pref[slot + (l0 > 0)] = excl + l0; }
-    if (tid == T - 1) run_pref[nent] = total;
-    __syncthreads();
-    int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;
-    int c0 = w * per, c1 = min(total, c0 + per);
-    if (c0 < c1) {
-      int lo = 0, hi = nent;  // largest j with run_pref[j] <= c0
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (run_pref[mid] <= c0) lo = mid; else hi = mid;
-      }
-      int j = lo;
-      for (int base = c0; base < c1; base += 32) {
-        while (run_pref[j + 1] <= base) j++;
-        int i = base + lane;
-        bool valid = i < c1;
-        double nx = 0.0, ny = 0.0, nt = 0.0;
-        int32_t id = 0;
-        if (valid) {
-          int jl = j;
-          while (run_pref[jl + 1] <= i) jl++;
-          const NodeRec *r = A.rec + (run_start[jl] + (i - run_pref[jl]));
-          double2 xy = *reinterpret_cast<const double2 *>(&r->x);
-          double2 ti = *reinterpret_cast<const double2 *>(&r->th);
-          nx = xy.x; ny = xy.y; nt = ti.x;
-          id = (int32_t)(__double_as_longlong(ti.y) & 0xffffffffll);
-        }
-        f(valid, nx, ny, nt, id);
-      }
-    }
-    __syncthreads();
   }
 }
 

@@ -35,9 +35,7 @@
 namespace drrt {
 
 static constexpr int WARP_MODE_WARPS = 8;    // one query per warp
-static constexpr int BLOCK_MODE_WARPS = 16;  // one query per CTA
 static constexpr int WARP_STAGE = 256;       // hits staged per warp-mode query
-static constexpr int BLOCK_STAGE = 4608;     // hits staged per CTA-mode query
 
 struct RangeArgs {
   GridView V;
@@ -48,8 +46,6 @@ struct RangeArgs {
   int64_t *offsets;
   int32_t *ids;
   double *dist;
-  int64_t cap;
-  unsigned long long *desc;
   int32_t *ticket;
   int32_t *counts;
   // CTA kernel: arena slices of chunk_len (<= CTA_CHUNK) rows
@@ -67,59 +63,88 @@ __device__ __forceinline__ bool walk_reaches(double pt, double nt, double r, int
   return !(pt - gate[id] > r);
 }
 
-template <int METRIC>
-__device__ __forceinline__ bool eval_candidate(const Query &Q, double nx, double ny, double nt,
-                                               int32_t id, const double *gate, double *dout) {
-  double s = metric_sum<METRIC>(Q.x, Q.y, Q.t, nx, ny, nt);
-  if (s < Q.s_hi) {
-    double d = sqrt(s);
-    if (id == 0) {
-      if (d <= Q.r) { *dout = d; return true; }  // kdtree.cpp:800-802
-    } else if (d < Q.r) {                         // kdtree.cpp:733, :765
-      if (METRIC == DRRT_METRIC_EUCLID || walk_reaches(Q.t, nt, Q.r, id, gate)) {
-        *dout = d;
-        return true;
-      }
-    }
-  }
-  if (Q.has_ghost) {  // kdtree.cpp:807-819
-    double s2 = metric_sum<METRIC>(Q.x, Q.y, Q.gt, nx, ny, nt);
-    if (s2 < Q.s_hi) {
-      double d = sqrt(s2);
-      if (d < Q.r && (METRIC == DRRT_METRIC_EUCLID || walk_reaches(Q.gt, nt, Q.r, id, gate))) {
-        *dout = d;
-        return true;
-      }
-    }
-  }
-  return false;
-}
-
-// Where a scanning warp puts its hits.
-struct Sink {
-  unsigned long long *keys;  // shared: (id << 32) | slot
-  double *sdist;             // shared
-  int *counter;              // shared
-  int capacity;
-  // direct mode (second pass of an overflowed query)
-  int32_t *gids;
-  double *gdist;
+// Why the ghost can be skipped (wrap-aware metric, wrap point == the metric's period W):
+// with a = |q.theta - n.theta| the first probe's theta term is min(a, W - a), whose square is
+// the squared distance of a to the nearer of {0, W}; the ghost q.theta +- W sees
+// a' = |q.theta +- W - n.theta| instead.  For a <= 1.5 W that distance never shrinks
+// (it stays equal on the far side of the seam and grows on the near side), so
+// metric(ghost, n) >= metric(q, n) in exact arithmetic; in IEEE double each theta term
+// carries at most a few roundings of magnitudes <= |q.theta| + |n.theta| + 2W, which the
+// band (2^-46 relative to that magnitude, against 2^-52 roundings) covers.  Candidates
+// outside |n.theta - q.theta| <= 1.45 W or |n.theta| <= 64 always take the ghost pass, and
+// so does a candidate the first probe finds in range but the signed prune hides.
+struct GhostBand {
+  double s_band;    // first-probe squared sums at or above this cannot be rescued by the ghost
+  double nlo, nhi;  // n.theta interval in which that holds
 };
 
-__device__ __forceinline__ void emit(const Sink &K, bool hit, int32_t id, double d, int lane) {
-  unsigned m = __ballot_sync(0xffffffffu, hit);
-  if (!m) return;
-  int base = 0;
-  if (lane == 0) base = atomicAdd(K.counter, __popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (hit) {
-    int slot = base + __popc(m & ((1u << lane) - 1));
-    if (K.gids) {
-      K.gids[slot] = id;
-      K.gdist[slot] = d;
-    } else if (slot < K.capacity) {
-      K.keys[slot] = ((unsigned long long)(unsigned)id << 32) | (unsigned)slot;
-      K.sdist[slot] = d;
+template <int METRIC>
+__device__ __forceinline__ GhostBand ghost_band(const Query &Q) {
+  GhostBand B;
+  const double band = Q.r + 1.4210854715202004e-14 * (fabs(Q.t) + 64.0 + 2.0 * DRRT_TWO_PI + fabs(Q.r));
+  B.s_band = band * band * (1.0 + 1.4210854715202004e-14);
+  B.nlo = fmax(-64.0, Q.t - 1.45 * DRRT_TWO_PI);
+  B.nhi = fmin(64.0, Q.t + 1.45 * DRRT_TWO_PI);
+  if (METRIC == DRRT_METRIC_EUCLID || !(fabs(Q.t) <= 64.0) || !(B.s_band == B.s_band)) {
+    B.s_band = 1.0e308;  // every rejected candidate takes the ghost pass
+    B.nlo = 1.0;
+    B.nhi = -1.0;
+  }
+  return B;
+}
+
+// Candidate test of the CTA kernel: eval_candidate's predicate with the ghost probe behind ghost_band,
+// for UNR candidates at once, written straight-line (selects, no per-candidate
+// branches) so that the FP64 chains of the candidates overlap; the gate[] look-up and the ghost
+// pass stay behind warp-level branches because they are rare.
+template <int METRIC, int UNR>
+__device__ __forceinline__ void eval_candidates(const Query &Q, const GhostBand &B, const bool *valid,
+                                                const double *nx, const double *ny, const double *nt,
+                                                const int32_t *id, const double *gate, bool *hit,
+                                                double *dout) {
+  double s[UNR], d[UNR];
+  bool askgate[UNR];
+#pragma unroll
+  for (int u = 0; u < UNR; u++) s[u] = metric_sum<METRIC>(Q.x, Q.y, Q.t, nx[u], ny[u], nt[u]);
+#pragma unroll
+  for (int u = 0; u < UNR; u++) d[u] = sqrt(s[u]);
+  bool anygate = false;
+#pragma unroll
+  for (int u = 0; u < UNR; u++) {
+    const bool pre = valid[u] && s[u] < Q.s_hi;
+    const bool root = id[u] == 0;
+    const bool in = pre && (root ? d[u] <= Q.r : d[u] < Q.r);     // kdtree.cpp:800-802, :733, :765
+    const bool fast = METRIC == DRRT_METRIC_EUCLID || root || !(Q.t - nt[u] > Q.r);  // walk_reaches, first clause
+    hit[u] = in && fast;
+    askgate[u] = in && !fast;
+    anygate |= askgate[u];
+    dout[u] = d[u];
+  }
+  if (METRIC != DRRT_METRIC_EUCLID && __any_sync(0xffffffffu, anygate)) {
+#pragma unroll
+    for (int u = 0; u < UNR; u++)
+      if (askgate[u]) hit[u] = !(Q.t - gate[id[u]] > Q.r);
+  }
+  if (Q.has_ghost) {  // kdtree.cpp:807-819; uniform
+    bool needg[UNR], any = false;
+#pragma unroll
+    for (int u = 0; u < UNR; u++) {
+      needg[u] = valid[u] && !hit[u] && (s[u] < B.s_band || !(nt[u] >= B.nlo && nt[u] <= B.nhi));
+      any |= needg[u];
+    }
+    if (__any_sync(0xffffffffu, any)) {
+      double s2[UNR], d2[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; u++) s2[u] = metric_sum<METRIC>(Q.x, Q.y, Q.gt, nx[u], ny[u], nt[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; u++) d2[u] = sqrt(s2[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; u++) {
+        const bool in = needg[u] && s2[u] < Q.s_hi && d2[u] < Q.r;
+        bool ok = in;
+        if (METRIC != DRRT_METRIC_EUCLID && in && (Q.gt - nt[u] > Q.r)) ok = !(Q.gt - gate[id[u]] > Q.r);
+        if (ok) { hit[u] = true; dout[u] = d2[u]; }
+      }
     }
   }
 }
@@ -240,7 +265,7 @@ __device__ void order_by_id(unsigned long long *keys, int n, int *hist, int *s_m
     for (int i = tid; i < n; i += T) order[i] = (uint16_t)(keys[i] & 0xffffu);
     group_sync<BLOCK>();
     // un-permute: slot s must again hold the key that owns sdist[s]
-    unsigned long long mine[(BLOCK ? BLOCK_STAGE : WARP_STAGE) / T + 1];
+    unsigned long long mine[WARP_STAGE / T + 1];
     int c = 0;
     for (int i = tid; i < n; i += T) mine[c++] = keys[i];
     group_sync<BLOCK>();
@@ -295,167 +320,114 @@ __device__ void order_by_id(unsigned long long *keys, int n, int *hist, int *s_m
   group_sync<BLOCK>();
 }
 
-// Ordered allocation: CTA `vb` publishes its hit total, later receives the sum
-// of all earlier CTAs' totals (decoupled look-back; vb comes from a ticket so
-// every predecessor is already running).
-static constexpr unsigned long long FLAG_AGG = 1ull << 62, FLAG_PREFIX = 2ull << 62;
-static constexpr unsigned long long VAL_MASK = (1ull << 62) - 1;
-
-__device__ __forceinline__ void lookback_publish(unsigned long long *desc, int vb, long long agg) {
-  volatile unsigned long long *vd = desc;
-  vd[vb] = (vb == 0 ? FLAG_PREFIX : FLAG_AGG) | (unsigned long long)agg;
-}
-
-__device__ long long lookback_resolve(unsigned long long *desc, int vb, long long agg, int lane) {
-  volatile unsigned long long *vd = desc;
-  if (vb == 0) return 0;
-  long long excl = 0;
-  int pos = vb - 1;
-  for (;;) {
-    // each lane inspects one predecessor, most recent first
-    int idx = pos - lane;
-    unsigned long long v = 0;
-    if (idx >= 0) {
-      do { v = vd[idx]; } while ((v >> 62) == 0);
-    }
-    unsigned has_prefix = __ballot_sync(0xffffffffu, idx >= 0 && (v >> 62) == 2);
-    int stop = has_prefix ? (__ffs(has_prefix) - 1) : 31;
-    long long contrib = (idx >= 0 && lane <= stop) ? (long long)(v & VAL_MASK) : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-    excl += contrib;
-    if (has_prefix || pos - 32 < 0) break;
-    pos -= 32;
-  }
-  if (lane == 0) vd[vb] = FLAG_PREFIX | (unsigned long long)(excl + agg);
-  return excl;
-}
-
-template <int METRIC, bool BLOCK>
-__global__ void __launch_bounds__(BLOCK ? BLOCK_MODE_WARPS * 32 : WARP_MODE_WARPS * 32, BLOCK ? 2 : 4)
-range_kernel(RangeArgs A) {
-  constexpr int WARPS = BLOCK ? BLOCK_MODE_WARPS : WARP_MODE_WARPS;
-  constexpr int T = WARPS * 32;
-  constexpr int STAGE = BLOCK ? BLOCK_STAGE : WARP_STAGE;
-  constexpr int NSTAGE = BLOCK ? 1 : WARPS;
-  constexpr int NB = BLOCK ? 4096 : 128;  // id buckets of the output sort
-  constexpr int RUN_SLOTS = BLOCK ? 2 * T : WARPS * RUNS_PER_BATCH;
+// ---------------------------------------------------------------------------
+// Warp-per-query kernel (small neighbourhoods, config 2b).  Every warp is on its own: it
+// takes a slice of consecutive queries from a ticket, answers them one after the other and
+// writes their rows back to back into the slice's share of the arena -- no barrier and no
+// ordered allocation between warps.  Per query: columns in batches of 32 (scan_columns),
+// hits ballot-compacted into the warp's staging area, ordered by a small counting sort on id
+// buckets, written with coalesced stores.
+template <int METRIC>
+__global__ void __launch_bounds__(WARP_MODE_WARPS * 32, 4) range_warp_kernel(RangeArgs A) {
+  constexpr int WARPS = WARP_MODE_WARPS, STAGE = WARP_STAGE, NB = 128;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_vb;
   __shared__ int s_count[WARPS];
-  __shared__ long long s_base;
-  __shared__ int s_runs[RUN_SLOTS];
-  __shared__ int s_pref[RUN_SLOTS + WARPS];
-  __shared__ long long s_tmp[WARPS];
-  __shared__ Query s_query;
-  __shared__ int s_hist[NSTAGE][NB + 1];
-  __shared__ int s_misc[NSTAGE][4 + WARPS];
-
+  __shared__ int s_runs[WARPS * RUNS_PER_BATCH];
+  __shared__ int s_pref[WARPS * (RUNS_PER_BATCH + 1)];
+  __shared__ int s_hist[WARPS][NB + 1];
+  __shared__ int s_misc[WARPS][4 + WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_vb = atomicAdd(A.ticket, 1);
-  if (threadIdx.x < WARPS) s_count[threadIdx.x] = 0;
-  __syncthreads();
-  const int vb = s_vb;
-
-  unsigned long long *all_keys = reinterpret_cast<unsigned long long *>(smem_raw);
-  double *all_dist = reinterpret_cast<double *>(all_keys + STAGE * NSTAGE);
-  uint16_t *all_order = reinterpret_cast<uint16_t *>(all_dist + STAGE * NSTAGE);
-
-  const int64_t qi = BLOCK ? (int64_t)vb : (int64_t)vb * WARPS + w;
-  const bool active = qi < A.nq;
-  const int g = BLOCK ? 0 : w;  // staging group of this thread
-  Query Q;
-  Sink K;
-  K.keys = all_keys + g * STAGE;
-  K.sdist = all_dist + g * STAGE;
-  K.counter = &s_count[g];
-  K.capacity = STAGE;
-  K.gids = nullptr;
-  K.gdist = nullptr;
-  uint16_t *order = all_order + g * STAGE;
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw) + w * STAGE;  // (id << 32) | slot
+  double *sdist = reinterpret_cast<double *>(smem_raw + (size_t)WARPS * STAGE * 8) + w * STAGE;
+  uint16_t *order = reinterpret_cast<uint16_t *>(smem_raw + (size_t)WARPS * STAGE * 16) + w * STAGE;
+  int *counter = &s_count[w];
   const GridView &V = A.V;
-  auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
-    double d = 0.0;
-    bool hit = valid && eval_candidate<METRIC>(Q, nx, ny, nt, id, V.gate, &d);
-    emit(K, hit, id, d, lane);
-  };
-  auto scan_all = [&]() {
-    if (BLOCK) {
-      if (V.n_indexed > 0) scan_columns_block<WARPS>(V, Q, s_runs, s_pref, s_tmp, visit);
-      scan_tail(V, w, WARPS, lane, visit);
-    } else {
-      if (V.n_indexed > 0)
-        scan_columns(V, Q, 0, 1, s_runs + w * RUNS_PER_BATCH, s_pref + w * (RUNS_PER_BATCH + 1),
-                     lane, visit);
-      scan_tail(V, 0, 1, lane, visit);
-    }
-  };
-  if (active) {  // uniform per CTA in CTA mode, per warp in warp mode
-    if (BLOCK) {
-      // one warp resolves the probe and the cell ranges for the whole CTA
-      if (w == 0) {
-        setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
-                            A.radius ? A.radius[qi] : A.radius_all, Q);
-        if (lane == 0) s_query = Q;
-      }
-      __syncthreads();
-      Q = s_query;
-    } else {
+  const unsigned ltmask = (1u << lane) - 1u;
+
+  for (;;) {
+    long long ck = 0;
+    if (lane == 0) ck = (long long)atomicAdd(A.ticket, 1);
+    ck = __shfl_sync(0xffffffffu, ck, 0);
+    if (ck >= A.nchunks) break;
+    const int64_t base = A.chunk_base ? A.chunk_base[ck] : ck * A.chunk_cap;
+    const int64_t cap = A.chunk_base ? A.chunk_base[ck + 1] - base : A.chunk_cap;
+    const int64_t q0 = ck * A.chunk_len, q1 = min(A.nq, q0 + (int64_t)A.chunk_len);
+    int64_t run = 0;
+    bool over = false;
+    for (int64_t qi = q0; qi < q1; qi++) {
+      Query Q;
       setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
                           A.radius ? A.radius[qi] : A.radius_all, Q);
+      const GhostBand GB = ghost_band<METRIC>(Q);
+      int32_t *gids = nullptr;
+      double *gdist = nullptr;
+      if (lane == 0) *counter = 0;
+      __syncwarp();
+      auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
+        bool hit;
+        double d;
+        eval_candidates<METRIC, 1>(Q, GB, &valid, &nx, &ny, &nt, &id, V.gate, &hit, &d);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (!m) return;
+        int pos = 0;
+        if (lane == 0) pos = atomicAdd(counter, __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (hit) {
+          const int slot = pos + __popc(m & ltmask);
+          if (gids) {
+            gids[slot] = id;
+            gdist[slot] = d;
+          } else if (slot < STAGE) {
+            keys[slot] = ((unsigned long long)(unsigned)id << 32) | (unsigned)slot;
+            sdist[slot] = d;
+          }
+        }
+      };
+      auto scan_all = [&]() {
+        if (V.n_indexed > 0)
+          scan_columns(V, Q, 0, 1, s_runs + w * RUNS_PER_BATCH, s_pref + w * (RUNS_PER_BATCH + 1), lane, visit);
+        scan_tail(V, 0, 1, lane, visit);
+      };
+      scan_all();
+      __syncwarp();
+      const int n = *counter;
+      const bool staged = n > 0 && n <= STAGE;
+      const bool fits = run + n <= cap;
+      if (lane == 0) {
+        A.offsets[qi] = base + run;
+        A.counts[qi] = n;
+        if (qi == A.nq - 1) A.offsets[A.nq] = base + run + n;
+      }
+      int32_t *oid = A.ids + base + run;
+      double *od = A.dist + base + run;
+      if (!fits) {
+        over = true;  // counted, not written: the host reruns with exact slices
+      } else if (staged) {
+        order_by_id<false, NB, 32>(keys, n, s_hist[w], s_misc[w], order, lane);
+        for (int i = lane; i < n; i += 32) {
+          const int slot = order[i];
+          oid[i] = (int32_t)(keys[slot] >> 32);
+          od[i] = sdist[slot];
+        }
+      } else if (n > 0) {
+        // more hits than the staging area: second pass straight into the arena
+        __syncwarp();
+        if (lane == 0) *counter = 0;
+        __syncwarp();
+        gids = oid;
+        gdist = od;
+        scan_all();
+        __syncwarp();
+        sort_pairs_global<false>(oid, od, n, lane, 32);
+      }
+      run += n;
+      __syncwarp();
     }
-    scan_all();
-  }
-  __syncthreads();
-
-  // ---- publish the CTA's hit total, then sort while predecessors finish
-  long long agg = 0;
-  if (w == 0) {
-    int c = (lane < (BLOCK ? 1 : WARPS)) ? s_count[lane] : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    agg = c;
-    if (lane == 0) lookback_publish(A.desc, vb, agg);
-  }
-  const int my_cnt = s_count[g];
-  const int tid = BLOCK ? (int)threadIdx.x : lane;
-  constexpr int GT = BLOCK ? T : 32;
-  const bool staged = active && my_cnt > 0 && my_cnt <= STAGE;  // uniform per group
-  if (staged) order_by_id<BLOCK, NB, GT>(K.keys, my_cnt, s_hist[g], s_misc[g], order, tid);
-  if (w == 0) {
-    long long excl = lookback_resolve(A.desc, vb, agg, lane);
-    if (lane == 0) s_base = excl;
-  }
-  __syncthreads();
-  long long my_off = s_base;
-  if (!BLOCK)
-    for (int i = 0; i < w; i++) my_off += s_count[i];
-  if (active && tid == 0) {
-    A.offsets[qi] = my_off;
-    A.counts[qi] = my_cnt;
-    if (qi == A.nq - 1) A.offsets[A.nq] = my_off + my_cnt;
-  }
-  if (!active || my_cnt == 0) return;   // uniform per group
-  if (my_off + my_cnt > A.cap) return;  // arena too small: the host grows it and reruns
-
-  int32_t *oid = A.ids + my_off;
-  double *od = A.dist + my_off;
-  if (staged) {
-    for (int i = tid; i < my_cnt; i += GT) {
-      int slot = order[i];
-      oid[i] = (int32_t)(K.keys[slot] >> 32);
-      od[i] = K.sdist[slot];
+    if (lane == 0) {
+      A.chunk_total[ck] = run;
+      atomicAdd(&A.totals[0], (unsigned long long)run);
+      if (over) atomicAdd(&A.totals[1], 1ull);
     }
-  } else {
-    // more hits than the staging area: second pass straight into the arena
-    group_sync<BLOCK>();
-    if (tid == 0) *K.counter = 0;
-    group_sync<BLOCK>();
-    K.gids = oid;
-    K.gdist = od;
-    scan_all();
-    group_sync<BLOCK>();
-    sort_pairs_global<BLOCK>(oid, od, my_cnt, tid, GT);
   }
 }
 
@@ -504,92 +476,6 @@ static constexpr int CTA_SMEM = CTA_OFF_RUNS + (CTA_RUNS_BYTES > CTA_CLIST_BYTES
 static_assert(CTA_OFF_HIST + CTA_STAGE * 8 <= CTA_SMEM, "fallback sort keys alias the sort scratch");
 static_assert(CTA_OFF_RUNS % 8 == 0 && CTA_OFF_HIST % 16 == 0 && CTA_OFF_WSTART % 16 == 0, "alignment");
 static_assert(CTA_STAGE % CTA_T == 0, "stage is a whole number of CTA trips");
-
-// Why the ghost can be skipped (wrap-aware metric, wrap point == the metric's period W):
-// with a = |q.theta - n.theta| the first probe's theta term is min(a, W - a), whose square is
-// the squared distance of a to the nearer of {0, W}; the ghost q.theta +- W sees
-// a' = |q.theta +- W - n.theta| instead.  For a <= 1.5 W that distance never shrinks
-// (it stays equal on the far side of the seam and grows on the near side), so
-// metric(ghost, n) >= metric(q, n) in exact arithmetic; in IEEE double each theta term
-// carries at most a few roundings of magnitudes <= |q.theta| + |n.theta| + 2W, which the
-// band (2^-46 relative to that magnitude, against 2^-52 roundings) covers.  Candidates
-// outside |n.theta - q.theta| <= 1.45 W or |n.theta| <= 64 always take the ghost pass, and
-// so does a candidate the first probe finds in range but the signed prune hides.
-struct GhostBand {
-  double s_band;    // first-probe squared sums at or above this cannot be rescued by the ghost
-  double nlo, nhi;  // n.theta interval in which that holds
-};
-
-template <int METRIC>
-__device__ __forceinline__ GhostBand ghost_band(const Query &Q) {
-  GhostBand B;
-  const double band = Q.r + 1.4210854715202004e-14 * (fabs(Q.t) + 64.0 + 2.0 * DRRT_TWO_PI + fabs(Q.r));
-  B.s_band = band * band * (1.0 + 1.4210854715202004e-14);
-  B.nlo = fmax(-64.0, Q.t - 1.45 * DRRT_TWO_PI);
-  B.nhi = fmin(64.0, Q.t + 1.45 * DRRT_TWO_PI);
-  if (METRIC == DRRT_METRIC_EUCLID || !(fabs(Q.t) <= 64.0) || !(B.s_band == B.s_band)) {
-    B.s_band = 1.0e308;  // every rejected candidate takes the ghost pass
-    B.nlo = 1.0;
-    B.nhi = -1.0;
-  }
-  return B;
-}
-
-// Candidate test of the CTA kernel: eval_candidate's predicate with the ghost probe behind ghost_band,
-// for UNR candidates at once, written straight-line (selects, no per-candidate
-// branches) so that the FP64 chains of the candidates overlap; the gate[] look-up and the ghost
-// pass stay behind warp-level branches because they are rare.
-template <int METRIC, int UNR>
-__device__ __forceinline__ void eval_candidates(const Query &Q, const GhostBand &B, const bool *valid,
-                                                const double *nx, const double *ny, const double *nt,
-                                                const int32_t *id, const double *gate, bool *hit,
-                                                double *dout) {
-  double s[UNR], d[UNR];
-  bool askgate[UNR];
-#pragma unroll
-  for (int u = 0; u < UNR; u++) s[u] = metric_sum<METRIC>(Q.x, Q.y, Q.t, nx[u], ny[u], nt[u]);
-#pragma unroll
-  for (int u = 0; u < UNR; u++) d[u] = sqrt(s[u]);
-  bool anygate = false;
-#pragma unroll
-  for (int u = 0; u < UNR; u++) {
-    const bool pre = valid[u] && s[u] < Q.s_hi;
-    const bool root = id[u] == 0;
-    const bool in = pre && (root ? d[u] <= Q.r : d[u] < Q.r);     // kdtree.cpp:800-802, :733, :765
-    const bool fast = METRIC == DRRT_METRIC_EUCLID || root || !(Q.t - nt[u] > Q.r);  // walk_reaches, first clause
-    hit[u] = in && fast;
-    askgate[u] = in && !fast;
-    anygate |= askgate[u];
-    dout[u] = d[u];
-  }
-  if (METRIC != DRRT_METRIC_EUCLID && __any_sync(0xffffffffu, anygate)) {
-#pragma unroll
-    for (int u = 0; u < UNR; u++)
-      if (askgate[u]) hit[u] = !(Q.t - gate[id[u]] > Q.r);
-  }
-  if (Q.has_ghost) {  // kdtree.cpp:807-819; uniform
-    bool needg[UNR], any = false;
-#pragma unroll
-    for (int u = 0; u < UNR; u++) {
-      needg[u] = valid[u] && !hit[u] && (s[u] < B.s_band || !(nt[u] >= B.nlo && nt[u] <= B.nhi));
-      any |= needg[u];
-    }
-    if (__any_sync(0xffffffffu, any)) {
-      double s2[UNR], d2[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; u++) s2[u] = metric_sum<METRIC>(Q.x, Q.y, Q.gt, nx[u], ny[u], nt[u]);
-#pragma unroll
-      for (int u = 0; u < UNR; u++) d2[u] = sqrt(s2[u]);
-#pragma unroll
-      for (int u = 0; u < UNR; u++) {
-        const bool in = needg[u] && s2[u] < Q.s_hi && d2[u] < Q.r;
-        bool ok = in;
-        if (METRIC != DRRT_METRIC_EUCLID && in && (Q.gt - nt[u] > Q.r)) ok = !(Q.gt - gate[id[u]] > Q.r);
-        if (ok) { hit[u] = true; dout[u] = d2[u]; }
-      }
-    }
-  }
-}
 
 template <int METRIC>
 __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
@@ -824,28 +710,40 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
   }
 }
 
-static int cta_kernel_grid(int metric, int *grid) {
-  static int per_sm[2] = {0, 0}, sms = 0;
-  const int mi = metric == DRRT_METRIC_EUCLID ? 1 : 0;
-  if (!per_sm[mi]) {
+static constexpr int WARP_SMEM = WARP_STAGE * WARP_MODE_WARPS * 18;
+
+// resident CTAs of the persistent kernels (occupancy x SMs), per metric and kernel
+static int kernel_grid(int metric, bool block_mode, int *grid) {
+  static int per_sm[2][2] = {{0, 0}, {0, 0}}, sms = 0;
+  const int mi = metric == DRRT_METRIC_EUCLID ? 1 : 0, ki = block_mode ? 1 : 0;
+  if (!per_sm[mi][ki]) {
     int dev = 0, v = 0;
     DRRT_CUDA(cudaGetDevice(&dev));
     DRRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (mi) {
-      DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<DRRT_METRIC_EUCLID>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
-      DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &v, range_cta_kernel<DRRT_METRIC_EUCLID>, CTA_T, CTA_SMEM));
+    if (block_mode) {
+      if (mi) {
+        DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<DRRT_METRIC_EUCLID>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
+        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &v, range_cta_kernel<DRRT_METRIC_EUCLID>, CTA_T, CTA_SMEM));
+      } else {
+        DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<DRRT_METRIC_R2S1_WRAP>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
+        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &v, range_cta_kernel<DRRT_METRIC_R2S1_WRAP>, CTA_T, CTA_SMEM));
+      }
     } else {
-      DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<DRRT_METRIC_R2S1_WRAP>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
-      DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &v, range_cta_kernel<DRRT_METRIC_R2S1_WRAP>, CTA_T, CTA_SMEM));
+      if (mi)
+        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &v, range_warp_kernel<DRRT_METRIC_EUCLID>, WARP_MODE_WARPS * 32, WARP_SMEM));
+      else
+        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &v, range_warp_kernel<DRRT_METRIC_R2S1_WRAP>, WARP_MODE_WARPS * 32, WARP_SMEM));
     }
-    if (v < 1) return set_error(DRRT_ERR_CUDA, "range: CTA kernel does not fit an SM");
-    per_sm[mi] = v;
+    if (v < 1) return set_error(DRRT_ERR_CUDA, "range: kernel does not fit an SM");
+    per_sm[mi][ki] = v;
   }
-  *grid = per_sm[mi] * sms;
+  *grid = per_sm[mi][ki] * sms;
   return DRRT_OK;
 }
 
@@ -987,103 +885,71 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
   A.q = q_dev; A.radius = radius_dev; A.radius_all = radius_all; A.nq = nq;
   A.offsets = S->r_offsets.p; A.counts = S->r_counts.p; A.ticket = S->d_ticket;
 
-  if (block_mode) {
-    // slices of chunk_len consecutive rows, sized from the expected neighbourhood; a small
-    // batch takes shorter slices so that every resident CTA still gets several of them
-    int grid = 0;
-    DRRT_CHECK(cta_kernel_grid(S->metric, &grid));
-    const int chunk_len = (int)std::max<int64_t>(1, std::min<int64_t>(CTA_CHUNK, nq / (4 * (int64_t)grid)));
-    const int64_t nchunks = (nq + chunk_len - 1) / chunk_len;
-    int64_t rowcap = (int64_t)(expected * 1.1 + 6.0 * sqrt(expected) + 64.0);
-    rowcap = std::min<int64_t>(rowcap, S->n);
-    DRRT_CHECK(S->r_chunk_total.reserve(nchunks + 1, st));
-    A.chunk_len = chunk_len;
-    A.nchunks = nchunks;
-    A.chunk_cap = rowcap * chunk_len;
-    A.chunk_base = nullptr;
-    A.chunk_total = S->r_chunk_total.p;
-    A.totals = (unsigned long long *)S->d_totals;
-    grid = (int)std::min<int64_t>(grid, nchunks);
-    int64_t extent = nchunks * A.chunk_cap;
-    for (int attempt = 0; attempt < 2; attempt++) {
-      DRRT_CHECK(S->r_ids.reserve(extent + 1, st));
-      DRRT_CHECK(S->r_dist.reserve(extent + 1, st));
-      A.ids = S->r_ids.p; A.dist = S->r_dist.p;
-      DRRT_CUDA(cudaMemsetAsync(S->d_ticket, 0, sizeof(int32_t), st));
-      DRRT_CUDA(cudaMemsetAsync(S->d_totals, 0, 2 * sizeof(unsigned long long), st));
+  // Both kernels write slices of chunk_len consecutive rows, sized from the expected
+  // neighbourhood; a small batch takes shorter slices so that every resident CTA (warp) still
+  // gets several of them.
+  int grid = 0;
+  DRRT_CHECK(kernel_grid(S->metric, block_mode, &grid));
+  const int64_t workers = block_mode ? grid : (int64_t)grid * WARP_MODE_WARPS;
+  const int chunk_len = (int)std::max<int64_t>(1, std::min<int64_t>(CTA_CHUNK, nq / (4 * workers)));
+  const int64_t nchunks = (nq + chunk_len - 1) / chunk_len;
+  int64_t rowcap = (int64_t)(expected * 1.1 + 6.0 * sqrt(expected) + 64.0);
+  rowcap = std::min<int64_t>(rowcap, S->n);
+  DRRT_CHECK(S->r_chunk_total.reserve(nchunks + 1, st));
+  A.chunk_len = chunk_len;
+  A.nchunks = nchunks;
+  A.chunk_cap = rowcap * chunk_len;
+  A.chunk_base = nullptr;
+  A.chunk_total = S->r_chunk_total.p;
+  A.totals = (unsigned long long *)S->d_totals;
+  grid = (int)std::min<int64_t>(grid, block_mode ? nchunks : (nchunks + WARP_MODE_WARPS - 1) / WARP_MODE_WARPS);
+  int64_t extent = nchunks * A.chunk_cap;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    DRRT_CHECK(S->r_ids.reserve(extent + 1, st));
+    DRRT_CHECK(S->r_dist.reserve(extent + 1, st));
+    A.ids = S->r_ids.p; A.dist = S->r_dist.p;
+    DRRT_CUDA(cudaMemsetAsync(S->d_ticket, 0, sizeof(int32_t), st));
+    DRRT_CUDA(cudaMemsetAsync(S->d_totals, 0, 2 * sizeof(unsigned long long), st));
+    if (block_mode) {
       if (S->metric == DRRT_METRIC_EUCLID)
         range_cta_kernel<DRRT_METRIC_EUCLID><<<grid, CTA_T, CTA_SMEM, st>>>(A);
       else
         range_cta_kernel<DRRT_METRIC_R2S1_WRAP><<<grid, CTA_T, CTA_SMEM, st>>>(A);
-      DRRT_LAUNCHED();
-      DRRT_CUDA(cudaGetLastError());
-      DRRT_CUDA(cudaMemcpyAsync(S->h_scalar, S->d_totals, 2 * sizeof(int64_t),
-                                cudaMemcpyDeviceToHost, st));
-      DRRT_CUDA(cudaStreamSynchronize(st));
-      const int64_t total = S->h_scalar[0], overflowed = S->h_scalar[1];
-      if (overflowed == 0) {
-        S->last_nq = nq;
-        S->last_total = total;
-        S->last_extent = extent;
-        S->last_packed = A.chunk_base != nullptr;
-        fill_result(S, out);
-        return DRRT_OK;
-      }
-      if (attempt == 1) break;
-      // some slice was too small: the counts are exact, rerun with exact slices
-      std::vector<int64_t> tot((size_t)nchunks), cb((size_t)nchunks + 1);
-      DRRT_CUDA(cudaMemcpyAsync(tot.data(), S->r_chunk_total.p, nchunks * sizeof(int64_t),
-                                cudaMemcpyDeviceToHost, st));
-      DRRT_CUDA(cudaStreamSynchronize(st));
-      cb[0] = 0;
-      for (int64_t c = 0; c < nchunks; c++) cb[c + 1] = cb[c] + tot[c];
-      DRRT_CHECK(S->r_chunk_base.reserve(nchunks + 1, st));
-      DRRT_CUDA(cudaMemcpyAsync(S->r_chunk_base.p, cb.data(), (nchunks + 1) * sizeof(int64_t),
-                                cudaMemcpyHostToDevice, st));
-      DRRT_CUDA(cudaStreamSynchronize(st));
-      A.chunk_base = S->r_chunk_base.p;
-      extent = cb[nchunks];
+    } else {
+      if (S->metric == DRRT_METRIC_EUCLID)
+        range_warp_kernel<DRRT_METRIC_EUCLID><<<grid, WARP_MODE_WARPS * 32, WARP_SMEM, st>>>(A);
+      else
+        range_warp_kernel<DRRT_METRIC_R2S1_WRAP><<<grid, WARP_MODE_WARPS * 32, WARP_SMEM, st>>>(A);
     }
-    return set_error(DRRT_ERR_STATE, "range: result slices did not converge");
-  }
-
-  // warp-per-query kernel: ordered allocation in the kernel, plain CSR
-  const int64_t nvb = (nq + WARP_MODE_WARPS - 1) / WARP_MODE_WARPS;
-  DRRT_CHECK(S->r_desc.reserve(nvb, st));
-  int64_t guess = (int64_t)std::min(1.0e12, expected * 1.3 * (double)nq) + 1024;
-  if ((int64_t)S->r_ids.cap < guess) {
-    DRRT_CHECK(S->r_ids.reserve(guess, st));
-    DRRT_CHECK(S->r_dist.reserve(guess, st));
-  }
-  A.desc = S->r_desc.p;
-  for (int attempt = 0; attempt < 3; attempt++) {
-    A.ids = S->r_ids.p; A.dist = S->r_dist.p;
-    A.cap = (int64_t)std::min(S->r_ids.cap, S->r_dist.cap);
-    DRRT_CUDA(cudaMemsetAsync(S->r_desc.p, 0, nvb * sizeof(unsigned long long), st));
-    DRRT_CUDA(cudaMemsetAsync(S->d_ticket, 0, sizeof(int32_t), st));
-    const size_t smem = (size_t)WARP_STAGE * WARP_MODE_WARPS * 18;
-    if (S->metric == DRRT_METRIC_EUCLID)
-      range_kernel<DRRT_METRIC_EUCLID, false><<<(unsigned)nvb, WARP_MODE_WARPS * 32, smem, st>>>(A);
-    else
-      range_kernel<DRRT_METRIC_R2S1_WRAP, false><<<(unsigned)nvb, WARP_MODE_WARPS * 32, smem, st>>>(A);
     DRRT_LAUNCHED();
     DRRT_CUDA(cudaGetLastError());
-    DRRT_CUDA(cudaMemcpyAsync(S->h_scalar, S->r_offsets.p + nq, sizeof(int64_t),
-                              cudaMemcpyDeviceToHost, st));
+    DRRT_CUDA(cudaMemcpyAsync(S->h_scalar, S->d_totals, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     DRRT_CUDA(cudaStreamSynchronize(st));
-    int64_t total = S->h_scalar[0];
-    if (total <= A.cap) {
+    const int64_t total = S->h_scalar[0], overflowed = S->h_scalar[1];
+    if (overflowed == 0) {
       S->last_nq = nq;
       S->last_total = total;
-      S->last_extent = total;
-      S->last_packed = true;
+      S->last_extent = extent;
+      S->last_packed = A.chunk_base != nullptr;
       fill_result(S, out);
       return DRRT_OK;
     }
-    DRRT_CHECK(S->r_ids.reserve(total + total / 8 + 1024, st));
-    DRRT_CHECK(S->r_dist.reserve(total + total / 8 + 1024, st));
+    if (attempt == 1) break;
+    // some slice was too small: the counts are exact, rerun with exact slices
+    std::vector<int64_t> tot((size_t)nchunks), cb((size_t)nchunks + 1);
+    DRRT_CUDA(cudaMemcpyAsync(tot.data(), S->r_chunk_total.p, nchunks * sizeof(int64_t),
+                              cudaMemcpyDeviceToHost, st));
+    DRRT_CUDA(cudaStreamSynchronize(st));
+    cb[0] = 0;
+    for (int64_t c = 0; c < nchunks; c++) cb[c + 1] = cb[c] + tot[c];
+    DRRT_CHECK(S->r_chunk_base.reserve(nchunks + 1, st));
+    DRRT_CUDA(cudaMemcpyAsync(S->r_chunk_base.p, cb.data(), (nchunks + 1) * sizeof(int64_t),
+                              cudaMemcpyHostToDevice, st));
+    DRRT_CUDA(cudaStreamSynchronize(st));
+    A.chunk_base = S->r_chunk_base.p;
+    extent = cb[nchunks];
   }
-  return set_error(DRRT_ERR_STATE, "range: result arena did not converge");
+  return set_error(DRRT_ERR_STATE, "range: result slices did not converge");
 }
 
 }  // namespace drrt

@@ -68,7 +68,6 @@ struct Store {
   DevBuf<int64_t> r_offsets;  // nq+1
   DevBuf<int32_t> r_ids;
   DevBuf<double> r_dist;
-  DevBuf<unsigned long long> r_desc;  // look-back descriptors (warp-per-query kernel)
   DevBuf<int32_t> r_counts;           // nq
   DevBuf<int64_t> r_chunk_total, r_chunk_base;  // CTA kernel: per-slice hit totals / exact slice starts
   // plain-CSR copy of a sliced result (range_pack_dev)

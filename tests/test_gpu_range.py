@@ -224,12 +224,17 @@ def test_range_dev_sliced_rows_and_pack(drrt, po):
     assert res2.packed == 1 and res2.extent == res2.total == roff[-1]
     off2, cnt2, ids2, dist2 = _rows_dev(drrt, res2)
     assert np.array_equal(off2, roff) and np.array_equal(ids2, rids) and np.array_equal(dist2, rdist)
-    # the small-neighbourhood kernel already answers with a plain CSR
+    # the small-neighbourhood (warp-per-query) kernel writes slices too
     res3 = t.KDFindWithinRange_dev(0.8, torch.from_numpy(q).cuda())
-    assert res3.packed == 1
-    off3, cnt3, ids3, _ = _rows_dev(drrt, res3)
-    soff, sids, _ = r.range_batch(q, 0.8)
-    assert np.array_equal(off3, soff) and np.array_equal(ids3, sids) and np.array_equal(cnt3, np.diff(soff))
+    off3, cnt3, ids3, dist3 = _rows_dev(drrt, res3)
+    soff, sids, sdist = r.range_batch(q, 0.8)
+    assert np.array_equal(cnt3, np.diff(soff)) and (off3[1:] >= off3[:-1] + cnt3).all()
+    for i in range(len(q)):
+        assert np.array_equal(ids3[off3[i]:off3[i] + cnt3[i]], sids[soff[i]:soff[i + 1]])
+        assert np.array_equal(dist3[off3[i]:off3[i] + cnt3[i]], sdist[soff[i]:soff[i + 1]])
+    res4 = t.range_pack()
+    off4, _, ids4, dist4 = _rows_dev(drrt, res4)
+    assert res4.packed == 1 and np.array_equal(off4, soff) and np.array_equal(ids4, sids) and np.array_equal(dist4, sdist)
 
 
 def test_range_slice_overflow_reruns_exact(drrt, po):
