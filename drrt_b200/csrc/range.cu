@@ -19,11 +19,12 @@
 // CTA (large ones) scans the candidate columns of its query in the cell-sorted
 // 32-byte NodeRec array -- runs flattened so every lane holds a candidate --
 // evaluates the f64 metric in the reference's operation order and compacts the
-// hits with ballots into shared memory.  The CTA publishes its hit total, and
-// while the in-kernel ordered allocation (decoupled look-back over CTA totals)
-// resolves, orders the staged hits by node id with a counting sort on id
-// buckets in shared memory.  The rows then go to their final CSR position
-// with coalesced stores.
+// hits with ballots into shared memory, orders them by node id (counting sort
+// on id buckets) and writes the row with coalesced stores.  Persistent warps /
+// CTAs take SLICES of consecutive queries from a ticket and write their rows
+// back to back into the slice's share of the result arena (rows addressed by
+// offsets[q] / counts[q]), so nothing is allocated in order across CTAs and
+// nobody waits for a predecessor; range_pack_dev makes a plain CSR of it.
 #include <math.h>
 
 #include <algorithm>
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, 4) range_warp_kernel(Ran
 //  * persistent CTAs take CHUNKS of CTA_CHUNK consecutive queries from a ticket
 //    and write the chunk's rows back to back into the chunk's own slice of the
 //    result arena -- no ordered allocation across CTAs, hence no CTA ever waits
-//    for a predecessor (the look-back of the generic kernel cost ~15 % here).
+//    for a predecessor (the decoupled look-back of the first version cost ~15 % here).
 //    Rows are addressed by offsets[q] / counts[q]; slices are sized from the
 //    expected neighbourhood and leave unused slots between chunks.  If a chunk
 //    overflows its slice the host reruns with exact slice sizes;
