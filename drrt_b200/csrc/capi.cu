@@ -226,7 +226,7 @@ int drrt_store_destroy(drrt_store *h) {
     if (S->d_ticket) cudaFree(S->d_ticket);
     if (S->d_edge_counter) cudaFree(S->d_edge_counter);
     S->x_unsafe.release(); S->x_len.release(); S->x_lmc.release(); S->x_best.release(); S->x_best_cost.release();
-    S->edge_paths.release(); S->og_off.release(); S->og_idx.release(); S->og_eobs.release();
+    S->edge_paths.release(); S->edge_masks.release(); S->edge_perm.release(); S->edge_bins.release(); S->og_off.release(); S->og_idx.release(); S->og_eobs.release();
     S->og_ball.release(); S->og_eax.release(); S->og_eay.release(); S->og_ebx.release(); S->og_eby.release();
     if (S->d_bounds) cudaFree(S->d_bounds);
     if (S->h_pending) cudaFreeHost(S->h_pending);
@@ -638,11 +638,11 @@ int drrt_dubins_trajectory_batch(drrt_store *h, int64_t n, const double *start, 
                                  double r_min, double *xy, int32_t *npts, char *type,
                                  double *length) {
   ENTER(h);
-  if (n < 0 || (n > 0 && (!start || !end || !xy || !npts)))
+  if (n < 0 || (n > 0 && (!start || !end || (xy && !npts) || (!xy && !type && !length))))
     return set_error(DRRT_ERR_INVALID, "trajectory: arguments");
   if (n == 0) return DRRT_OK;
   cudaStream_t st = S->stream;
-  const size_t per = (size_t)DRRT_TRAJ_MAX * 2;
+  const size_t per = xy ? (size_t)DRRT_TRAJ_MAX * 2 : 0;  // xy == NULL: word and length only
   DRRT_CHECK(S->d_stage.reserve(3 * n, st));
   DRRT_CHECK(S->d_stage2.reserve(3 * n, st));
   DRRT_CHECK(S->d_stage3.reserve(n * per + n, st));
@@ -651,10 +651,10 @@ int drrt_dubins_trajectory_batch(drrt_store *h, int64_t n, const double *start, 
   DRRT_CHECK(upload(start, S->d_stage.p, 3 * n * sizeof(double), st));
   DRRT_CHECK(upload(end, S->d_stage2.p, 3 * n * sizeof(double), st));
   double *len_dev = S->d_stage3.p + n * per;
-  DRRT_CHECK(trajectory_batch_dev(S, n, S->d_stage.p, S->d_stage2.p, r_min, S->d_stage3.p,
+  DRRT_CHECK(trajectory_batch_dev(S, n, S->d_stage.p, S->d_stage2.p, r_min, xy ? S->d_stage3.p : nullptr,
                                   S->i_stage.p, (char *)S->b_stage.p, len_dev, st));
-  DRRT_CHECK(download(xy, S->d_stage3.p, n * per * sizeof(double), st));
-  DRRT_CHECK(download(npts, S->i_stage.p, n * sizeof(int32_t), st));
+  if (xy) DRRT_CHECK(download(xy, S->d_stage3.p, n * per * sizeof(double), st));
+  if (npts) DRRT_CHECK(download(npts, S->i_stage.p, n * sizeof(int32_t), st));
   if (type) DRRT_CHECK(download(type, S->b_stage.p, 4 * n, st));
   if (length) DRRT_CHECK(download(length, len_dev, n * sizeof(double), st));
   DRRT_CUDA(cudaStreamSynchronize(st));

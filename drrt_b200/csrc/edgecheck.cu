@@ -37,6 +37,7 @@
 namespace drrt {
 
 static constexpr int EDGE_T = 128;
+static constexpr int64_t RANKED_SOLVE_MIN = 16384;  // smaller Dubins batches take the one-kernel solve
 #ifndef DRRT_PF_AHEAD
 #define DRRT_PF_AHEAD 8192
 #endif
@@ -324,17 +325,8 @@ __device__ __forceinline__ bool region_empty(const ObstacleGrid &G, double lox, 
   return true;
 }
 
-// K4a: Edge::NewEdge + the candidate solve of CalculateTrajectory, one thread per edge
-__global__ void __launch_bounds__(EDGE_T)
-dubins_solve_kernel(EdgeArgs A, DubinsPath *paths) {
-  const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
-  if (e >= A.n) return;
-  double sx, sy, st, ex, ey, et;
-  load_pose(A, e, false, sx, sy, st);
-  load_pose(A, e, true, ex, ey, et);
-  DubinsPath P;
-  double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
-  dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
+// marks the parts of a solved path that cannot collide and stores the record
+__device__ __forceinline__ void finish_path(const EdgeArgs &A, int64_t e, DubinsPath &P, DubinsPath *paths) {
   if (A.obs.n > 0 && A.grid.nx > 0) {
     // parts whose whole circle (or straight piece) lies where no obstacle comes within the
     // robot radius need no per-segment test; a path made only of such parts is free
@@ -354,6 +346,103 @@ dubins_solve_kernel(EdgeArgs A, DubinsPath *paths) {
   }
   paths[e] = P;
   if (A.length) A.length[e] = P.dist;
+}
+
+// K4a: Edge::NewEdge + the candidate solve of CalculateTrajectory, one thread per edge, all
+// six candidates in double (small batches; the ranked pipeline below is the fast path)
+__global__ void __launch_bounds__(EDGE_T)
+dubins_solve_kernel(EdgeArgs A, DubinsPath *paths) {
+  const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
+  if (e >= A.n) return;
+  double sx, sy, st, ex, ey, et;
+  load_pose(A, e, false, sx, sy, st);
+  load_pose(A, e, true, ex, ey, et);
+  DubinsPath P;
+  double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
+  dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
+  finish_path(A, e, P, paths);
+}
+
+// K4a, ranked: the double-precision solve of all six Dubins words costs ~5800 instructions per
+// edge (22 atan2, 2 acos, 6 sincos) and 142 registers.  Here a float32 pass first lists the
+// candidates that can be the shortest (dubins_rank: almost always exactly one), the edges are
+// binned by that list (six single-candidate bins + one for everything else), and each bin is
+// solved by a kernel specialised for its candidate (~70 registers, a sixth of the work).
+static constexpr int RANK_BINS = 7;
+
+__device__ __forceinline__ int rank_bin(int mask) {
+  return (__popc(mask) == 1) ? (__ffs(mask) - 1) : (RANK_BINS - 1);
+}
+
+__global__ void __launch_bounds__(256)
+dubins_rank_kernel(EdgeArgs A, uint8_t *masks, unsigned long long *bin_count) {
+  __shared__ unsigned s_hist[RANK_BINS];
+  if (threadIdx.x < RANK_BINS) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < A.n) {
+    double sx, sy, st, ex, ey, et;
+    load_pose(A, e, false, sx, sy, st);
+    load_pose(A, e, true, ex, ey, et);
+    const int mask = dubins_rank(sx, sy, st, ex, ey, et, A.r_min);
+    masks[e] = (uint8_t)mask;
+    atomicAdd(&s_hist[rank_bin(mask)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < RANK_BINS && s_hist[threadIdx.x])
+    atomicAdd(&bin_count[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+}
+
+// bin_state: [0..7) counts, [8..16) exclusive starts (8 entries), [16..23) scatter cursors
+__global__ void dubins_bin_scan_kernel(unsigned long long *bin_state) {
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int b = 0; b < RANK_BINS; b++) {
+      bin_state[8 + b] = acc;
+      bin_state[16 + b] = acc;
+      acc += bin_state[b];
+    }
+    bin_state[8 + RANK_BINS] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dubins_bin_scatter_kernel(int64_t n, const uint8_t *masks, unsigned long long *bin_state, uint32_t *perm) {
+  __shared__ unsigned s_hist[RANK_BINS];
+  __shared__ unsigned long long s_base[RANK_BINS];
+  if (threadIdx.x < RANK_BINS) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int bin = 0;
+  unsigned local = 0;
+  if (e < n) {
+    bin = rank_bin(masks[e]);
+    local = atomicAdd(&s_hist[bin], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < RANK_BINS && s_hist[threadIdx.x])
+    s_base[threadIdx.x] = atomicAdd(&bin_state[16 + threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+  __syncthreads();
+  if (e < n) perm[s_base[bin] + local] = (uint32_t)e;
+}
+
+// MASK > 0: every edge of the bin has exactly that candidate list; MASK == 0: the list is read
+template <int MASK>
+__global__ void __launch_bounds__(EDGE_T)
+dubins_solve_bin_kernel(EdgeArgs A, DubinsPath *paths, const uint32_t *perm, const uint8_t *masks,
+                        const unsigned long long *bin_state, int bin) {
+  const unsigned long long lo = bin_state[8 + bin], hi = bin_state[8 + bin + 1];
+  for (unsigned long long i = lo + (unsigned long long)blockIdx.x * EDGE_T + threadIdx.x; i < hi;
+       i += (unsigned long long)gridDim.x * EDGE_T) {
+    const int64_t e = perm[i];
+    double sx, sy, st, ex, ey, et;
+    load_pose(A, e, false, sx, sy, st);
+    load_pose(A, e, true, ex, ey, et);
+    DubinsPath P;
+    double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
+    dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P, MASK ? MASK : (int)masks[e]);
+    finish_path(A, e, P, paths);
+  }
 }
 
 // K4b: polyline walk + ExplicitEdgeCheck2D per segment, lanes refill from a global counter
@@ -659,8 +748,33 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
     if (st != S->stream) DRRT_CUDA(cudaStreamSynchronize(S->stream));
     DRRT_CHECK(S->edge_paths.reserve((size_t)n * sizeof(DubinsPath), st));
     DubinsPath *paths = reinterpret_cast<DubinsPath *>(S->edge_paths.p);
-    dubins_solve_kernel<<<nb, EDGE_T, 0, st>>>(A, paths);
-    DRRT_LAUNCHED();
+    if (n < RANKED_SOLVE_MIN || n >= 0x7fffffff) {
+      dubins_solve_kernel<<<nb, EDGE_T, 0, st>>>(A, paths);
+      DRRT_LAUNCHED();
+    } else {
+      DRRT_CHECK(S->edge_masks.reserve((size_t)n, st));
+      DRRT_CHECK(S->edge_perm.reserve((size_t)n, st));
+      DRRT_CHECK(S->edge_bins.reserve(32, st));
+      unsigned long long *bins = S->edge_bins.p;
+      DRRT_CUDA(cudaMemsetAsync(bins, 0, 32 * sizeof(unsigned long long), st));
+      const unsigned nb256 = (unsigned)((n + 255) / 256);
+      dubins_rank_kernel<<<nb256, 256, 0, st>>>(A, S->edge_masks.p, bins);
+      dubins_bin_scan_kernel<<<1, 32, 0, st>>>(bins);
+      dubins_bin_scatter_kernel<<<nb256, 256, 0, st>>>(n, S->edge_masks.p, bins, S->edge_perm.p);
+      // one specialised solve per single-candidate bin, a generic one for the rest; persistent
+      // grids sized for the machine (a bin's extent is only known on the device)
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
+      const unsigned g = (unsigned)std::min<int64_t>(nb, (int64_t)sms * 12);
+      dubins_solve_bin_kernel<CAND_RSL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 0);
+      dubins_solve_bin_kernel<CAND_RSR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 1);
+      dubins_solve_bin_kernel<CAND_RLR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 2);
+      dubins_solve_bin_kernel<CAND_LSR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 3);
+      dubins_solve_bin_kernel<CAND_LSL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 4);
+      dubins_solve_bin_kernel<CAND_LRL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 5);
+      dubins_solve_bin_kernel<0><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 6);
+      for (int k = 0; k < 10; k++) DRRT_LAUNCHED();
+    }
     if (A.obs.n == 0) {
       DRRT_CUDA(cudaMemsetAsync(verdict_dev, 0, (size_t)n, st));  // nothing to collide with
     } else {
@@ -757,17 +871,19 @@ __global__ void trajectory_kernel(int64_t n, const double *start, const double *
   DubinsPath P;
   double edge_dist = metric_dist(metric, s[0], s[1], s[2], g[0], g[1], g[2]);
   dubins_solve(s[0], s[1], s[2], g[0], g[1], g[2], r_min, edge_dist, P);
-  PolylineWalker W;
-  W.start(&P, r_min);
-  double x, y;
-  int k = 0;
-  double *out = xy + (size_t)e * DRRT_TRAJ_MAX * 2;
-  while (k < DRRT_TRAJ_MAX && W.next(&x, &y)) {
-    out[2 * k] = x;
-    out[2 * k + 1] = y;
-    k++;
+  if (xy) {
+    PolylineWalker W;
+    W.start(&P, r_min);
+    double x, y;
+    int k = 0;
+    double *out = xy + (size_t)e * DRRT_TRAJ_MAX * 2;
+    while (k < DRRT_TRAJ_MAX && W.next(&x, &y)) {
+      out[2 * k] = x;
+      out[2 * k + 1] = y;
+      k++;
+    }
+    npts[e] = k;
   }
-  npts[e] = k;
   if (length) length[e] = P.dist;
   if (type) {
     const char *names = "xxx\0rsl\0rsr\0rlr\0lsr\0lsl\0lrl\0" "0s0\0";
@@ -778,7 +894,7 @@ __global__ void trajectory_kernel(int64_t n, const double *start, const double *
 int trajectory_batch_dev(Store *S, int64_t n, const double *start_dev, const double *end_dev,
                          double r_min, double *xy_dev, int32_t *npts_dev, char *type_dev,
                          double *length_dev, cudaStream_t st) {
-  if (n < 0 || !start_dev || !end_dev || !xy_dev || !npts_dev)
+  if (n < 0 || !start_dev || !end_dev || (xy_dev && !npts_dev))
     return set_error(DRRT_ERR_INVALID, "trajectory: arguments");
   if (n == 0) return DRRT_OK;
   trajectory_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, start_dev, end_dev, r_min,

@@ -148,58 +148,81 @@ __device__ __forceinline__ void arc_part(DubinsPath &out, int k, int kind, doubl
   P.b = atan2(ty - cy, tx - cx);
 }
 
-// edge_dist = Edge::NewEdge's dist_ (dubinsedge.cpp:19), read by the "0s0" test
+// Candidate bits, in the order CalculateTrajectory tries them.
+enum { CAND_RSL = 1, CAND_RSR = 2, CAND_RLR = 4, CAND_LSR = 8, CAND_LSL = 16, CAND_LRL = 32, CAND_ALL = 63 };
+
+// edge_dist = Edge::NewEdge's dist_ (dubinsedge.cpp:19), read by the "0s0" test.
+// `mask` lists the candidates to evaluate (CAND_ALL: all six, as the reference does).  The
+// winner is the first candidate, in the reference's order, of smallest length under the strict
+// `bestDist > len` test; leaving out candidates that are provably longer than the shortest
+// one changes neither the winner nor bestDist (dubins_rank below decides that, conservatively).
 __device__ void dubins_solve(double sx, double sy, double st, double ex, double ey, double et,
-                             double r_min, double edge_dist, DubinsPath &out) {
-  // :183-202 turn-circle centres
+                             double r_min, double edge_dist, DubinsPath &out, int mask = CAND_ALL) {
+  // :183-202 turn-circle centres (each only if a listed candidate uses it)
   double sn, cs;
-  sincos(st - (DRRT_PI / 2.0), &sn, &cs);
-  const double ircx = sx + r_min * cs, ircy = sy + r_min * sn;
-  sincos(st + (DRRT_PI / 2.0), &sn, &cs);
-  const double ilcx = sx + r_min * cs, ilcy = sy + r_min * sn;
-  sincos(et - (DRRT_PI / 2.0), &sn, &cs);
-  const double grcx = ex + r_min * cs, grcy = ey + r_min * sn;
-  sincos(et + (DRRT_PI / 2.0), &sn, &cs);
-  const double glcx = ex + r_min * cs, glcy = ey + r_min * sn;
+  double ircx = 0, ircy = 0, ilcx = 0, ilcy = 0, grcx = 0, grcy = 0, glcx = 0, glcy = 0;
+  if (mask & (CAND_RSL | CAND_RSR | CAND_RLR)) {
+    sincos(st - (DRRT_PI / 2.0), &sn, &cs);
+    ircx = sx + r_min * cs; ircy = sy + r_min * sn;
+  }
+  if (mask & (CAND_LSR | CAND_LSL | CAND_LRL)) {
+    sincos(st + (DRRT_PI / 2.0), &sn, &cs);
+    ilcx = sx + r_min * cs; ilcy = sy + r_min * sn;
+  }
+  if (mask & (CAND_RSR | CAND_RLR | CAND_LSR)) {
+    sincos(et - (DRRT_PI / 2.0), &sn, &cs);
+    grcx = ex + r_min * cs; grcy = ey + r_min * sn;
+  }
+  if (mask & (CAND_RSL | CAND_LSL | CAND_LRL)) {
+    sincos(et + (DRRT_PI / 2.0), &sn, &cs);
+    glcx = ex + r_min * cs; glcy = ey + r_min * sn;
+  }
 
   double best = DRRT_INF;
   int type = TRAJ_XXX;
-  double D, R, sq, a, b, d0, d1, v0, v1, first, second, third, len;
+  double D = 0, R, sq, a, b, d0, d1, v0 = 0, v1 = 0, first, second, third, len;
 
   // rsl :216-254
   double rsl_x0 = 0, rsl_x1 = 0, rsl_y0 = 0, rsl_y1 = 0;
-  d0 = glcx - ircx; d1 = glcy - ircy;
-  D = sqrt(d0 * d0 + d1 * d1);
-  v0 = d0 / D; v1 = d1 / D;
-  R = -2.0 * r_min / D;
-  if (!(fabs(R) > 1.0)) {
-    sq = sqrt(1.0 - R * R);
-    a = r_min * (R * v0 + v1 * sq);
-    b = r_min * (R * v1 - v0 * sq);
-    rsl_x0 = ircx - a; rsl_x1 = glcx + a;
-    rsl_y0 = ircy - b; rsl_y1 = glcy + b;
-    first = right_turn_dist(sx, sy, rsl_x0, rsl_y0, ircx, ircy, r_min);
-    second = len2(rsl_x1 - rsl_x0, rsl_y1 - rsl_y0);
-    third = left_turn_dist(rsl_x1, rsl_y1, ex, ey, glcx, glcy, r_min);
-    len = first + second + third;
-    if (best > len) { best = len; type = TRAJ_RSL; }
+  if (mask & CAND_RSL) {
+    d0 = glcx - ircx; d1 = glcy - ircy;
+    D = sqrt(d0 * d0 + d1 * d1);
+    v0 = d0 / D; v1 = d1 / D;
+    R = -2.0 * r_min / D;
+    if (!(fabs(R) > 1.0)) {
+      sq = sqrt(1.0 - R * R);
+      a = r_min * (R * v0 + v1 * sq);
+      b = r_min * (R * v1 - v0 * sq);
+      rsl_x0 = ircx - a; rsl_x1 = glcx + a;
+      rsl_y0 = ircy - b; rsl_y1 = glcy + b;
+      first = right_turn_dist(sx, sy, rsl_x0, rsl_y0, ircx, ircy, r_min);
+      second = len2(rsl_x1 - rsl_x0, rsl_y1 - rsl_y0);
+      third = left_turn_dist(rsl_x1, rsl_y1, ex, ey, glcx, glcy, r_min);
+      len = first + second + third;
+      if (best > len) { best = len; type = TRAJ_RSL; }
+    }
   }
 
   // rsr :257-290
-  d0 = grcx - ircx; d1 = grcy - ircy;
-  D = sqrt(d0 * d0 + d1 * d1);
-  v0 = d0 / D; v1 = d1 / D;
-  const double rsr_x0 = -r_min * v1 + ircx, rsr_x1 = -r_min * v1 + grcx;
-  const double rsr_y0 = r_min * v0 + ircy, rsr_y1 = r_min * v0 + grcy;
-  first = right_turn_dist(sx, sy, rsr_x0, rsr_y0, ircx, ircy, r_min);
-  second = len2(rsr_x1 - rsr_x0, rsr_y1 - rsr_y0);
-  third = right_turn_dist(rsr_x1, rsr_y1, ex, ey, grcx, grcy, r_min);
-  len = first + second + third;
-  if (best > len) { best = len; type = TRAJ_RSR; }
+  double rsr_x0 = 0, rsr_x1 = 0, rsr_y0 = 0, rsr_y1 = 0;
+  if (mask & (CAND_RSR | CAND_RLR)) {
+    d0 = grcx - ircx; d1 = grcy - ircy;
+    D = sqrt(d0 * d0 + d1 * d1);
+    v0 = d0 / D; v1 = d1 / D;
+  }
+  if (mask & CAND_RSR) {
+    rsr_x0 = -r_min * v1 + ircx; rsr_x1 = -r_min * v1 + grcx;
+    rsr_y0 = r_min * v0 + ircy; rsr_y1 = r_min * v0 + grcy;
+    first = right_turn_dist(sx, sy, rsr_x0, rsr_y0, ircx, ircy, r_min);
+    second = len2(rsr_x1 - rsr_x0, rsr_y1 - rsr_y0);
+    third = right_turn_dist(rsr_x1, rsr_y1, ex, ey, grcx, grcy, r_min);
+    len = first + second + third;
+    if (best > len) { best = len; type = TRAJ_RSR; }
+  }
 
   // rlr :293-328 (D, v of rsr)
   double rlr_rlx = 0, rlr_rly = 0, rlr_lrx = 0, rlr_lry = 0, rlr_cx = 0, rlr_cy = 0;
-  if (D < 4.0 * r_min) {
+  if ((mask & CAND_RLR) && D < 4.0 * r_min) {
     double theta = -acos(D / (4 * r_min)) + atan2(v1, v0);
     sincos(theta, &sn, &cs);
     rlr_cx = ircx + 2 * r_min * cs;
@@ -215,38 +238,45 @@ __device__ void dubins_solve(double sx, double sy, double st, double ex, double 
 
   // lsr :331-369
   double lsr_x0 = 0, lsr_x1 = 0, lsr_y0 = 0, lsr_y1 = 0;
-  d0 = grcx - ilcx; d1 = grcy - ilcy;
-  D = sqrt(d0 * d0 + d1 * d1);
-  v0 = d0 / D; v1 = d1 / D;
-  R = 2.0 * r_min / D;
-  if (!(fabs(R) > 1.0)) {
-    sq = sqrt(1.0 - R * R);
-    a = R * v0 + v1 * sq;
-    b = R * v1 - v0 * sq;
-    lsr_x0 = ilcx + a * r_min; lsr_x1 = grcx - a * r_min;
-    lsr_y0 = ilcy + b * r_min; lsr_y1 = grcy - b * r_min;
-    first = left_turn_dist(sx, sy, lsr_x0, lsr_y0, ilcx, ilcy, r_min);
-    second = len2(lsr_x1 - lsr_x0, lsr_y1 - lsr_y0);
-    third = right_turn_dist(lsr_x1, lsr_y1, ex, ey, grcx, grcy, r_min);
-    len = first + second + third;
-    if (best > len) { best = len; type = TRAJ_LSR; }
+  if (mask & CAND_LSR) {
+    d0 = grcx - ilcx; d1 = grcy - ilcy;
+    D = sqrt(d0 * d0 + d1 * d1);
+    v0 = d0 / D; v1 = d1 / D;
+    R = 2.0 * r_min / D;
+    if (!(fabs(R) > 1.0)) {
+      sq = sqrt(1.0 - R * R);
+      a = R * v0 + v1 * sq;
+      b = R * v1 - v0 * sq;
+      lsr_x0 = ilcx + a * r_min; lsr_x1 = grcx - a * r_min;
+      lsr_y0 = ilcy + b * r_min; lsr_y1 = grcy - b * r_min;
+      first = left_turn_dist(sx, sy, lsr_x0, lsr_y0, ilcx, ilcy, r_min);
+      second = len2(lsr_x1 - lsr_x0, lsr_y1 - lsr_y0);
+      third = right_turn_dist(lsr_x1, lsr_y1, ex, ey, grcx, grcy, r_min);
+      len = first + second + third;
+      if (best > len) { best = len; type = TRAJ_LSR; }
+    }
   }
 
   // lsl :372-405
-  d0 = glcx - ilcx; d1 = glcy - ilcy;
-  D = sqrt(d0 * d0 + d1 * d1);
-  v0 = d0 / D; v1 = d1 / D;
-  const double lsl_x0 = r_min * v1 + ilcx, lsl_x1 = r_min * v1 + glcx;
-  const double lsl_y0 = -r_min * v0 + ilcy, lsl_y1 = -r_min * v0 + glcy;
-  first = left_turn_dist(sx, sy, lsl_x0, lsl_y0, ilcx, ilcy, r_min);
-  second = len2(lsl_x1 - lsl_x0, lsl_y1 - lsl_y0);
-  third = left_turn_dist(lsl_x1, lsl_y1, ex, ey, glcx, glcy, r_min);
-  len = first + second + third;
-  if (best > len) { best = len; type = TRAJ_LSL; }
+  double lsl_x0 = 0, lsl_x1 = 0, lsl_y0 = 0, lsl_y1 = 0;
+  if (mask & (CAND_LSL | CAND_LRL)) {
+    d0 = glcx - ilcx; d1 = glcy - ilcy;
+    D = sqrt(d0 * d0 + d1 * d1);
+    v0 = d0 / D; v1 = d1 / D;
+  }
+  if (mask & CAND_LSL) {
+    lsl_x0 = r_min * v1 + ilcx; lsl_x1 = r_min * v1 + glcx;
+    lsl_y0 = -r_min * v0 + ilcy; lsl_y1 = -r_min * v0 + glcy;
+    first = left_turn_dist(sx, sy, lsl_x0, lsl_y0, ilcx, ilcy, r_min);
+    second = len2(lsl_x1 - lsl_x0, lsl_y1 - lsl_y0);
+    third = left_turn_dist(lsl_x1, lsl_y1, ex, ey, glcx, glcy, r_min);
+    len = first + second + third;
+    if (best > len) { best = len; type = TRAJ_LSL; }
+  }
 
   // lrl :408-443 (D, v of lsl; arc lengths R,L,R as the reference writes them)
   double lrl_rlx = 0, lrl_rly = 0, lrl_lrx = 0, lrl_lry = 0, lrl_cx = 0, lrl_cy = 0;
-  if (D < 4.0 * r_min) {
+  if ((mask & CAND_LRL) && D < 4.0 * r_min) {
     double theta = -acos(D / (4 * r_min)) + atan2(v1, v0);
     sincos(theta, &sn, &cs);
     lrl_cx = ilcx + 2 * r_min * cs;
@@ -303,6 +333,123 @@ __device__ void dubins_solve(double sx, double sy, double st, double ex, double 
     default:
       break;
   }
+}
+
+// Which candidates can be the shortest?  A float32 pass over all six (start pose moved to the
+// origin first, in double, so that magnitudes stay small) ranks them; a candidate is listed
+// when it may exist and its float length is within `margin` of the shortest candidate that
+// surely exists, or when the float pass cannot tell: it sits on an existence boundary (D near
+// 2r / 4r), has a turn angle near the 0 / 2pi jump of Right/LeftTurnDist, a degenerate centre
+// distance, or is not finite.  Float errors here are ~1e-6 * scale in coordinates and lengths;
+// bands and margin are 1e-3-sized, three orders above that.  The listed candidates are then
+// solved in double exactly as the reference does; the others are provably longer than the
+// winner, so the winner and bestDist are the reference's (dubins_solve).
+__device__ __forceinline__ int dubins_rank(double sx, double sy, double st, double ex, double ey,
+                                           double et, double r_min) {
+  const float TWO_PI_F = 6.28318530718f;
+  const float r = (float)r_min;
+  const float gx = (float)(ex - sx), gy = (float)(ey - sy);
+  const float scale = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fabsf(r));
+  // float32 is only trusted for ordinary geometry
+  if (!(r > 0.0f) || !(scale <= 64.0f * r) || !(fabs(st) <= 64.0) || !(fabs(et) <= 64.0)) return CAND_ALL;
+  const float band = 1e-3f * (r + scale);    // existence boundaries, degenerate D
+  const float margin = 2e-3f * (r + scale);  // length comparison
+  const float eps_th = 1e-3f;                // turn angles near the 0 / 2pi jump
+  float ss, cs0, se, ce;
+  sincosf((float)st, &ss, &cs0);
+  sincosf((float)et, &se, &ce);
+  // turn-circle centres relative to the start point (dubinsedge.cpp:183-202)
+  const float ircx = r * ss, ircy = -r * cs0, ilcx = -r * ss, ilcy = r * cs0;
+  const float grcx = gx + r * se, grcy = gy - r * ce, glcx = gx - r * se, glcy = gy + r * ce;
+  bool unsure[6] = {false, false, false, false, false, false};
+  bool exists[6] = {false, true, false, false, true, false};
+  float len[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto turn = [&](float ax, float ay, float bx, float by, float cx, float cy, bool right, bool &uns) {
+    const float ta = atan2f(ay - cy, ax - cx), tb = atan2f(by - cy, bx - cx);
+    float th = right ? ta - tb : tb - ta;
+    if (fabsf(th) < eps_th || fabsf(fabsf(th) - TWO_PI_F) < eps_th) uns = true;
+    if (th < 0.f) th += TWO_PI_F;
+    return th * r;
+  };
+  auto norm = [](float x, float y) { return sqrtf(x * x + y * y); };
+  float d0, d1, D, v0, v1;
+  // rsl
+  d0 = glcx - ircx; d1 = glcy - ircy; D = norm(d0, d1);
+  if (D > 2.f * r - band) {
+    exists[0] = true;
+    if (D < 2.f * r + band) unsure[0] = true;
+    v0 = d0 / D; v1 = d1 / D;
+    const float R = fminf(fmaxf(-2.f * r / D, -1.f), 1.f), sq = sqrtf(fmaxf(1.f - R * R, 0.f));
+    const float a = r * (R * v0 + v1 * sq), b = r * (R * v1 - v0 * sq);
+    const float x0 = ircx - a, y0 = ircy - b, x1 = glcx + a, y1 = glcy + b;
+    len[0] = turn(0.f, 0.f, x0, y0, ircx, ircy, true, unsure[0]) + norm(x1 - x0, y1 - y0) +
+             turn(x1, y1, gx, gy, glcx, glcy, false, unsure[0]);
+  }
+  // rsr, rlr
+  d0 = grcx - ircx; d1 = grcy - ircy; D = norm(d0, d1);
+  v0 = d0 / D; v1 = d1 / D;
+  if (D < band) unsure[1] = true;
+  {
+    const float x0 = -r * v1 + ircx, y0 = r * v0 + ircy, x1 = -r * v1 + grcx, y1 = r * v0 + grcy;
+    len[1] = turn(0.f, 0.f, x0, y0, ircx, ircy, true, unsure[1]) + norm(x1 - x0, y1 - y0) +
+             turn(x1, y1, gx, gy, grcx, grcy, true, unsure[1]);
+  }
+  if (D < 4.f * r + band) {
+    exists[2] = true;
+    if (D > 4.f * r - band || D < band) unsure[2] = true;
+    const float theta = -acosf(fminf(D / (4.f * r), 1.f)) + atan2f(v1, v0);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    const float cx = ircx + 2.f * r * cs, cy = ircy + 2.f * r * sn;
+    const float rlx = (cx + ircx) * 0.5f, rly = (cy + ircy) * 0.5f, lrx = (cx + grcx) * 0.5f, lry = (cy + grcy) * 0.5f;
+    len[2] = turn(0.f, 0.f, rlx, rly, ircx, ircy, true, unsure[2]) +
+             turn(rlx, rly, lrx, lry, cx, cy, false, unsure[2]) +
+             turn(lrx, lry, gx, gy, grcx, grcy, true, unsure[2]);
+  }
+  // lsr
+  d0 = grcx - ilcx; d1 = grcy - ilcy; D = norm(d0, d1);
+  if (D > 2.f * r - band) {
+    exists[3] = true;
+    if (D < 2.f * r + band) unsure[3] = true;
+    v0 = d0 / D; v1 = d1 / D;
+    const float R = fminf(fmaxf(2.f * r / D, -1.f), 1.f), sq = sqrtf(fmaxf(1.f - R * R, 0.f));
+    const float a = R * v0 + v1 * sq, b = R * v1 - v0 * sq;
+    const float x0 = ilcx + a * r, y0 = ilcy + b * r, x1 = grcx - a * r, y1 = grcy - b * r;
+    len[3] = turn(0.f, 0.f, x0, y0, ilcx, ilcy, false, unsure[3]) + norm(x1 - x0, y1 - y0) +
+             turn(x1, y1, gx, gy, grcx, grcy, true, unsure[3]);
+  }
+  // lsl, lrl
+  d0 = glcx - ilcx; d1 = glcy - ilcy; D = norm(d0, d1);
+  v0 = d0 / D; v1 = d1 / D;
+  if (D < band) unsure[4] = true;
+  {
+    const float x0 = r * v1 + ilcx, y0 = -r * v0 + ilcy, x1 = r * v1 + glcx, y1 = -r * v0 + glcy;
+    len[4] = turn(0.f, 0.f, x0, y0, ilcx, ilcy, false, unsure[4]) + norm(x1 - x0, y1 - y0) +
+             turn(x1, y1, gx, gy, glcx, glcy, false, unsure[4]);
+  }
+  if (D < 4.f * r + band) {
+    exists[5] = true;
+    if (D > 4.f * r - band || D < band) unsure[5] = true;
+    const float theta = -acosf(fminf(D / (4.f * r), 1.f)) + atan2f(v1, v0);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    const float cx = ilcx + 2.f * r * cs, cy = ilcy + 2.f * r * sn;
+    const float lrx = (cx + ilcx) * 0.5f, lry = (cy + ilcy) * 0.5f, rlx = (cx + glcx) * 0.5f, rly = (cy + glcy) * 0.5f;
+    len[5] = turn(0.f, 0.f, lrx, lry, ilcx, ilcy, true, unsure[5]) +   // R, L, R as the reference writes them
+             turn(lrx, lry, rlx, rly, cx, cy, false, unsure[5]) +
+             turn(rlx, rly, gx, gy, glcx, glcy, true, unsure[5]);
+  }
+  float best = 3.0e38f;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    if (exists[k] && !(len[k] == len[k] && fabsf(len[k]) < 1.0e30f)) unsure[k] = true;  // not finite
+    if (exists[k] && !unsure[k]) best = fminf(best, len[k]);
+  }
+  int mask = 0;
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+    if (exists[k] && (unsure[k] || len[k] <= best + margin)) mask |= 1 << k;
+  return mask ? mask : CAND_ALL;
 }
 
 // Walks the polyline of a solved path point by point, in the order

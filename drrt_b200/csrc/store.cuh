@@ -121,6 +121,10 @@ struct Store {
   int64_t last_extend_total = -1;
   // solved Dubins paths handed from the solve kernel to the walk kernel
   DevBuf<unsigned char> edge_paths;
+  // ranked solve: candidate list per edge, edges permuted by list, bin counters
+  DevBuf<uint8_t> edge_masks;
+  DevBuf<uint32_t> edge_perm;
+  DevBuf<unsigned long long> edge_bins;
   unsigned long long *d_edge_counter = nullptr;
 };
 

@@ -371,6 +371,19 @@ class KDTree:
         names = [types.raw[4 * i:4 * i + 3].decode() for i in range(n)]
         return xy, npts, names, length
 
+    def DubinsWords(self, start, end, r_min=1.0):
+        """edge_type_ and dist_ after CalculateTrajectory, without the polyline (all six candidates
+        solved in double: the reference's own sequence)."""
+        s = _f64(start, (-1, 3))
+        e = _f64(end, (-1, 3))
+        n = s.shape[0]
+        types = C.create_string_buffer(4 * n)
+        length = np.zeros(n, dtype=np.float64)
+        check(self._lib.drrt_dubins_trajectory_batch(self._h, n, _ptr(s, c_dp), _ptr(e, c_dp),
+                                                     float(r_min), None, None, types, _ptr(length, c_dp)))
+        names = np.frombuffer(types.raw, dtype="S4").astype("S3")
+        return names, length
+
     # -- ExplicitNodeCheck obstacle.cpp:1087-1090
     def ExplicitNodeCheck(self, points, robot_radius=0.5, collision_distance=0.1):
         p = _f64(points, (-1, 3))

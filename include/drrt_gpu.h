@@ -242,7 +242,8 @@ DRRT_API int drrt_extend_batch_dev(drrt_store *h, int64_t nq, const double *q_de
 
 /* DubinsEdge::CalculateTrajectory polyline (edge->trajectory_, read by
  * src/moverobot.cpp:107,158): up to DRRT_TRAJ_MAX (x,y) points per edge.
- * xy: n x DRRT_TRAJ_MAX x 2 f64; npts: n; type: n x 4 chars ("rsl\0"...) */
+ * xy: n x DRRT_TRAJ_MAX x 2 f64; npts: n; type: n x 4 chars ("rsl\0"...).
+ * xy == NULL (and npts == NULL): only the Dubins word and edge->dist_ are returned. */
 #define DRRT_TRAJ_MAX 200
 DRRT_API int drrt_dubins_trajectory_batch(drrt_store *h, int64_t n, const double *start,
                                  const double *end, double r_min, double *xy,

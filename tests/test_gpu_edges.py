@@ -140,3 +140,42 @@ def test_edge_round_trip_properties_full_size(drrt, po):
     t.SetObstacles(kind=[], used=[], life_span=[], origin=np.zeros((0, 2)), radius=[],
                    vert_off=[0], verts=np.zeros((0, 2)))
     assert not t.ExplicitEdgeCheck(s[:100000], e[:100000], want_length=False).any()
+
+
+def test_ranked_solve_matches_full_solve(drrt, po):
+    # large Dubins batches rank the six candidates in float32 and solve only the ones that can
+    # win in double (edgecheck.cu "K4a, ranked"); the lengths must be bit-identical to the
+    # solve of all six candidates, on ordinary edges and on near-degenerate ones
+    rng = np.random.default_rng(871)
+    t = drrt.KDTree()
+    t.SetObstacles(**synth.obstacles(32, 872))
+    parts = []
+    for max_len in (0.3, 0.66, 2.0, 4.1, 9.0):
+        parts.append(synth.random_edges(120_000, int(rng.integers(1 << 30)), max_len=max_len))
+    s = np.concatenate([p[0] for p in parts])
+    e = np.concatenate([p[1] for p in parts])
+    k = 40_000
+    # existence boundaries and ties: centres 2r / 4r apart, equal headings, mirrored poses
+    s[:k, 2] = rng.uniform(0, synth.TWO_PI, k)
+    e[:k, 2] = s[:k, 2]                                           # parallel headings: rsr == lsl ties
+    d = rng.choice([2.0, 4.0, 1e-7, 1.0], k) + rng.normal(0, 1e-6, k)
+    ang = s[:k, 2] + rng.choice([0.0, np.pi / 2, np.pi, -np.pi / 2], k)
+    e[:k, 0] = s[:k, 0] + d * np.cos(ang)
+    e[:k, 1] = s[:k, 1] + d * np.sin(ang)
+    e[k:2 * k, 2] = s[k:2 * k, 2] + np.pi                          # opposite headings
+    v, ln = t.ExplicitEdgeCheck(s, e)                              # ranked pipeline (n >= 16384)
+    names, full = t.DubinsWords(s, e)                              # all six candidates
+    assert np.array_equal(ln, full)
+    # and the one-kernel solve used for small batches gives the same verdicts and lengths
+    for lo in range(0, 160_000, 16_000):
+        v2, ln2 = t.ExplicitEdgeCheck(s[lo:lo + 16_000], e[lo:lo + 16_000])
+        assert np.array_equal(ln2, full[lo:lo + 16_000]) and np.array_equal(v2, v[lo:lo + 16_000])
+    # verdicts against the oracle on the ordinary edges (the constructed ties above are decided
+    # by the last ulp of atan2, where CUDA and glibc may pick different words of equal length)
+    ro = po.RefObstacles(**synth.obstacles(32, 872))
+    idx = 2 * k + rng.permutation(len(s) - 2 * k)[:60_000]
+    rv, rln, clr = ro.edge_check_batch(s[idx], e[idx], want_clearance=True)
+    diff = np.nonzero(v[idx] != rv)[0]
+    assert (clr[diff] < BAND).all() and len(diff) <= 3
+    ok = rln < 1e11
+    assert np.allclose(ln[idx][ok], rln[ok], rtol=1e-9, atol=1e-9)
