@@ -343,7 +343,27 @@ __device__ void dubins_solve(double sx, double sy, double st, double ex, double 
 // distance, or is not finite.  Float errors here are ~1e-6 * scale in coordinates and lengths;
 // bands and margin are 1e-3-sized, three orders above that.  The listed candidates are then
 // solved in double exactly as the reference does; the others are provably longer than the
-// winner, so the winner and bestDist are the reference's (dubins_solve).
+// winner, so the winner and bestDist are the reference's (dubins_solve).  The float pass uses
+// fast approximations (rank_atan2 1.2e-5 rad, __sincosf, __fdividef): their errors are part of
+// the same budget.
+// atan2 to ~1.2e-5 rad (Hastings' five-term odd polynomial on [0,1] plus octant folding): the
+// ranking only needs angles to well under its 1e-3 bands
+__device__ __forceinline__ float rank_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = __fdividef(mn, mx);  // NaN for 0/0: the candidate then counts as "cannot tell"
+  const float s = a * a;
+  float r = a * (0.9998660f + s * (-0.3302995f + s * (0.1801410f + s * (-0.0851330f + s * 0.0208351f))));
+  if (ay > ax) r = 1.57079632679f - r;
+  if (x < 0.f) r = 3.14159265359f - r;
+  return (y < 0.f) ? -r : r;
+}
+
+__device__ __forceinline__ void rank_sincos(float x, float *sn, float *cs) {
+  x -= 6.28318530718f * rintf(x * 0.15915494309f);  // into [-pi, pi], where __sincosf is accurate to ~1e-6
+  __sincosf(x, sn, cs);
+}
+
 __device__ __forceinline__ int dubins_rank(double sx, double sy, double st, double ex, double ey,
                                            double et, double r_min) {
   const float TWO_PI_F = 6.28318530718f;
@@ -356,8 +376,8 @@ __device__ __forceinline__ int dubins_rank(double sx, double sy, double st, doub
   const float margin = 2e-3f * (r + scale);  // length comparison
   const float eps_th = 1e-3f;                // turn angles near the 0 / 2pi jump
   float ss, cs0, se, ce;
-  sincosf((float)st, &ss, &cs0);
-  sincosf((float)et, &se, &ce);
+  rank_sincos((float)st, &ss, &cs0);
+  rank_sincos((float)et, &se, &ce);
   // turn-circle centres relative to the start point (dubinsedge.cpp:183-202)
   const float ircx = r * ss, ircy = -r * cs0, ilcx = -r * ss, ilcy = r * cs0;
   const float grcx = gx + r * se, grcy = gy - r * ce, glcx = gx - r * se, glcy = gy + r * ce;
@@ -365,7 +385,7 @@ __device__ __forceinline__ int dubins_rank(double sx, double sy, double st, doub
   bool exists[6] = {false, true, false, false, true, false};
   float len[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   auto turn = [&](float ax, float ay, float bx, float by, float cx, float cy, bool right, bool &uns) {
-    const float ta = atan2f(ay - cy, ax - cx), tb = atan2f(by - cy, bx - cx);
+    const float ta = rank_atan2(ay - cy, ax - cx), tb = rank_atan2(by - cy, bx - cx);
     float th = right ? ta - tb : tb - ta;
     if (fabsf(th) < eps_th || fabsf(fabsf(th) - TWO_PI_F) < eps_th) uns = true;
     if (th < 0.f) th += TWO_PI_F;
@@ -397,9 +417,9 @@ __device__ __forceinline__ int dubins_rank(double sx, double sy, double st, doub
   if (D < 4.f * r + band) {
     exists[2] = true;
     if (D > 4.f * r - band || D < band) unsure[2] = true;
-    const float theta = -acosf(fminf(D / (4.f * r), 1.f)) + atan2f(v1, v0);
+    const float theta = -acosf(fminf(D / (4.f * r), 1.f)) + rank_atan2(v1, v0);
     float sn, cs;
-    sincosf(theta, &sn, &cs);
+    rank_sincos(theta, &sn, &cs);
     const float cx = ircx + 2.f * r * cs, cy = ircy + 2.f * r * sn;
     const float rlx = (cx + ircx) * 0.5f, rly = (cy + ircy) * 0.5f, lrx = (cx + grcx) * 0.5f, lry = (cy + grcy) * 0.5f;
     len[2] = turn(0.f, 0.f, rlx, rly, ircx, ircy, true, unsure[2]) +
@@ -430,9 +450,9 @@ __device__ __forceinline__ int dubins_rank(double sx, double sy, double st, doub
   if (D < 4.f * r + band) {
     exists[5] = true;
     if (D > 4.f * r - band || D < band) unsure[5] = true;
-    const float theta = -acosf(fminf(D / (4.f * r), 1.f)) + atan2f(v1, v0);
+    const float theta = -acosf(fminf(D / (4.f * r), 1.f)) + rank_atan2(v1, v0);
     float sn, cs;
-    sincosf(theta, &sn, &cs);
+    rank_sincos(theta, &sn, &cs);
     const float cx = ilcx + 2.f * r * cs, cy = ilcy + 2.f * r * sn;
     const float lrx = (cx + ilcx) * 0.5f, lry = (cy + ilcy) * 0.5f, rlx = (cx + glcx) * 0.5f, rly = (cy + glcy) * 0.5f;
     len[5] = turn(0.f, 0.f, lrx, lry, ilcx, ilcy, true, unsure[5]) +   // R, L, R as the reference writes them
