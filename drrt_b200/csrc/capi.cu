@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" boundary declared in include/drrt_gpu.h.
 // Host entry points stage caller buffers through device scratch owned by the
 // handle, on the handle's stream, and return after the results are on the host.
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -221,7 +222,7 @@ int drrt_store_destroy(drrt_store *h) {
     S->o_kind.release(); S->o_voff.release(); S->oa_kind.release(); S->oa_voff.release();
     S->oa_live.release(); S->o_ox.release(); S->o_oy.release(); S->o_rad.release();
     S->o_vx.release(); S->o_vy.release(); S->oa_ox.release(); S->oa_oy.release();
-    S->oa_rad.release(); S->oa_vx.release(); S->oa_vy.release(); S->o_mask.release();
+    S->oa_rad.release(); S->oa_vx.release(); S->oa_vy.release(); S->o_mask.release(); S->o_covers.release();
     if (S->d_pending) cudaFree(S->d_pending);
     if (S->d_ticket) cudaFree(S->d_ticket);
     if (S->d_edge_counter) cudaFree(S->d_edge_counter);
@@ -406,6 +407,7 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
   std::vector<double> ox(n_obs), oy(n_obs), rad(radius, radius + n_obs), vx(nv_all), vy(nv_all);
   std::vector<double> aox, aoy, arad, avx, avy;
   std::vector<int32_t> src_act;
+  std::vector<uint8_t> covers_act;
   for (int i = 0; i <= n_obs; i++) vo_all[i] = n_obs ? vert_off[i] : 0;
   for (int v = 0; v < nv_all; v++) { vx[v] = verts_xy[2 * v]; vy[v] = verts_xy[2 * v + 1]; }
   for (int i = 0; i < n_obs; i++) {
@@ -419,6 +421,10 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
       aox.push_back(ox[i]); aoy.push_back(oy[i]); arad.push_back(rad[i]);
       for (int v = vert_off[i]; v < vert_off[i + 1]; v++) { avx.push_back(vx[v]); avy.push_back(vy[v]); }
       vo_act.push_back((int32_t)avx.size());
+      double far = 0.0;  // obstacle.h:134-141 sets radius_ to this; a caller may not
+      for (int v = vert_off[i]; v < vert_off[i + 1]; v++)
+        far = std::max(far, sqrt((vx[v] - ox[i]) * (vx[v] - ox[i]) + (vy[v] - oy[i]) * (vy[v] - oy[i])));
+      covers_act.push_back(rad[i] * (1.0 + 1e-12) >= far ? 1 : 0);
     }
   }
   cudaStream_t st = S->stream;
@@ -427,6 +433,7 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
   DRRT_CHECK(put(S->o_ox, aox, st)); DRRT_CHECK(put(S->o_oy, aoy, st));
   DRRT_CHECK(put(S->o_rad, arad, st)); DRRT_CHECK(put(S->o_vx, avx, st));
   DRRT_CHECK(put(S->o_vy, avy, st));
+  DRRT_CHECK(put(S->o_covers, covers_act, st));
   DRRT_CHECK(put(S->oa_kind, k_all, st)); DRRT_CHECK(put(S->oa_voff, vo_all, st));
   DRRT_CHECK(put(S->oa_live, live, st));
   DRRT_CHECK(put(S->oa_ox, ox, st)); DRRT_CHECK(put(S->oa_oy, oy, st));

@@ -46,6 +46,7 @@ static constexpr long long PATH_PREFETCH_AHEAD = DRRT_PF_AHEAD;  // edges claime
 struct ObsView {
   int n;
   const uint8_t *mask;  // null, or per obstacle: 0 = leave it out (subset checks of the sweeps)
+  const uint8_t *covers;  // per obstacle: radius_ is at least the largest vertex distance from origin_
   const int32_t *kind;
   const double *ox, *oy, *rad;
   const int32_t *voff;
@@ -510,46 +511,106 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
   }
 }
 
-// K5: LineCheck (obstacle.cpp:1098-1133), one thread per edge
+// K5: LineCheck (obstacle.cpp:1098-1133), one thread per edge.
+//
+// The reference cuts the straight edge into 50 collinear pieces (repeated +-dist/50, :1108-1133)
+// and tests each piece against every obstacle.  The pieces tile the edge (to within ~1e-13 of
+// accumulated rounding), so  min_i SegmentDistSqrd(piece_i, Q) = SegmentDistSqrd(edge, Q)  up to
+// that rounding, and the OR over the pieces is decided by ONE exact test of the whole edge per
+// nearby polygon edge / ball -- unless the distance lies within eps (1e-9 relative) of the
+// threshold, or the obstacle's bounding circle (obstacle.cpp:765-779) is not known to contain
+// its polygon: those edges take the reference's 50-piece loop verbatim.  A polygon edge within
+// radius - eps of the edge is within radius of one piece, and that piece is then within
+// radius + O.radius_ of the origin when O.radius_ covers the vertices (`covers`), so the piece
+// passes the bounding reject as well.
+template <bool MASKED>
+__device__ __forceinline__ int line_screen(const ObsView &O, const ObstacleGrid &G, double sx, double sy,
+                                           double ex, double ey, double radius) {
+  if (G.nx == 0) return 2;
+  const double eps = 1e-9 * (1.0 + fmax(fmax(fabs(sx), fabs(sy)), fmax(fabs(ex), fabs(ey))));
+  if (!(eps < 0.25 * radius)) return 2;
+  const double r_far = (radius + eps) * (radius + eps), r_near = (radius - eps) * (radius - eps);
+  const double len = sqrt((ex - sx) * (ex - sx) + (ey - sy) * (ey - sy));
+  if (!(len == len) || !(len < 1.0e30)) return 2;
+  // walk the edge in stretches of about four cells, looking at the cells each stretch's box touches
+  const double cell = 1.0 / G.inv_cell;
+  const int pieces = (int)fmin(fmax(ceil(len / (4.0 * cell)), 1.0), 4096.0);
+  int state = 0;
+  int pcx0 = 1, pcx1 = 0, pcy0 = 1, pcy1 = 0;  // cell box of the previous stretch (empty)
+  for (int k = 0; k < pieces; k++) {
+    const double t0 = (double)k / pieces, t1 = (double)(k + 1) / pieces;
+    const double ax = sx + (ex - sx) * t0, ay = sy + (ey - sy) * t0;
+    const double bx = sx + (ex - sx) * t1, by = sy + (ey - sy) * t1;
+    const double lox = fmin(ax, bx) - eps, hix = fmax(ax, bx) + eps;
+    const double loy = fmin(ay, by) - eps, hiy = fmax(ay, by) + eps;
+    const double fx0 = floor((lox - G.x0) * G.inv_cell), fx1 = floor((hix - G.x0) * G.inv_cell);
+    const double fy0 = floor((loy - G.y0) * G.inv_cell), fy1 = floor((hiy - G.y0) * G.inv_cell);
+    if (fx1 < 0.0 || fy1 < 0.0 || fx0 > (double)(G.nx - 1) || fy0 > (double)(G.ny - 1)) continue;
+    const int cx0 = (int)fmax(fx0, 0.0), cx1 = (int)fmin(fx1, (double)(G.nx - 1));
+    const int cy0 = (int)fmax(fy0, 0.0), cy1 = (int)fmin(fy1, (double)(G.ny - 1));
+    for (int cx = cx0; cx <= cx1; cx++)
+      for (int cy = cy0; cy <= cy1; cy++) {
+        if (cx >= pcx0 && cx <= pcx1 && cy >= pcy0 && cy <= pcy1) continue;  // seen with the last stretch
+        const int c = cx * G.ny + cy;
+        for (int q = G.off[c]; q < G.off[c + 1]; q++) {
+          const int j = G.idx[q];
+          if (j >= G.n_edges) {  // ball: obstacle.cpp:765-781
+            const int b = G.ball[j - G.n_edges];
+            if (MASKED && !O.mask[b]) continue;
+            const double d2 = dist_sqrd_point_segment(O.ox[b], O.oy[b], sx, sy, ex, ey);
+            const double hi = radius + O.rad[b] + eps, lo = radius + O.rad[b] - eps;
+            if (d2 > hi * hi) continue;
+            if (d2 < lo * lo && lo > 0.0) return 1;
+            state = 2;
+            continue;
+          }
+          const int o = G.eobs[j];
+          if (MASKED && !O.mask[o]) continue;
+          const double sd = segment_dist_sqrd(sx, sy, ex, ey, G.eax[j], G.eay[j], G.ebx[j], G.eby[j]);
+          if (sd > r_far) continue;
+          if (sd < r_near && O.covers[o]) return 1;
+          state = 2;
+        }
+      }
+    pcx0 = cx0; pcx1 = cx1; pcy0 = cy0; pcy1 = cy1;
+  }
+  return state;
+}
+
 template <bool MASKED>
 __global__ void __launch_bounds__(EDGE_T)
 linecheck_kernel(EdgeArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ObsView O = A.obs;
   if (A.obs_smem && O.n > 0) stage_obstacles(O, smem_raw);
-  __shared__ WarpScratch s_ws[EDGE_T / 32];
-  WarpScratch *ws = &s_ws[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
-  const bool live = e < A.n;
-  double sx = 0, sy = 0, st = 0, ex = 0, ey = 0, et = 0;
-  if (live) {
-    load_pose(A, e, false, sx, sy, st);
-    load_pose(A, e, true, ex, ey, et);
-  }
+  if (e >= A.n) return;
+  double sx, sy, st, ex, ey, et;
+  load_pose(A, e, false, sx, sy, st);
+  load_pose(A, e, true, ex, ey, et);
+  const double th = atan2(ey - sy, ex - sx);
+  const double dist = metric_dist(A.metric, sx, sy, th, ex, ey, th);
   bool hit = false;
-  double th = atan2(ey - sy, ex - sx);
-  double dist = metric_dist(A.metric, sx, sy, th, ex, ey, th);
   if (O.n > 0) {
-    const double traj_length = 50;
-    double x_val = sx, y_val = sy;
-    const double x_dist = fabs(ex - x_val), y_dist = fabs(ey - y_val);
-    double px = x_val, py = y_val;
-    for (int i = 0; i < 50; i++) {
-      if (ex > sx) x_val += x_dist / traj_length; else x_val -= x_dist / traj_length;
-      if (ey > sy) y_val += y_dist / traj_length; else y_val -= y_dist / traj_length;
-      bool h = warp_segments_vs_obstacles<MASKED>(O, A.grid, live && !hit, px, py, x_val, y_val,
-                                          A.robot_radius, ws, lane);
-      hit = hit || h;
-      if (__all_sync(0xffffffffu, hit || !live)) break;
-      px = x_val;
-      py = y_val;
+    const int state = line_screen<MASKED>(O, A.grid, sx, sy, ex, ey, A.robot_radius);
+    hit = state == 1;
+    if (state == 2) {
+      // too close to call from the whole edge: the reference's 50 pieces
+      const double traj_length = 50;
+      double x_val = sx, y_val = sy;
+      const double x_dist = fabs(ex - x_val), y_dist = fabs(ey - y_val);
+      double px = x_val, py = y_val;
+      for (int i = 0; i < 50 && !hit; i++) {
+        if (ex > sx) x_val += x_dist / traj_length; else x_val -= x_dist / traj_length;
+        if (ey > sy) y_val += y_dist / traj_length; else y_val -= y_dist / traj_length;
+        hit = segment_vs_obstacles<MASKED>(O, A.grid, px, py, x_val, y_val, A.robot_radius);
+        px = x_val;
+        py = y_val;
+      }
     }
   }
-  if (live) {
-    A.verdict[e] = hit ? 1 : 0;
-    if (A.length) A.length[e] = dist;
-  }
+  A.verdict[e] = hit ? 1 : 0;
+  if (A.length) A.length[e] = dist;
 }
 
 // distance from an axis-aligned rectangle to a segment (0 when they touch)
@@ -720,6 +781,7 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   A.robot_radius = robot_radius; A.r_min = r_min;
   A.obs.n = S->has_obstacles ? S->obs.n_active : 0;
   A.obs.mask = S->edge_mask;
+  A.obs.covers = S->o_covers.p;
   A.obs.kind = S->obs.kind; A.obs.ox = S->obs.ox; A.obs.oy = S->obs.oy; A.obs.rad = S->obs.rad;
   A.obs.voff = S->obs.vert_off; A.obs.vx = S->obs.vx; A.obs.vy = S->obs.vy;
   A.verdict = verdict_dev; A.length = length_dev;

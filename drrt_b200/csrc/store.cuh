@@ -103,6 +103,7 @@ struct Store {
   std::vector<double> h_all_ox, h_all_oy, h_all_rad;
   std::vector<int32_t> h_all_kind;
   DevBuf<uint8_t> o_mask;                // per ACTIVE obstacle: taking part in a subset check
+  DevBuf<uint8_t> o_covers;              // per ACTIVE obstacle: radius_ covers every polygon vertex
   const uint8_t *edge_mask = nullptr;    // set for the duration of a subset check
   ObstacleGrid ogrid{};
   double ogrid_radius = -1.0;
