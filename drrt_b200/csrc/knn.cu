@@ -23,6 +23,7 @@ static constexpr int KNN_KMAX = 128;
 
 struct KnnArgs {
   GridView V;
+  const int32_t *qlist;  // null, or [count, q0, q1, ...]: only these queries (knn_select_kernel's leftovers)
   const double *q;
   int64_t nq;
   int k;
@@ -79,8 +80,10 @@ knn_kernel(KnnArgs A) {
   __shared__ int s_runs[KNN_WARPS][RUNS_PER_BATCH];
   __shared__ int s_pref[KNN_WARPS][RUNS_PER_BATCH + 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t qi = (int64_t)blockIdx.x * KNN_WARPS + w;
-  if (qi >= A.nq) return;
+  // plain mode: one query per warp; list mode: the warps share the listed queries
+  const int64_t count = A.qlist ? (int64_t)A.qlist[0] : A.nq;
+  for (int64_t slot = (int64_t)blockIdx.x * KNN_WARPS + w; slot < count; slot += (int64_t)gridDim.x * KNN_WARPS) {
+  const int64_t qi = A.qlist ? (int64_t)A.qlist[slot + 1] : slot;
   const GridView &V = A.V;
   TopK T;
   T.k = A.k;
@@ -150,6 +153,107 @@ knn_kernel(KnnArgs A) {
     A.ids[qi * A.k + i] = have ? T.id[i] : -1;
     A.dist[qi * A.k + i] = have ? T.d[i] : DRRT_INF;
   }
+  __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// k <= KSEL_KMAX: collect, then select.  The warp gathers every node within the current radius
+// (ballot-compacted into its staging area, like a range query), and once at least k are inside
+// -- all nodes within r are then known, so the k nearest are among them -- orders them with a
+// small bitonic network on (dist, id) and writes the first k.  No per-candidate insertion.
+static constexpr int KSEL_KMAX = 64;
+static constexpr int KSEL_CAP = 256;  // staged candidates per query; more than that: knn_kernel
+
+// all-ascending bitonic network over n (any n) (d, id) pairs, one warp
+__device__ void warp_sort_pairs(double *d, int32_t *id, int n, int lane) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  int lk = 1;
+  auto cex = [&](int i, int j) {
+    if (j < n) {
+      const double di = d[i], dj = d[j];
+      const int32_t ii = id[i], ij = id[j];
+      if (pair_less(dj, ij, di, ii)) { d[i] = dj; id[i] = ij; d[j] = di; id[j] = ii; }
+    }
+  };
+  for (int k = 2; k <= np2; k <<= 1, lk++) {
+    const int half = k >> 1;
+    for (int p = lane; p < (np2 >> 1); p += 32) {
+      const int blk = p >> (lk - 1), o = p & (half - 1);
+      cex(blk * k + o, blk * k + k - 1 - o);
+    }
+    __syncwarp();
+    for (int jj = half >> 1; jj > 0; jj >>= 1) {
+      for (int p = lane; p < (np2 >> 1); p += 32) {
+        const int i = ((p & ~(jj - 1)) << 1) | (p & (jj - 1));
+        cex(i, i + jj);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_select_kernel(KnnArgs A, int32_t *fallback) {
+  __shared__ int s_runs[KNN_WARPS][RUNS_PER_BATCH];
+  __shared__ int s_pref[KNN_WARPS][RUNS_PER_BATCH + 1];
+  __shared__ double s_d[KNN_WARPS][KSEL_CAP];
+  __shared__ int32_t s_id[KNN_WARPS][KSEL_CAP];
+  __shared__ int s_count[KNN_WARPS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t qi = (int64_t)blockIdx.x * KNN_WARPS + w;
+  if (qi >= A.nq) return;
+  const GridView &V = A.V;
+  const double qx = A.q[3 * qi], qy = A.q[3 * qi + 1], qt = A.q[3 * qi + 2];
+  const unsigned ltmask = (1u << lane) - 1u;
+  double *sd = s_d[w];
+  int32_t *sid = s_id[w];
+  double r = A.r0;
+  bool all = false;
+  auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
+    const double d = sqrt(metric_sum<METRIC>(qx, qy, qt, nx, ny, nt));
+    const bool in = valid && (all || d <= r);
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (!m) return;
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(&s_count[w], __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (in) {
+      const int slot = pos + __popc(m & ltmask);
+      if (slot < KSEL_CAP) { sd[slot] = d; sid[slot] = id; }
+    }
+  };
+  int n = 0;
+  for (;;) {
+    if (lane == 0) s_count[w] = 0;
+    __syncwarp();
+    all = true;
+    if (V.n_indexed > 0) {
+      Query Q;
+      setup_query<METRIC>(V, qx, qy, qt, r, Q);
+      Q.has_ghost = false;
+      all = covers_all(V, Q);
+      scan_columns(V, Q, 0, 1, s_runs[w], s_pref[w], lane, visit);
+    }
+    scan_tail(V, 0, 1, lane, visit);
+    __syncwarp();
+    n = s_count[w];
+    // every node within r is staged: k of them settle the answer (unscanned nodes are farther)
+    if (n >= A.k || all || n > KSEL_CAP) break;
+    r *= 2.0;
+  }
+  if (n > KSEL_CAP) {  // a crowded neighbourhood: leave the query to the insertion kernel
+    if (lane == 0) fallback[atomicAdd(&fallback[0], 1) + 1] = (int32_t)qi;
+    return;
+  }
+  warp_sort_pairs(sd, sid, n, lane);
+  for (int i = lane; i < A.k; i += 32) {
+    const bool have = i < n;
+    A.ids[qi * A.k + i] = have ? sid[i] : -1;
+    A.dist[qi * A.k + i] = have ? sd[i] : DRRT_INF;
+  }
 }
 
 int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
@@ -172,6 +276,20 @@ int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids
   }
   size_t smem = (size_t)KNN_WARPS * k * (sizeof(double) + sizeof(int32_t));
   unsigned nb = (unsigned)((nq + KNN_WARPS - 1) / KNN_WARPS);
+  if (k <= KSEL_KMAX && !A.nearest && nq < 0x7ffffff0) {
+    // collect-then-select; queries whose ball holds more than KSEL_CAP nodes are listed and
+    // answered by the insertion kernel afterwards (none on an evenly filled store)
+    DRRT_CHECK(S->i_stage2.reserve((size_t)nq + 2, st));
+    int32_t *fb = S->i_stage2.p;
+    DRRT_CUDA(cudaMemsetAsync(fb, 0, sizeof(int32_t), st));
+    if (S->metric == DRRT_METRIC_EUCLID)
+      knn_select_kernel<DRRT_METRIC_EUCLID><<<nb, KNN_WARPS * 32, 0, st>>>(A, fb);
+    else
+      knn_select_kernel<DRRT_METRIC_R2S1_WRAP><<<nb, KNN_WARPS * 32, 0, st>>>(A, fb);
+    DRRT_LAUNCHED();
+    A.qlist = fb;  // the list length is only known on the device: a small grid strides over it
+    nb = std::min(nb, 592u);
+  }
   if (S->metric == DRRT_METRIC_EUCLID)
     knn_kernel<DRRT_METRIC_EUCLID><<<nb, KNN_WARPS * 32, smem, st>>>(A);
   else

@@ -71,3 +71,19 @@ def test_knn_full_scale_sample(drrt, po):
     assert np.array_equal(nid[:64], ids[:, 0])
     off, rid, rd = t.KDFindWithinRange(nd * (1 + 1e-12) + 1e-12, synth.queries()[:2000])
     assert (np.diff(off) >= 1).all()
+
+
+def test_knn_crowded_neighbourhoods_use_the_insertion_kernel(drrt, po):
+    # the collect-then-select kernel stages at most 256 nodes per query; queries inside a dense
+    # blob exceed that at the first radius and are answered by the insertion kernel instead
+    pos = synth.box_points(40_000, 78)
+    rng = np.random.default_rng(79)
+    pos[10_000:16_000] = [25.0, 25.0, 3.0] + rng.normal(0, 0.15, (6000, 3))
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(400, 80)
+    q[:200] = [25.0, 25.0, 3.0] + rng.normal(0, 0.1, (200, 3))
+    for k in (1, 16, 64):
+        ids, dist = t.KDFindKNearest(k, q)
+        rids, rdist = r.knn_batch(q, k)
+        assert np.array_equal(ids, rids), k
+        assert np.array_equal(dist, rdist), k
