@@ -388,8 +388,8 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak,
                              # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel
-                             # on this workload (ncu --set full, profiles/r01v3_range_cta_kernel.txt)
-                             "traffic": 3.451e9, "traffic_unit": "bytes/launch",
+                             # on this workload (ncu --set full, profiles/r01v5_range_cta_kernel.txt)
+                             "traffic": 3.627e9, "traffic_unit": "bytes/launch",
                              "peak_kind": peak_kind,
                              "kernel": "range_cta_kernel<R2S1> (CTA per query)",
                              "algorithmic_bytes_per_launch": alg_bytes},
