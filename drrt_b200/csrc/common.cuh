@@ -77,6 +77,8 @@ struct ObstacleTable {
   const double *a_vx, *a_vy;
 };
 
+struct __align__(32) EdgeRec { double ax, ay, bx, by; };
+
 // Broadphase of the edge checks: a uniform grid whose cells list the polygon
 // EDGES (and kind-1 balls) that come within the robot radius of the cell.
 struct ObstacleGrid {
@@ -85,7 +87,7 @@ struct ObstacleGrid {
   const int32_t *off;     // nx*ny + 1
   const int32_t *idx;     // entry < n_edges: polygon edge; else ball (entry - n_edges)
   int32_t n_edges;
-  const double *eax, *eay, *ebx, *eby;  // polygon edge end points (A = previous vertex)
+  const struct EdgeRec *erec;  // polygon edge end points (A = previous vertex), one 256-bit load each
   const int32_t *eobs;    // owning active obstacle of each edge
   const int32_t *ball;    // active-obstacle index of each kind-1 ball
 };

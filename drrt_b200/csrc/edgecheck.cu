@@ -43,6 +43,13 @@ static constexpr int64_t RANKED_SOLVE_MIN = 16384;  // smaller Dubins batches ta
 #endif
 static constexpr long long PATH_PREFETCH_AHEAD = DRRT_PF_AHEAD;  // edges claimed ahead of the walk
 
+__device__ __forceinline__ void load_edge(const ObstacleGrid &G, int j, double &ax, double &ay, double &bx, double &by) {
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(G.erec + j));
+  ax = __longlong_as_double((long long)a); ay = __longlong_as_double((long long)b);
+  bx = __longlong_as_double((long long)c); by = __longlong_as_double((long long)d);
+}
+
 struct ObsView {
   int n;
   const uint8_t *mask;  // null, or per obstacle: 0 = leave it out (subset checks of the sweeps)
@@ -119,7 +126,8 @@ __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const Obs
             continue;
           }
           if (MASKED && !O.mask[G.eobs[j]]) continue;
-          double ax = G.eax[j], ay = G.eay[j], bx = G.ebx[j], by = G.eby[j];
+          double ax, ay, bx, by;
+          load_edge(G, j, ax, ay, bx, by);
           // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
           if (dist_sqrd_point_segment(p0x, p0y, ax, ay, bx, by) > far2) continue;
           if (segment_dist_sqrd(p0x, p0y, p1x, p1y, ax, ay, bx, by) < rr &&   // :796-803
@@ -153,7 +161,8 @@ __device__ __forceinline__ bool entry_hits(const ObsView &O, const ObstacleGrid 
     return within_reach(O, b, sg[0], sg[1], sg[2], sg[3], radius);
   }
   if (MASKED && !O.mask[G.eobs[j]]) return false;
-  double ax = G.eax[j], ay = G.eay[j], bx = G.ebx[j], by = G.eby[j];
+  double ax, ay, bx, by;
+  load_edge(G, j, ax, ay, bx, by);
   // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
   if (dist_sqrd_point_segment(sg[0], sg[1], ax, ay, bx, by) > sg[4]) return false;
   return segment_dist_sqrd(sg[0], sg[1], sg[2], sg[3], ax, ay, bx, by) < radius * radius &&  // :796-803
@@ -566,7 +575,9 @@ __device__ __forceinline__ int line_screen(const ObsView &O, const ObstacleGrid 
           }
           const int o = G.eobs[j];
           if (MASKED && !O.mask[o]) continue;
-          const double sd = segment_dist_sqrd(sx, sy, ex, ey, G.eax[j], G.eay[j], G.ebx[j], G.eby[j]);
+          double qax, qay, qbx, qby;
+          load_edge(G, j, qax, qay, qbx, qby);
+          const double sd = segment_dist_sqrd(sx, sy, ex, ey, qax, qay, qbx, qby);
           if (sd > r_far) continue;
           if (sd < r_near && O.covers[o]) return 1;
           state = 2;
@@ -741,13 +752,13 @@ static int ensure_obstacle_grid(Store *S, double robot_radius, cudaStream_t st) 
     return DRRT_OK;
   };
   DRRT_CHECK(up(S->og_off, off)); DRRT_CHECK(up(S->og_idx, idx));
-  DRRT_CHECK(up(S->og_eax, eax)); DRRT_CHECK(up(S->og_eay, eay));
-  DRRT_CHECK(up(S->og_ebx, ebx)); DRRT_CHECK(up(S->og_eby, eby));
   DRRT_CHECK(up(S->og_eobs, eobs)); DRRT_CHECK(up(S->og_ball, ball));
+  std::vector<EdgeRec> erec(ne);
+  for (size_t j = 0; j < ne; j++) erec[j] = EdgeRec{eax[j], eay[j], ebx[j], eby[j]};
+  DRRT_CHECK(up(S->og_erec, erec));
   DRRT_CUDA(cudaStreamSynchronize(st));
   G.off = S->og_off.p; G.idx = S->og_idx.p;
-  G.eax = S->og_eax.p; G.eay = S->og_eay.p; G.ebx = S->og_ebx.p; G.eby = S->og_eby.p;
-  G.eobs = S->og_eobs.p; G.ball = S->og_ball.p;
+  G.eobs = S->og_eobs.p; G.ball = S->og_ball.p; G.erec = S->og_erec.p;
   S->ogrid = G;
   S->ogrid_radius = robot_radius;
   return DRRT_OK;

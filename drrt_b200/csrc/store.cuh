@@ -108,7 +108,7 @@ struct Store {
   ObstacleGrid ogrid{};
   double ogrid_radius = -1.0;
   DevBuf<int32_t> og_off, og_idx, og_eobs, og_ball;
-  DevBuf<double> og_eax, og_eay, og_ebx, og_eby;
+  DevBuf<EdgeRec> og_erec;
   // fused Extend: per-neighbour verdicts / lengths (2 per pair), query poses of the CSR rows
   DevBuf<uint8_t> x_unsafe;
   DevBuf<double> x_len, x_lmc;
