@@ -38,10 +38,7 @@ namespace drrt {
 
 static constexpr int EDGE_T = 128;
 static constexpr int64_t RANKED_SOLVE_MIN = 16384;  // smaller Dubins batches take the one-kernel solve
-#ifndef DRRT_PF_AHEAD
-#define DRRT_PF_AHEAD 8192
-#endif
-static constexpr long long PATH_PREFETCH_AHEAD = DRRT_PF_AHEAD;  // edges claimed ahead of the walk
+static constexpr int WALK_CLAIM = 64;  // edges a warp claims at a time
 
 __device__ __forceinline__ void load_edge(const ObstacleGrid &G, int j, double &ax, double &ay, double &bx, double &by) {
   unsigned long long a, b, c, d;
@@ -270,7 +267,6 @@ struct EdgeArgs {
   double robot_radius, r_min;
   ObsView obs;
   ObstacleGrid grid;
-  int obs_smem;                     // stage the obstacle table in shared memory
   uint8_t *verdict;
   double *length;
 };
@@ -301,24 +297,6 @@ __device__ __forceinline__ void load_pose(const EdgeArgs &A, int64_t e, bool end
     const double *p = (end ? A.end : A.start) + 3 * e;
     x = p[0]; y = p[1]; t = p[2];
   }
-}
-
-// copies the active-obstacle table into shared memory and repoints the view
-__device__ __forceinline__ void stage_obstacles(ObsView &O, unsigned char *smem) {
-  const int n = O.n;
-  const int nv = O.voff[n];
-  double *s_ox = reinterpret_cast<double *>(smem);
-  double *s_oy = s_ox + n, *s_rad = s_oy + n, *s_vx = s_rad + n, *s_vy = s_vx + nv;
-  int32_t *s_kind = reinterpret_cast<int32_t *>(s_vy + nv);
-  int32_t *s_voff = s_kind + n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    s_ox[i] = O.ox[i]; s_oy[i] = O.oy[i]; s_rad[i] = O.rad[i]; s_kind[i] = O.kind[i];
-  }
-  for (int i = threadIdx.x; i <= n; i += blockDim.x) s_voff[i] = O.voff[i];
-  for (int i = threadIdx.x; i < nv; i += blockDim.x) { s_vx[i] = O.vx[i]; s_vy[i] = O.vy[i]; }
-  __syncthreads();
-  O.ox = s_ox; O.oy = s_oy; O.rad = s_rad; O.vx = s_vx; O.vy = s_vy;
-  O.kind = s_kind; O.voff = s_voff;
 }
 
 // no grid entry (polygon edge or ball within the robot radius) in any cell touching the box
@@ -459,45 +437,65 @@ dubins_solve_bin_kernel(EdgeArgs A, DubinsPath *paths, const uint32_t *perm, con
 template <bool MASKED>  // MASKED: only the obstacles of a subset take part (obstacle sweeps)
 __global__ void __launch_bounds__(EDGE_T)
 dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next_edge) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ObsView O = A.obs;
-  if (A.obs_smem && O.n > 0) stage_obstacles(O, smem_raw);
+  const ObsView &O = A.obs;
   const int lane = threadIdx.x & 31;
   __shared__ WarpScratch s_ws[EDGE_T / 32];
+  // Every lane works one edge ahead: while it walks an edge, the path record of the edge it
+  // will walk next is already on its way into the lane's other slot (cp.async), so a lane that
+  // finishes an edge never waits for global memory -- the records were written by the solve
+  // kernels and have long left L2 (112 B x 10 M edges).
+  __shared__ __align__(16) DubinsPath s_path[2][EDGE_T];
   WarpScratch *ws = &s_ws[threadIdx.x >> 5];
   PolylineWalker W;
   W.part = 3;
   long long e = -1;       // edge this lane is walking
+  long long en = -1;      // edge it walks next (record in flight or landed in s_path[cur ^ 1])
+  int cur = 0;
   bool exhausted = false; // no unclaimed edges left
   bool have_prev = false;
   double px = 0.0, py = 0.0;
+  long long w_next = 0, w_end = 0;  // the warp's reserve of claimed edges (uniform)
+  bool w_done = false;              // the global counter has run past the last edge
   for (;;) {
-    // lanes without an edge claim the next ones (one atomic per warp)
-    unsigned need = __ballot_sync(0xffffffffu, e < 0 && !exhausted);
-    if (need) {
-      int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if (lane == leader) base = atomicAdd(next_edge, (unsigned long long)__popc(need));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (e < 0 && !exhausted) {
-        long long mine = (long long)base + __popc(need & ((1u << lane) - 1));
-        if (mine >= A.n) {
-          exhausted = true;
-        } else {
-          e = mine;
-          // the records were written by the solve kernel and no longer sit in L2 (112 B x 10 M
-          // edges): pull the one that will be claimed a few trips from now out of DRAM early
-          if (mine + PATH_PREFETCH_AHEAD < A.n) {
-            const char *pf = reinterpret_cast<const char *>(paths + mine + PATH_PREFETCH_AHEAD);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + sizeof(DubinsPath) - 16));
-          }
-          W.start(paths + e, A.r_min, true);
-          have_prev = false;
-        }
-      }
+    if (e < 0 && en >= 0) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      e = en;
+      en = -1;
+      cur ^= 1;
+      W.start(&s_path[cur][threadIdx.x], A.r_min, true);
+      have_prev = false;
     }
-    if (__all_sync(0xffffffffu, e < 0)) break;
+    // lanes without a next edge take one from the warp's reserve of claimed edges and start its
+    // copy; the reserve is refilled WALK_CLAIM edges at a time, so the round trip of the global
+    // atomic is paid once per WALK_CLAIM edges instead of in every trip
+    unsigned need = __ballot_sync(0xffffffffu, en < 0 && !exhausted);
+    if (need) {
+      if (w_next == w_end && !w_done) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(next_edge, (unsigned long long)WALK_CLAIM);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        w_next = (long long)base;
+        w_end = min((long long)base + WALK_CLAIM, (long long)A.n);
+        if (w_next >= A.n) { w_done = true; w_end = w_next; }
+      }
+      const int avail = (int)(w_end - w_next);
+      const int rank = __popc(need & ((1u << lane) - 1));
+      if (en < 0 && !exhausted) {
+        if (rank < avail) {
+          en = w_next + rank;
+          const char *src = reinterpret_cast<const char *>(paths + en);
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_path[cur ^ 1][threadIdx.x]);
+#pragma unroll
+          for (int k = 0; k < (int)sizeof(DubinsPath); k += 16)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k), "l"(src + k) : "memory");
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        } else if (w_done) {
+          exhausted = true;
+        }  // else: served from the next refill
+      }
+      w_next += min(__popc(need), avail);
+    }
+    if (__all_sync(0xffffffffu, e < 0 && en < 0)) break;
     // every lane advances its polyline by one point; the new segments are tested together
     double cx = 0.0, cy = 0.0;
     bool ended = false, test = false;
@@ -591,9 +589,7 @@ __device__ __forceinline__ int line_screen(const ObsView &O, const ObstacleGrid 
 template <bool MASKED>
 __global__ void __launch_bounds__(EDGE_T)
 linecheck_kernel(EdgeArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  ObsView O = A.obs;
-  if (A.obs_smem && O.n > 0) stage_obstacles(O, smem_raw);
+  const ObsView &O = A.obs;
   const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
   if (e >= A.n) return;
   double sx, sy, st, ex, ey, et;
@@ -764,11 +760,6 @@ static int ensure_obstacle_grid(Store *S, double robot_radius, cudaStream_t st) 
   return DRRT_OK;
 }
 
-static size_t obstacle_smem_bytes(const Store *S, int nverts) {
-  size_t n = (size_t)S->obs.n_active;
-  return (3 * n + 2 * (size_t)nverts) * sizeof(double) + (2 * n + 1) * sizeof(int32_t) + 16;
-}
-
 int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const double *end_dev,
                         const int32_t *sid_dev, const int32_t *eid_dev, int edge_kind,
                         double robot_radius, double r_min, uint8_t *verdict_dev,
@@ -796,20 +787,10 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   A.obs.kind = S->obs.kind; A.obs.ox = S->obs.ox; A.obs.oy = S->obs.oy; A.obs.rad = S->obs.rad;
   A.obs.voff = S->obs.vert_off; A.obs.vx = S->obs.vx; A.obs.vy = S->obs.vy;
   A.verdict = verdict_dev; A.length = length_dev;
-  size_t smem = 0;
+  const size_t smem = 0;
   if (A.obs.n > 0) {
     DRRT_CHECK(ensure_obstacle_grid(S, robot_radius, st));
     A.grid = S->ogrid;
-    size_t need = obstacle_smem_bytes(S, S->obs.n_active_verts);
-    if (need <= 96 * 1024) { smem = need; A.obs_smem = 1; }
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    DRRT_CUDA(cudaFuncSetAttribute(dubins_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    DRRT_CUDA(cudaFuncSetAttribute(dubins_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    DRRT_CUDA(cudaFuncSetAttribute(linecheck_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    DRRT_CUDA(cudaFuncSetAttribute(linecheck_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_done = true;
   }
   const bool masked = A.obs.mask != nullptr;
   unsigned nb = (unsigned)((n + EDGE_T - 1) / EDGE_T);
