@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
   __shared__ long long s_tmp[WARPS];
   __shared__ int s_wsum[WARPS];
   __shared__ Query s_query;
+  __shared__ double s_q[CTA_CHUNK][4];
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const GridView &V = A.V;
@@ -519,14 +520,24 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
     const int64_t q0 = ck * A.chunk_len, q1 = min(A.nq, q0 + (int64_t)A.chunk_len);
     int64_t run = 0;    // hits of the chunk's earlier rows
     bool over = false;  // some row did not fit the slice
+    // the slice's queries in one round of loads (the barrier at the top of the loop ordered the
+    // previous slice's reads of s_q)
+    if (tid < 4 * CTA_CHUNK) {
+      const int k = tid >> 2, c = tid & 3;
+      const int64_t qk = q0 + k;
+      double v = 0.0;
+      if (qk < q1) v = c < 3 ? A.q[3 * qk + c] : (A.radius ? A.radius[qk] : A.radius_all);
+      s_q[k][c] = v;
+    }
+    __syncthreads();
 
     for (int64_t qi = q0; qi < q1; qi++) {
       if (tid == 0) { s_count = 0; s_crowded = 0; s_nlist = 0; }
       for (int i = tid; i < CTA_NW / 4; i += T) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
       if (w == 0) {
         Query Q0;
-        setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
-                            A.radius ? A.radius[qi] : A.radius_all, Q0);
+        const double *sq = s_q[qi - q0];
+        setup_query<METRIC>(V, sq[0], sq[1], sq[2], sq[3], Q0);
         if (lane == 0) s_query = Q0;
       }
       __syncthreads();
