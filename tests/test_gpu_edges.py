@@ -179,3 +179,25 @@ def test_ranked_solve_matches_full_solve(drrt, po):
     assert (clr[diff] < BAND).all() and len(diff) <= 3
     ok = rln < 1e11
     assert np.allclose(ln[idx][ok], rln[ok], rtol=1e-9, atol=1e-9)
+
+
+def test_ranked_solve_other_turn_radii(drrt, po):
+    # the float32 ranking scales its bands with r_min and the edge length
+    t = drrt.KDTree()
+    for r_min, max_len, seed in ((0.6, 3.0, 891), (2.5, 1.0, 892), (0.05, 4.0, 893)):
+        s, e = synth.random_edges(60_000, seed, max_len=max_len)
+        _, ln = t.ExplicitEdgeCheck(s, e, r_min=r_min)          # ranked pipeline
+        _, full = t.DubinsWords(s, e, r_min=r_min)              # all six candidates
+        assert np.array_equal(ln, full), r_min
+
+
+def test_long_straight_edges(drrt, po):
+    # LineCheck over many grid cells (Theta*'s any-angle edges cross the whole map)
+    o = synth.obstacles()
+    t, ro = _obs(drrt, po, o)
+    rng = np.random.default_rng(895)
+    s = synth.box_points(40_000, 896)
+    e = synth.box_points(40_000, 897)
+    e[:10_000] = s[:10_000] + rng.normal(0, 0.01, (10_000, 3))   # very short ones too
+    e[10_000:10_050] = s[10_000:10_050]                          # zero length
+    _compare(t, ro, s, e, kind=1)
