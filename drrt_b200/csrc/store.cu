@@ -39,11 +39,32 @@ __global__ void kd_insert_init(int64_t base, int64_t n, const double *__restrict
   if (id == 0) {  // kdtree.cpp:94-99
     split[0] = 0;
     ins_cur[k] = -1;
-  } else {
-    ins_cur[k] = 0;
-    ins_split[k] = 0;  // bit 7 clear: nothing contended yet
-    ins_gate[k] = GATE_NONE;
+    return;
   }
+  // Descent through the nodes that were in the tree before this batch (kdtree.cpp:104-126):
+  // their links never change during the batch, so no lock-step round is needed down to the
+  // first child slot that is empty or holds a node of the batch -- the rounds start there.
+  int32_t c = 0;
+  int s = 0;
+  double g = GATE_NONE;
+  if (base > 0) {
+    const double px = pos[3 * k + 0], py = pos[3 * k + 1], pt = pos[3 * k + 2];
+    for (;;) {
+      const double mine = s == 0 ? px : (s == 1 ? py : pt);
+      const double theirs = s == 0 ? x[c] : (s == 1 ? y[c] : th[c]);
+      const bool go_left = mine < theirs;
+      const int32_t child = go_left ? left[c] : right[c];
+      if (child == EMPTY || child >= base) break;  // kd_insert_step takes over at c
+      if (go_left && s == 2 && theirs < g) g = theirs;
+      c = child;
+      s = (s == 2) ? 0 : s + 1;
+    }
+  } else {
+    c = 0;
+  }
+  ins_cur[k] = c;
+  ins_split[k] = (uint8_t)s;  // bit 7 clear: nothing contended yet
+  ins_gate[k] = g;
 }
 
 __device__ __forceinline__ double coord(const double *x, const double *y, const double *th,
