@@ -164,6 +164,8 @@ def main():
         run_reference(args)
         return
 
+    # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import drrt_b200
