@@ -340,8 +340,8 @@ __device__ void dubins_solve(double sx, double sy, double st, double ex, double 
 // when it may exist and its float length is within `margin` of the shortest candidate that
 // surely exists, or when the float pass cannot tell: it sits on an existence boundary (D near
 // 2r / 4r), has a turn angle near the 0 / 2pi jump of Right/LeftTurnDist, a degenerate centre
-// distance, or is not finite.  Float errors here are ~1e-6 * scale in coordinates and lengths;
-// bands and margin are 1e-3-sized, three orders above that.  The listed candidates are then
+// distance, or is not finite.  The bands and the margin are several times the float error budget
+// spelled out in the function.  The listed candidates are then
 // solved in double exactly as the reference does; the others are provably longer than the
 // winner, so the winner and bestDist are the reference's (dubins_solve).  The float pass uses
 // fast approximations (rank_atan2 1.2e-5 rad, __sincosf, __fdividef): their errors are part of
@@ -372,9 +372,12 @@ __device__ __forceinline__ int dubins_rank(double sx, double sy, double st, doub
   const float scale = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fabsf(r));
   // float32 is only trusted for ordinary geometry
   if (!(r > 0.0f) || !(scale <= 64.0f * r) || !(fabs(st) <= 64.0) || !(fabs(et) <= 64.0)) return CAND_ALL;
-  const float band = 1e-3f * (r + scale);    // existence boundaries, degenerate D
-  const float margin = 2e-3f * (r + scale);  // length comparison
-  const float eps_th = 1e-3f;                // turn angles near the 0 / 2pi jump
+  // error budget of the float pass: rank_atan2 1.2e-5 rad per angle, a turn is the difference of
+  // two (2.5e-5 with the rounding of its points), a length three of those times r plus ~1e-6 of
+  // segment: < 1e-4 * (r + scale), and two lengths are compared
+  const float band = 2e-4f * (r + scale);    // existence boundaries, degenerate D
+  const float margin = 5e-4f * (r + scale);  // length comparison
+  const float eps_th = 2e-4f;                // turn angles near the 0 / 2pi jump
   float ss, cs0, se, ce;
   rank_sincos((float)st, &ss, &cs0);
   rank_sincos((float)et, &se, &ce);
