@@ -226,7 +226,7 @@ int drrt_store_destroy(drrt_store *h) {
     if (S->d_pending) cudaFree(S->d_pending);
     if (S->d_ticket) cudaFree(S->d_ticket);
     if (S->d_edge_counter) cudaFree(S->d_edge_counter);
-    S->x_unsafe.release(); S->x_len.release(); S->x_lmc.release(); S->x_best.release(); S->x_best_cost.release();
+    S->x_unsafe.release(); S->x_len.release(); S->x_lmc.release(); S->x_best.release(); S->x_row.release(); S->x_best_cost.release();
     S->edge_paths.release(); S->edge_masks.release(); S->edge_perm.release(); S->edge_bins.release(); S->og_off.release(); S->og_idx.release(); S->og_eobs.release();
     S->og_ball.release(); S->og_erec.release();
     if (S->d_bounds) cudaFree(S->d_bounds);

@@ -259,6 +259,7 @@ struct EdgeArgs {
   // neighbour-list mode (drrt_extend_batch): edge e = 2*t + dir over the CSR rows of a range
   // result; dir 0 = query -> neighbour (FindBestParent), dir 1 = neighbour -> query (Extend)
   const int64_t *csr_off;
+  const int32_t *csr_row;  // row (query) of every pair
   const int32_t *csr_ids;
   const double *csr_q;
   int64_t csr_nq;
@@ -280,11 +281,7 @@ __device__ __forceinline__ void load_pose(const EdgeArgs &A, int64_t e, bool end
       int32_t id = A.csr_ids[pair];
       x = A.sx[id]; y = A.sy[id]; t = A.sth[id];
     } else {
-      int64_t lo = 0, hi = A.csr_nq;  // row with csr_off[row] <= pair < csr_off[row + 1]
-      while (hi - lo > 1) {
-        int64_t mid = (lo + hi) >> 1;
-        if (A.csr_off[mid] <= pair) lo = mid; else hi = mid;
-      }
+      const int64_t lo = A.csr_row[pair];  // the query whose neighbour list holds this pair
       x = A.csr_q[3 * lo]; y = A.csr_q[3 * lo + 1]; t = A.csr_q[3 * lo + 2];
     }
     return;
@@ -778,6 +775,7 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   A.sx = S->x.p; A.sy = S->y.p; A.sth = S->th.p;
   if (csr) {
     A.csr_off = S->csr_off; A.csr_ids = S->csr_ids; A.csr_q = S->csr_q; A.csr_nq = S->csr_nq;
+    A.csr_row = S->x_row.p;
   }
   A.metric = S->metric; A.edge_kind = edge_kind;
   A.robot_radius = robot_radius; A.r_min = r_min;
@@ -880,6 +878,11 @@ __global__ void best_parent_kernel(int64_t nq, const int64_t *off, const int32_t
   }
 }
 
+__global__ void fill_rows_kernel(int64_t nq, const int64_t *off, int32_t *row) {
+  for (int64_t q = blockIdx.x; q < nq; q += gridDim.x)
+    for (int64_t p = off[q] + threadIdx.x; p < off[q + 1]; p += blockDim.x) row[p] = (int32_t)q;
+}
+
 int extend_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *radius_dev,
                      double radius_all, double robot_radius, double r_min, const double *lmc_dev,
                      cudaStream_t st, drrt_range_result *rr, uint8_t **unsafe_dev, double **len_dev,
@@ -896,6 +899,11 @@ int extend_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *ra
   *unsafe_dev = S->x_unsafe.p;
   *len_dev = S->x_len.p;
   if (total > 0) {
+    // row index of every pair, written once (the edge kernels would otherwise search the offsets
+    // for every pose they load)
+    DRRT_CHECK(S->x_row.reserve((size_t)total + 1, st));
+    fill_rows_kernel<<<(unsigned)std::min<int64_t>(nq, 148 * 16), 256, 0, st>>>(nq, rr->offsets_dev, S->x_row.p);
+    DRRT_LAUNCHED();
     S->csr_q = q_dev;
     S->csr_nq = nq;
     int rc = edgecheck_batch_dev(S, 2 * total, nullptr, nullptr, nullptr, nullptr, DRRT_EDGE_DUBINS,

@@ -112,7 +112,7 @@ struct Store {
   // fused Extend: per-neighbour verdicts / lengths (2 per pair), query poses of the CSR rows
   DevBuf<uint8_t> x_unsafe;
   DevBuf<double> x_len, x_lmc;
-  DevBuf<int32_t> x_best;
+  DevBuf<int32_t> x_best, x_row;
   DevBuf<double> x_best_cost;
   const double *csr_q = nullptr;
   const int64_t *csr_off = nullptr;
