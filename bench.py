@@ -260,7 +260,20 @@ def main():
     dist_pin = torch.empty(hits_2a + 1024, dtype=torch.float64).pin_memory()
     lib = capi.load()
 
+    off_pin = torch.empty(N_QUERIES + 1, dtype=torch.int64).pin_memory()
+
     def e2e_step():
+        # the one-call host query: rows of a finished sub-batch cross PCIe while the next
+        # sub-batch is computed
+        total = C.c_int64()
+        capi.check(lib.drrt_range_batch_into(tree._h, N_QUERIES, C.cast(q_pin.data_ptr(), capi.c_dp),
+                                             None, r2a, ids_pin.numel(),
+                                             C.cast(off_pin.data_ptr(), capi.c_i64p),
+                                             C.cast(ids_pin.data_ptr(), capi.c_ip),
+                                             C.cast(dist_pin.data_ptr(), capi.c_dp), C.byref(total)))
+        return total.value
+
+    def e2e_two_call_step():
         total = C.c_int64()
         capi.check(lib.drrt_range_batch(tree._h, N_QUERIES, C.cast(q_pin.data_ptr(), capi.c_dp), None,
                                         r2a, C.cast(counts_pin.data_ptr(), capi.c_ip),
@@ -269,23 +282,33 @@ def main():
                                         C.cast(dist_pin.data_ptr(), capi.c_dp)))
         return total.value
 
+    def e2e_time(step):
+        for _ in range(2):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            assert step() == hits_2a
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return world * N_QUERIES * e2e_steps / float(dt.item())
+
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * N_QUERIES * e2e_steps / float(e2e_dt.item())
+    launches0 = capi.launches()
+    e2e_value = e2e_time(e2e_step)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * N_QUERIES,
-           "d2h_bytes_per_step": 4 * N_QUERIES + 12 * hits_2a}
+           "d2h_bytes_per_step": 8 * (N_QUERIES + 1) + 12 * hits_2a,
+           "call": "drrt_range_batch_into (one call, pinned host buffers; 16384-query sub-batches, "
+                   "row copies overlap the next sub-batch)",
+           "gpu_launches_per_step": (capi.launches() - launches0) // (e2e_steps + 2)}
 
     extra = {}
     if not args.no_extra:
+        extra["e2e_two_call"] = {"queries_per_s": e2e_time(e2e_two_call_step),
+                                 "call": "drrt_range_batch (counts) + drrt_range_fetch (rows): kernel, "
+                                         "pack, then the copies"}
         # 2b: sparse radius (~76 hits/query)
         ms = timed(step_range(r2b), args.steps, 3) / args.steps
         res = state["res"]

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DRRT_B200_LIB: another build of the same library (kernel A/B runs); still no CPU path
 LIB_PATH = os.environ.get("DRRT_B200_LIB") or os.path.join(_HERE, "libdrrt_b200.so")
 
-OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_NO_DEVICE, ERR_STATE = range(7)
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_NO_DEVICE, ERR_STATE, ERR_CAPACITY = range(8)
 METRIC_R2S1_WRAP, METRIC_EUCLID = 0, 1
 EDGE_DUBINS, EDGE_STRAIGHT = 0, 1
 TRAJ_MAX = 200
@@ -52,6 +52,8 @@ SIGNATURES = {
     "drrt_store_positions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_dp]),
     "drrt_range_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, c_ip, c_i64p]),
     "drrt_range_fetch": (C.c_int, [C.c_void_p, c_ip, c_dp]),
+    "drrt_range_batch_into": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_int64,
+                                        c_i64p, c_ip, c_dp, c_i64p]),
     "drrt_range_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_void_p, C.POINTER(RangeResult)]),
     "drrt_range_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RangeResult)]),

@@ -233,6 +233,12 @@ int drrt_store_destroy(drrt_store *h) {
     if (S->h_pending) cudaFreeHost(S->h_pending);
     if (S->h_bounds) cudaFreeHost(S->h_bounds);
     if (S->h_scalar) cudaFreeHost(S->h_scalar);
+    for (int b = 0; b < 2; b++) {
+      S->p_off[b].release(); S->p_ids[b].release(); S->p_dist[b].release();
+      if (S->ev_packed[b]) cudaEventDestroy(S->ev_packed[b]);
+      if (S->ev_copied[b]) cudaEventDestroy(S->ev_copied[b]);
+    }
+    if (S->copy_stream) cudaStreamDestroy(S->copy_stream);
     if (S->stream) cudaStreamDestroy(S->stream);
   }
   delete S;
@@ -346,6 +352,90 @@ int drrt_range_fetch(drrt_store *h, int32_t *ids, double *dist) {
     if (dist) DRRT_CHECK(download(dist, res.dist_dev, S->last_total * sizeof(double), st));
   }
   DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+// Sub-batch of the streamed host query: large enough that the CTA kernel still takes
+// full-length slices on every resident CTA, small enough that the first rows leave early.
+static constexpr int64_t INTO_SUB = 16384;
+
+int drrt_range_batch_into(drrt_store *h, int64_t nq, const double *q, const double *radius,
+                          double radius_all, int64_t cap, int64_t *offsets, int32_t *ids,
+                          double *dist, int64_t *total) {
+  ENTER(h);
+  if (nq < 0 || cap < 0 || (nq > 0 && (!q || !offsets)) || (cap > 0 && !ids))
+    return set_error(DRRT_ERR_INVALID, "range_into: arguments");
+  cudaStream_t st = S->stream;
+  if (!S->copy_stream) {
+    DRRT_CUDA(cudaStreamCreateWithFlags(&S->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_packed[b], cudaEventDisableTiming));
+      DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_copied[b], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t cs = S->copy_stream;
+  DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
+  DRRT_CHECK(upload(q, S->q_stage.p, 3 * nq * sizeof(double), st));
+  if (radius) {
+    DRRT_CHECK(S->rad_stage.reserve(nq + 1, st));
+    DRRT_CHECK(upload(radius, S->rad_stage.p, nq * sizeof(double), st));
+  }
+  if (offsets) offsets[0] = 0;
+  const int64_t sub = nq > INTO_SUB + INTO_SUB / 2 ? INTO_SUB : std::max<int64_t>(nq, 1);
+  std::vector<int64_t> bases;
+  int64_t base = 0;
+  int rc = DRRT_OK;
+  bool used[2] = {false, false};
+  // one sub-batch: query, pack into buffer b, queue the copies; an error leaves the loop but the
+  // copies already queued into the caller's buffers are always waited for below
+  auto sub_batch = [&](int64_t k0, int64_t nb, int b) -> int {
+    drrt_range_result res{};
+    DRRT_CHECK(range_batch_dev(S, nb, S->q_stage.p + 3 * k0, radius ? S->rad_stage.p + k0 : nullptr,
+                               radius_all, st, &res));
+    // buffer b is free once the copies of sub-batch k - 2 have left it (growing it frees the
+    // old block, so wait on the host in that case; otherwise the stream waits)
+    const size_t need = (size_t)res.total + 1;
+    if (used[b]) {
+      if (need > S->p_ids[b].cap || need > S->p_dist[b].cap || (size_t)nb + 1 > S->p_off[b].cap)
+        DRRT_CUDA(cudaEventSynchronize(S->ev_copied[b]));
+      else
+        DRRT_CUDA(cudaStreamWaitEvent(st, S->ev_copied[b], 0));
+    }
+    DRRT_CHECK(S->p_off[b].reserve(nb + 1, st));
+    DRRT_CHECK(S->p_ids[b].reserve(need, st));
+    DRRT_CHECK(S->p_dist[b].reserve(need, st));
+    DRRT_CHECK(range_pack_to(S, st, S->p_off[b].p, S->p_ids[b].p, S->p_dist[b].p));
+    DRRT_CUDA(cudaEventRecord(S->ev_packed[b], st));
+    DRRT_CUDA(cudaStreamWaitEvent(cs, S->ev_packed[b], 0));
+    // offsets of the sub-batch are relative to its first row; the base is added below
+    DRRT_CHECK(download(offsets + k0, S->p_off[b].p, (nb + 1) * sizeof(int64_t), cs));
+    if (base + res.total <= cap && res.total > 0) {
+      DRRT_CHECK(download(ids + base, S->p_ids[b].p, res.total * sizeof(int32_t), cs));
+      if (dist) DRRT_CHECK(download(dist + base, S->p_dist[b].p, res.total * sizeof(double), cs));
+    }
+    DRRT_CUDA(cudaEventRecord(S->ev_copied[b], cs));
+    used[b] = true;
+    bases.push_back(base);
+    base += res.total;
+    return DRRT_OK;
+  };
+  for (int64_t k0 = 0, k = 0; k0 < nq && rc == DRRT_OK; k0 += sub, k++)
+    rc = sub_batch(k0, std::min(sub, nq - k0), (int)(k & 1));
+  cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st);
+  S->last_nq = -1;  // the handle holds one sub-batch only: nothing to fetch or pack
+  if (rc != DRRT_OK) return rc;
+  DRRT_CUDA(e1);
+  DRRT_CUDA(e2);
+  // (the entry a sub-batch shares with its successor was overwritten by the successor's 0)
+  for (size_t k = 1; k < bases.size(); k++) {
+    const int64_t k0 = (int64_t)k * sub, nb = std::min(sub, nq - k0);
+    for (int64_t i = 0; i < nb; i++) offsets[k0 + i] += bases[k];
+  }
+  if (nq > 0) offsets[nq] = base;
+  if (total) *total = base;
+  if (base > cap)
+    return set_error(DRRT_ERR_CAPACITY, "range_into: %lld hits, caller buffers hold %lld",
+                     (long long)base, (long long)cap);
   return DRRT_OK;
 }
 

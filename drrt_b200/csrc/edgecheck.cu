@@ -310,42 +310,98 @@ __device__ __forceinline__ bool region_empty(const ObstacleGrid &G, double lox, 
   return true;
 }
 
-// marks the parts of a solved path that cannot collide and stores the record
-__device__ __forceinline__ void finish_path(const EdgeArgs &A, int64_t e, DubinsPath &P, DubinsPath *paths) {
-  if (A.obs.n > 0 && A.grid.nx > 0) {
-    // parts whose whole circle (or straight piece) lies where no obstacle comes within the
-    // robot radius need no per-segment test; a path made only of such parts is free
-    int idle = 0, parts = 0;
-    const double rr = fabs(A.r_min) * (1.0 + 1e-9) + 1e-9;
-    for (int k = 0; k < 3; k++) {
-      int kind = P.kind(k);
-      if (kind == PART_NONE) continue;
-      parts++;
-      const DubinsPart &p = P.part[k];
-      bool empty = (kind == PART_LINE)
-                       ? region_empty(A.grid, fmin(p.cx, p.a), fmin(p.cy, p.b), fmax(p.cx, p.a), fmax(p.cy, p.b))
-                       : region_empty(A.grid, p.cx - rr, p.cy - rr, p.cx + rr, p.cy + rr);
-      if (empty) { idle++; P.kinds |= 1 << (8 + k); }
+// Decides what it can about a solved path and hands the rest to the walk kernel.  All 32 lanes
+// of a warp call it together (`valid`: the lane has an edge).
+//  * parts whose whole circle (or straight piece) lies where no obstacle comes within the robot
+//    radius need no per-segment test; a path made only of such parts is free;
+//  * the verdict is an OR over the polyline's segments, so their order is free: the FIRST and the
+//    LAST segment are tested right here, where every lane has an edge, with the warp-cooperative
+//    test of the walk (the reference's own segment test on the reference's own two points, only
+//    earlier).  The planner's nodes are not filtered against the obstacles (the range query
+//    returns what the tree holds), so the usual colliding edge has an end pose within the robot
+//    radius of an obstacle boundary: in config 3 ~95 % of the colliding edges are decided by
+//    these two segments, and an edge whose START is clear would otherwise be walked to its very
+//    last segment before the hit shows;
+//  * an undecided edge gets the next slot of the compact work list (its record carries the edge
+//    id in place of dist_, which the walk does not read), so the walk kernel neither loads nor
+//    spends a trip on the decided ones.
+// work[0] = walk claim counter, work[1] = number of records listed.
+template <bool MASKED>
+__device__ __forceinline__ void finish_path_impl(const EdgeArgs &A, bool valid, int64_t e, DubinsPath &P,
+                                                 DubinsPath *paths, unsigned long long *work,
+                                                 WarpScratch *ws) {
+  const int lane = threadIdx.x & 31;
+  if (valid && A.length) A.length[e] = P.dist;
+  if (A.obs.n == 0) return;    // nothing to collide with: the host clears the verdicts
+  int decided = valid ? -1 : 0;  // 0 free, 1 collides (a lane without an edge has nothing to decide)
+  if (valid) {
+    if (A.grid.nx > 0) {
+      int idle = 0, parts = 0;
+      const double rr = fabs(A.r_min) * (1.0 + 1e-9) + 1e-9;
+      for (int k = 0; k < 3; k++) {
+        int kind = P.kind(k);
+        if (kind == PART_NONE) continue;
+        parts++;
+        const DubinsPart &p = P.part[k];
+        bool empty = (kind == PART_LINE)
+                         ? region_empty(A.grid, fmin(p.cx, p.a), fmin(p.cy, p.b), fmax(p.cx, p.a), fmax(p.cy, p.b))
+                         : region_empty(A.grid, p.cx - rr, p.cy - rr, p.cx + rr, p.cy + rr);
+        if (empty) { idle++; P.kinds |= 1 << (8 + k); }
+      }
+      if (idle == parts) decided = 0;
+    } else if ((P.kinds & 63) == 0) {
+      decided = 0;  // no path (dubinsedge.cpp:897 falls through to false)
     }
-    if (idle == parts) P.kinds = 0;  // the walk kernel reports it free without walking
   }
-  paths[e] = P;
-  if (A.length) A.length[e] = P.dist;
+  PolylineWalker W;
+  double x0 = 0.0, y0 = 0.0, x1 = 0.0, y1 = 0.0;
+  bool test = false;
+  if (decided < 0) {
+    W.start(&P, A.r_min, false);
+    test = W.next(&x0, &y0) && W.next(&x1, &y1);
+  }
+  if (warp_segments_vs_obstacles<MASKED>(A.obs, A.grid, test, x0, y0, x1, y1, A.robot_radius, ws, lane))
+    decided = 1;
+  test = false;
+  if (decided < 0) test = W.last_segment(&P, A.r_min, &x0, &y0, &x1, &y1);
+  if (warp_segments_vs_obstacles<MASKED>(A.obs, A.grid, test, x0, y0, x1, y1, A.robot_radius, ws, lane))
+    decided = 1;
+  if (valid && decided >= 0) A.verdict[e] = (uint8_t)decided;
+  // warp-aggregated append of the undecided edges
+  const unsigned m = __ballot_sync(0xffffffffu, decided < 0);
+  if (decided < 0) {
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&work[1], (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    P.dist = __longlong_as_double((long long)e);
+    paths[base + __popc(m & ((1u << lane) - 1u))] = P;
+  }
+}
+
+__device__ __forceinline__ void finish_path(const EdgeArgs &A, bool valid, int64_t e, DubinsPath &P,
+                                            DubinsPath *paths, unsigned long long *work, WarpScratch *ws) {
+  if (A.obs.mask) finish_path_impl<true>(A, valid, e, P, paths, work, ws);
+  else finish_path_impl<false>(A, valid, e, P, paths, work, ws);
 }
 
 // K4a: Edge::NewEdge + the candidate solve of CalculateTrajectory, one thread per edge, all
 // six candidates in double (small batches; the ranked pipeline below is the fast path)
 __global__ void __launch_bounds__(EDGE_T)
-dubins_solve_kernel(EdgeArgs A, DubinsPath *paths) {
+dubins_solve_kernel(EdgeArgs A, DubinsPath *paths, unsigned long long *work) {
+  __shared__ WarpScratch s_ws[EDGE_T / 32];
   const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
-  if (e >= A.n) return;
-  double sx, sy, st, ex, ey, et;
-  load_pose(A, e, false, sx, sy, st);
-  load_pose(A, e, true, ex, ey, et);
+  const bool valid = e < A.n;
   DubinsPath P;
-  double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
-  dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
-  finish_path(A, e, P, paths);
+  P.kinds = 0;
+  if (valid) {
+    double sx, sy, st, ex, ey, et;
+    load_pose(A, e, false, sx, sy, st);
+    load_pose(A, e, true, ex, ey, et);
+    double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
+    dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
+  }
+  finish_path(A, valid, e, P, paths, work, &s_ws[threadIdx.x >> 5]);
 }
 
 // K4a, ranked: the double-precision solve of all six Dubins words costs ~5800 instructions per
@@ -415,25 +471,33 @@ dubins_bin_scatter_kernel(int64_t n, const uint8_t *masks, unsigned long long *b
 template <int MASK>
 __global__ void __launch_bounds__(EDGE_T)
 dubins_solve_bin_kernel(EdgeArgs A, DubinsPath *paths, const uint32_t *perm, const uint8_t *masks,
-                        const unsigned long long *bin_state, int bin) {
+                        const unsigned long long *bin_state, int bin, unsigned long long *work) {
+  __shared__ WarpScratch s_ws[EDGE_T / 32];
   const unsigned long long lo = bin_state[8 + bin], hi = bin_state[8 + bin + 1];
-  for (unsigned long long i = lo + (unsigned long long)blockIdx.x * EDGE_T + threadIdx.x; i < hi;
-       i += (unsigned long long)gridDim.x * EDGE_T) {
-    const int64_t e = perm[i];
-    double sx, sy, st, ex, ey, et;
-    load_pose(A, e, false, sx, sy, st);
-    load_pose(A, e, true, ex, ey, et);
+  // whole warps stay in the loop (finish_path is warp-cooperative)
+  for (unsigned long long w0 = lo + (unsigned long long)blockIdx.x * EDGE_T + (threadIdx.x & ~31u); w0 < hi;
+       w0 += (unsigned long long)gridDim.x * EDGE_T) {
+    const unsigned long long i = w0 + (threadIdx.x & 31u);
+    const bool valid = i < hi;
+    int64_t e = 0;
     DubinsPath P;
-    double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
-    dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P, MASK ? MASK : (int)masks[e]);
-    finish_path(A, e, P, paths);
+    P.kinds = 0;
+    if (valid) {
+      e = perm[i];
+      double sx, sy, st, ex, ey, et;
+      load_pose(A, e, false, sx, sy, st);
+      load_pose(A, e, true, ex, ey, et);
+      double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
+      dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P, MASK ? MASK : (int)masks[e]);
+    }
+    finish_path(A, valid, e, P, paths, work, &s_ws[threadIdx.x >> 5]);
   }
 }
 
 // K4b: polyline walk + ExplicitEdgeCheck2D per segment, lanes refill from a global counter
 template <bool MASKED>  // MASKED: only the obstacles of a subset take part (obstacle sweeps)
 __global__ void __launch_bounds__(EDGE_T)
-dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next_edge) {
+dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work) {
   const ObsView &O = A.obs;
   const int lane = threadIdx.x & 31;
   __shared__ WarpScratch s_ws[EDGE_T / 32];
@@ -443,10 +507,13 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
   // kernels and have long left L2 (112 B x 10 M edges).
   __shared__ __align__(16) DubinsPath s_path[2][EDGE_T];
   WarpScratch *ws = &s_ws[threadIdx.x >> 5];
+  // the undecided edges, listed by the solve kernels (finish_path); a record carries its edge id
+  const long long n_work = (long long)work[1];
+  unsigned long long *next_edge = &work[0];
   PolylineWalker W;
   W.part = 3;
-  long long e = -1;       // edge this lane is walking
-  long long en = -1;      // edge it walks next (record in flight or landed in s_path[cur ^ 1])
+  long long e = -1;       // record this lane is walking
+  long long en = -1;      // record it walks next (in flight or landed in s_path[cur ^ 1])
   int cur = 0;
   bool exhausted = false; // no unclaimed edges left
   bool have_prev = false;
@@ -472,8 +539,8 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
         if (lane == 0) base = atomicAdd(next_edge, (unsigned long long)WALK_CLAIM);
         base = __shfl_sync(0xffffffffu, base, 0);
         w_next = (long long)base;
-        w_end = min((long long)base + WALK_CLAIM, (long long)A.n);
-        if (w_next >= A.n) { w_done = true; w_end = w_next; }
+        w_end = min((long long)base + WALK_CLAIM, n_work);
+        if (w_next >= n_work) { w_done = true; w_end = w_next; }
       }
       const int avail = (int)(w_end - w_next);
       const int rank = __popc(need & ((1u << lane) - 1));
@@ -504,7 +571,7 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *next
     bool hit = warp_segments_vs_obstacles<MASKED>(O, A.grid, test, px, py, cx, cy, A.robot_radius, ws, lane);
     if (e >= 0) {
       if (ended || hit) {  // :878-889 first hit decides the edge
-        A.verdict[e] = hit ? 1 : 0;
+        A.verdict[__double_as_longlong(s_path[cur][threadIdx.x].dist)] = hit ? 1 : 0;
         e = -1;
       } else {
         px = cx;
@@ -800,8 +867,11 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
     if (st != S->stream) DRRT_CUDA(cudaStreamSynchronize(S->stream));
     DRRT_CHECK(S->edge_paths.reserve((size_t)n * sizeof(DubinsPath), st));
     DubinsPath *paths = reinterpret_cast<DubinsPath *>(S->edge_paths.p);
+    // [0] claim counter of the walk, [1] number of undecided edges listed by the solve kernels
+    unsigned long long *work = S->d_edge_counter;
+    DRRT_CUDA(cudaMemsetAsync(work, 0, 2 * sizeof(unsigned long long), st));
     if (n < RANKED_SOLVE_MIN || n >= 0x7fffffff) {
-      dubins_solve_kernel<<<nb, EDGE_T, 0, st>>>(A, paths);
+      dubins_solve_kernel<<<nb, EDGE_T, 0, st>>>(A, paths, work);
       DRRT_LAUNCHED();
     } else {
       DRRT_CHECK(S->edge_masks.reserve((size_t)n, st));
@@ -818,19 +888,18 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
       const unsigned g = (unsigned)std::min<int64_t>(nb, (int64_t)sms * 12);
-      dubins_solve_bin_kernel<CAND_RSL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 0);
-      dubins_solve_bin_kernel<CAND_RSR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 1);
-      dubins_solve_bin_kernel<CAND_RLR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 2);
-      dubins_solve_bin_kernel<CAND_LSR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 3);
-      dubins_solve_bin_kernel<CAND_LSL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 4);
-      dubins_solve_bin_kernel<CAND_LRL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 5);
-      dubins_solve_bin_kernel<0><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 6);
+      dubins_solve_bin_kernel<CAND_RSL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 0, work);
+      dubins_solve_bin_kernel<CAND_RSR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 1, work);
+      dubins_solve_bin_kernel<CAND_RLR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 2, work);
+      dubins_solve_bin_kernel<CAND_LSR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 3, work);
+      dubins_solve_bin_kernel<CAND_LSL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 4, work);
+      dubins_solve_bin_kernel<CAND_LRL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 5, work);
+      dubins_solve_bin_kernel<0><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 6, work);
       for (int k = 0; k < 10; k++) DRRT_LAUNCHED();
     }
     if (A.obs.n == 0) {
       DRRT_CUDA(cudaMemsetAsync(verdict_dev, 0, (size_t)n, st));  // nothing to collide with
     } else {
-      DRRT_CUDA(cudaMemsetAsync(S->d_edge_counter, 0, sizeof(unsigned long long), st));
       // persistent grid: enough CTAs to fill the machine, lanes pull edges until none are left
       int per_sm = 0;
       if (masked)
@@ -840,8 +909,8 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
       unsigned grid = (unsigned)std::min<int64_t>(nb, (int64_t)std::max(per_sm, 1) * sms);
-      if (masked) dubins_walk_kernel<true><<<grid, EDGE_T, smem, st>>>(A, paths, S->d_edge_counter);
-      else dubins_walk_kernel<false><<<grid, EDGE_T, smem, st>>>(A, paths, S->d_edge_counter);
+      if (masked) dubins_walk_kernel<true><<<grid, EDGE_T, smem, st>>>(A, paths, work);
+      else dubins_walk_kernel<false><<<grid, EDGE_T, smem, st>>>(A, paths, work);
       DRRT_LAUNCHED();
     }
   }

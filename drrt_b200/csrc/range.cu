@@ -832,6 +832,24 @@ static void fill_result(Store *S, drrt_range_result *out) {
   out->extent = out->packed ? S->last_total : S->last_extent;
 }
 
+int range_pack_to(Store *S, cudaStream_t st, int64_t *off_out, int32_t *ids_out, double *dist_out) {
+  if (S->last_nq < 0) return set_error(DRRT_ERR_STATE, "pack: no range batch on this handle");
+  const int64_t nq = S->last_nq;
+  if (nq == 0) return DRRT_OK;
+  scan_counts_kernel<<<1, 1024, 0, st>>>(S->r_counts.p, nq, off_out);
+  DRRT_LAUNCHED();
+  if (S->last_total > 0) {
+    const int32_t *ids = S->last_packed_in_alt ? S->r_ids2.p : S->r_ids.p;
+    const double *dist = S->last_packed_in_alt ? S->r_dist2.p : S->r_dist.p;
+    const int64_t *off = S->last_packed_in_alt ? S->r_offsets2.p : S->r_offsets.p;
+    pack_rows_kernel<<<(unsigned)std::min<int64_t>(nq, 148 * 16), 256, 0, st>>>(
+        nq, off, S->r_counts.p, off_out, ids, dist, ids_out, dist_out);
+    DRRT_LAUNCHED();
+  }
+  DRRT_CUDA(cudaGetLastError());
+  return DRRT_OK;
+}
+
 // Makes the last result a plain CSR (rows back to back in query order).
 int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out) {
   if (S->last_nq < 0) return set_error(DRRT_ERR_STATE, "pack: no range batch on this handle");
@@ -840,13 +858,7 @@ int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out) {
     DRRT_CHECK(S->r_offsets2.reserve(nq + 1, st));
     DRRT_CHECK(S->r_ids2.reserve(S->last_total + 1, st));
     DRRT_CHECK(S->r_dist2.reserve(S->last_total + 1, st));
-    scan_counts_kernel<<<1, 1024, 0, st>>>(S->r_counts.p, nq, S->r_offsets2.p);
-    DRRT_LAUNCHED();
-    pack_rows_kernel<<<(unsigned)std::min<int64_t>(nq, 148 * 16), 256, 0, st>>>(
-        nq, S->r_offsets.p, S->r_counts.p, S->r_offsets2.p, S->r_ids.p, S->r_dist.p, S->r_ids2.p,
-        S->r_dist2.p);
-    DRRT_LAUNCHED();
-    DRRT_CUDA(cudaGetLastError());
+    DRRT_CHECK(range_pack_to(S, st, S->r_offsets2.p, S->r_ids2.p, S->r_dist2.p));
     S->last_packed_in_alt = true;
   }
   fill_result(S, out);

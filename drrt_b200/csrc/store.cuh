@@ -75,6 +75,13 @@ struct Store {
   DevBuf<int32_t> r_ids2;
   DevBuf<double> r_dist2;
   DevBuf<double> q_stage, rad_stage;
+  // streamed host query (drrt_range_batch_into): the packed rows of a sub-batch, double
+  // buffered, leave on copy_stream while the next sub-batch is computed on stream
+  DevBuf<int64_t> p_off[2];
+  DevBuf<int32_t> p_ids[2];
+  DevBuf<double> p_dist[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   int32_t *d_ticket = nullptr;
   unsigned long long *d_totals = nullptr;  // inside the d_ticket allocation
   int64_t last_nq = -1, last_total = 0, last_extent = 0;
@@ -144,6 +151,9 @@ int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, DevBuf<int32_
 int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *radius_dev,
                     double radius_all, cudaStream_t st, drrt_range_result *out);
 int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out);
+// rows of the last result written back to back into caller-chosen device buffers
+// (off_out: nq + 1 exclusive prefix sums of the counts); the handle's result state is untouched
+int range_pack_to(Store *S, cudaStream_t st, int64_t *off_out, int32_t *ids_out, double *dist_out);
 // knn.cu
 int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
                   double *dist_dev, cudaStream_t st, bool nearest = false);

@@ -146,6 +146,40 @@ class KDTree:
         np.cumsum(counts, out=off[1:])
         return off, ids, dist
 
+    def KDFindWithinRangeInto(self, range_, query_points, offsets, ids, dist=None):
+        """The same query in one streamed call into caller buffers (numpy arrays or pinned
+        CPU torch tensors: offsets int64[nq+1], ids int32[cap], dist f64[cap] or None).
+        -> total hits.  Raises DrrtError(ERR_CAPACITY) when the rows do not fit; offsets
+        are complete then, so the retry can be sized."""
+        q = _f64(query_points, (-1, 3))
+        nq = q.shape[0]
+        rad = None
+        r_all = 0.0
+        if np.ndim(range_) == 0:
+            r_all = float(range_)
+        else:
+            rad = _f64(range_, (nq,))
+
+        def host_ptr(a, ty, np_dtype):
+            if a is None:
+                return None, 0
+            if isinstance(a, np.ndarray):
+                assert a.dtype == np_dtype and a.flags.c_contiguous
+                return _ptr(a, ty), a.size
+            assert not a.is_cuda and a.is_contiguous()
+            return C.cast(a.data_ptr(), ty), a.numel()
+
+        op, on = host_ptr(offsets, capi.c_i64p, np.int64)
+        ip, cap = host_ptr(ids, c_ip, np.int32)
+        dp, dn = host_ptr(dist, c_dp, np.float64)
+        assert on >= nq + 1 and (dist is None or dn >= cap)
+        total = C.c_int64()
+        with self._lock:
+            check(self._lib.drrt_range_batch_into(self._h, nq, _ptr(q, c_dp),
+                                                  _ptr(rad, c_dp) if rad is not None else None,
+                                                  r_all, cap, op, ip, dp, C.byref(total)))
+        return total.value
+
     # KDFindMoreWithinRange kdtree.cpp:822-851 is the same search; the caller's
     # list de-duplication (AddToRangeList :670-682) is the caller's to do.
     KDFindMoreWithinRange = KDFindWithinRange

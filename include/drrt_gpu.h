@@ -45,7 +45,8 @@ enum {
   DRRT_ERR_CUDA = 3,        /* a CUDA call failed; see drrt_last_error() */
   DRRT_ERR_NOMEM = 4,
   DRRT_ERR_NO_DEVICE = 5,
-  DRRT_ERR_STATE = 6        /* call order (e.g. fetch without a batch) */
+  DRRT_ERR_STATE = 6,       /* call order (e.g. fetch without a batch) */
+  DRRT_ERR_CAPACITY = 7     /* caller buffers too small; the sizes needed were returned */
 };
 
 /* the reference passes a host function pointer (include/DRRT/kdtree.h:21,47-49);
@@ -108,6 +109,23 @@ DRRT_API int drrt_range_batch(drrt_store *h, int64_t nq, const double *q,
                      const double *radius, double radius_all, int32_t *counts,
                      int64_t *total);
 DRRT_API int drrt_range_fetch(drrt_store *h, int32_t *ids, double *dist);
+
+/* The same query in ONE call, for a caller that can bound the result size
+ * (e.g. from the previous batch: the RRTx radius shrinks monotonically,
+ * src/drrt.cpp:16-27).  ids/dist hold cap elements (dist may be NULL);
+ * offsets[nq+1] receives the CSR row starts, *total the number of hits.
+ * The queries are answered in sub-batches on the handle's stream and the rows
+ * of a finished sub-batch leave for the host on a second stream while the next
+ * one is computed, so the PCIe transfer of the rows (12 B per hit) overlaps the
+ * kernel instead of following it.  If total > cap the call returns
+ * DRRT_ERR_CAPACITY: offsets and *total are complete, rows that did not fit
+ * whole are not copied, and a retry with cap >= *total succeeds.  Afterwards
+ * the handle holds no result (drrt_range_fetch / drrt_range_pack need a
+ * drrt_range_batch[_dev] first). */
+DRRT_API int drrt_range_batch_into(drrt_store *h, int64_t nq, const double *q,
+                          const double *radius, double radius_all, int64_t cap,
+                          int64_t *offsets, int32_t *ids, double *dist,
+                          int64_t *total);
 
 /* device-resident variant: queries/radii on the device; results stay in
  * library-owned device buffers valid until the next range call on h.

@@ -253,3 +253,59 @@ def test_range_slice_overflow_reruns_exact(drrt, po):
     off, cnt, ids, dist = _rows_dev(drrt, res)
     assert np.array_equal(off, roff) and np.array_equal(ids, rids) and np.array_equal(dist, rdist)
     _check(t, r, q, 3.0)
+
+
+def test_range_streamed_one_call(drrt, po):
+    """drrt_range_batch_into: the sub-batched, copy-overlapped host call returns exactly
+    the two-call result (several sub-batches, per-query radii, CTA mode), reports
+    DRRT_ERR_CAPACITY with complete offsets when the rows do not fit, and leaves no
+    fetchable result on the handle."""
+    from drrt_b200 import capi
+    pos = synth.box_points(200_000, 71)
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(40_000, 72)              # three sub-batches of 16384
+    rad = np.random.default_rng(73).uniform(0.2, 1.2, len(q))
+    for radius in (0.9, rad):
+        off, ids, dist = t.KDFindWithinRange(radius, q)
+        o2 = np.full(len(q) + 1, -1, dtype=np.int64)
+        i2 = np.empty(len(ids) + 7, dtype=np.int32)
+        d2 = np.empty(len(ids) + 7, dtype=np.float64)
+        total = t.KDFindWithinRangeInto(radius, q, o2, i2, d2)
+        assert total == len(ids)
+        assert np.array_equal(o2, off)
+        assert np.array_equal(i2[:total], ids) and np.array_equal(d2[:total], dist)
+    # rows either side of a sub-batch boundary against the oracle itself
+    sl = slice(16380, 16390)
+    roff, rids, rdist = r.range_batch(q[sl], 0.9)
+    i2 = np.empty(1_600_000, dtype=np.int32)
+    d2 = np.empty(1_600_000, dtype=np.float64)
+    total = t.KDFindWithinRangeInto(0.9, q, o2, i2, d2)
+    a, b = o2[sl.start], o2[sl.stop]
+    assert np.array_equal(o2[sl.start:sl.stop + 1] - a, roff)
+    assert np.array_equal(i2[a:b], rids) and np.array_equal(d2[a:b], rdist)
+    # CTA-per-query sub-batches, ids only, pinned torch buffers
+    import torch
+    qd = synth.box_points(30_000, 74)
+    off, ids, dist = t.KDFindWithinRange(4.0, qd)
+    o3 = torch.empty(len(qd) + 1, dtype=torch.int64).pin_memory()
+    i3 = torch.empty(len(ids), dtype=torch.int32).pin_memory()
+    assert t.KDFindWithinRangeInto(4.0, qd, o3, i3, None) == len(ids)
+    assert np.array_equal(o3.numpy(), off) and np.array_equal(i3.numpy(), ids)
+    # too small: error, offsets complete, a sized retry succeeds
+    small = np.empty(len(ids) * 6 // 10, dtype=np.int32)  # the first sub-batch fits, the second does not
+    o4 = np.empty(len(qd) + 1, dtype=np.int64)
+    with pytest.raises(drrt.capi.DrrtError) as ei:
+        t.KDFindWithinRangeInto(4.0, qd, o4, small, None)
+    assert ei.value.code == capi.ERR_CAPACITY
+    assert np.array_equal(o4, off)
+    cut = np.searchsorted(off, len(small), side="right") - 1  # rows of whole sub-batches that fit
+    assert cut >= 16384
+    full = off[16384]
+    assert np.array_equal(small[:full], ids[:full])
+    # nothing to fetch afterwards
+    lib = capi.load()
+    assert lib.drrt_range_fetch(t._h, None, None) == capi.ERR_STATE
+    # empty batch
+    o5 = np.full(1, -1, dtype=np.int64)
+    assert t.KDFindWithinRangeInto(1.0, np.empty((0, 3)), o5, np.empty(0, dtype=np.int32), None) == 0
+    assert o5[0] == 0
