@@ -310,62 +310,105 @@ __device__ __forceinline__ bool region_empty(const ObstacleGrid &G, double lox, 
   return true;
 }
 
+// Is the point (x, y) so close to an obstacle that any polyline segment ending in a point within
+// 1e-12 of it collides?  True when a polygon edge listed for the point's grid cell (every edge
+// within the robot radius of the cell is) lies closer than radius - 1e-9 and its obstacle's
+// radius_ covers its polygon, or the point is that deep inside a ball's reach.  Then
+//  * SegmentDistSqrd of the segment against that edge is 0 or at most the endpoint's own
+//    DistanceSqrdPointToSegment (distancefunctions.cpp:153-163), i.e. < radius^2 (:796-803), and
+//  * the segment passes the obstacle's bounding reject (obstacle.cpp:765-779): the endpoint is
+//    within radius - 1e-9 of a polygon point, which is within radius_ of origin_,
+// with nine orders of magnitude between the 1e-9 margin and the rounding of either test.
+template <bool MASKED>
+__device__ __forceinline__ bool point_surely_collides(const ObsView &O, const ObstacleGrid &G, double x,
+                                                      double y, double radius) {
+  const double rs = radius - 1e-9;
+  if (G.nx == 0 || !(rs > 0.0)) return false;
+  const double fx = floor((x - G.x0) * G.inv_cell), fy = floor((y - G.y0) * G.inv_cell);
+  if (!(fx >= 0.0 && fy >= 0.0 && fx <= (double)(G.nx - 1) && fy <= (double)(G.ny - 1))) return false;
+  const int c = (int)fx * G.ny + (int)fy;
+  const double rr = rs * rs;
+  for (int e = G.off[c]; e < G.off[c + 1]; e++) {
+    const int j = G.idx[e];
+    if (j >= G.n_edges) {  // ball: obstacle.cpp:781
+      const int b = G.ball[j - G.n_edges];
+      if (MASKED && !O.mask[b]) continue;
+      const double dx = x - O.ox[b], dy = y - O.oy[b], reach = rs + O.rad[b];
+      if (reach > 0.0 && dx * dx + dy * dy < reach * reach) return true;
+      continue;
+    }
+    const int o = G.eobs[j];
+    if (MASKED && !O.mask[o]) continue;
+    if (!O.covers[o]) continue;
+    double ax, ay, bx, by;
+    load_edge(G, j, ax, ay, bx, by);
+    if (dist_sqrd_point_segment(x, y, ax, ay, bx, by) < rr) return true;
+  }
+  return false;
+}
+
 // Decides what it can about a solved path and hands the rest to the walk kernel.  All 32 lanes
-// of a warp call it together (`valid`: the lane has an edge).
+// of a warp call it together (`valid`: the lane has an edge from (sx, sy) to (ex, ey)).
 //  * parts whose whole circle (or straight piece) lies where no obstacle comes within the robot
 //    radius need no per-segment test; a path made only of such parts is free;
-//  * the verdict is an OR over the polyline's segments, so their order is free: the FIRST and the
-//    LAST segment are tested right here, where every lane has an edge, with the warp-cooperative
-//    test of the walk (the reference's own segment test on the reference's own two points, only
-//    earlier).  The planner's nodes are not filtered against the obstacles (the range query
-//    returns what the tree holds), so the usual colliding edge has an end pose within the robot
-//    radius of an obstacle boundary: in config 3 ~95 % of the colliding edges are decided by
-//    these two segments, and an edge whose START is clear would otherwise be walked to its very
-//    last segment before the hit shows;
+//  * every path starts in the start pose and ends in the end pose (to the rounding of one
+//    atan2 + sincos, ~1e-14), and the verdict is an OR over its segments: a pose that
+//    point_surely_collides decides the edge without walking it.  The planner's nodes are not
+//    filtered against the obstacles (the range query returns what the tree holds), so the usual
+//    colliding edge is of this kind -- in config 3 ~95 % of them -- and one whose START is
+//    clear would otherwise be walked to its very last segment before the hit shows;
 //  * an undecided edge gets the next slot of the compact work list (its record carries the edge
 //    id in place of dist_, which the walk does not read), so the walk kernel neither loads nor
 //    spends a trip on the decided ones.
 // work[0] = walk claim counter, work[1] = number of records listed.
 template <bool MASKED>
 __device__ __forceinline__ void finish_path_impl(const EdgeArgs &A, bool valid, int64_t e, DubinsPath &P,
-                                                 DubinsPath *paths, unsigned long long *work,
-                                                 WarpScratch *ws) {
+                                                 double sx, double sy, double ex, double ey,
+                                                 DubinsPath *paths, unsigned long long *work) {
   const int lane = threadIdx.x & 31;
   if (valid && A.length) A.length[e] = P.dist;
   if (A.obs.n == 0) return;    // nothing to collide with: the host clears the verdicts
   int decided = valid ? -1 : 0;  // 0 free, 1 collides (a lane without an edge has nothing to decide)
   if (valid) {
-    if (A.grid.nx > 0) {
-      int idle = 0, parts = 0;
+    if ((P.kinds & 63) == 0) {
+      decided = 0;  // no path: dubinsedge.cpp:897 falls through to false
+    } else if (A.grid.nx > 0) {
+      int idle = 0, parts = 0, last = 0;
       const double rr = fabs(A.r_min) * (1.0 + 1e-9) + 1e-9;
       for (int k = 0; k < 3; k++) {
         int kind = P.kind(k);
         if (kind == PART_NONE) continue;
         parts++;
+        last = k;
         const DubinsPart &p = P.part[k];
         bool empty = (kind == PART_LINE)
                          ? region_empty(A.grid, fmin(p.cx, p.a), fmin(p.cy, p.b), fmax(p.cx, p.a), fmax(p.cy, p.b))
                          : region_empty(A.grid, p.cx - rr, p.cy - rr, p.cx + rr, p.cy + rr);
         if (empty) { idle++; P.kinds |= 1 << (8 + k); }
       }
-      if (idle == parts) decided = 0;
-    } else if ((P.kinds & 63) == 0) {
-      decided = 0;  // no path (dubinsedge.cpp:897 falls through to false)
+      if (idle == parts) {
+        decided = 0;
+      } else if (point_surely_collides<MASKED>(A.obs, A.grid, sx, sy, A.robot_radius)) {
+        decided = 1;
+      } else {
+        // the last arc ends in phi_end (the end pose) unless |dphi| / 0.1 sits on an integer, where
+        // the reference's loop may leave the last entry Zero() (PolylineWalker::next)
+        bool ends_in_pose = true;
+        const int kind = P.kind(last);
+        if (kind != PART_LINE) {
+          const DubinsPart &p = P.part[last];
+          double pe = p.b;
+          if (kind == PART_ARC_R) { if (pe > p.a) pe -= 2.0 * DRRT_PI; }
+          else { if (pe < p.a) pe += 2.0 * DRRT_PI; }
+          if (pe != p.a) {
+            const double steps = fabs(pe - p.a) / 0.1, frac = steps - floor(steps);
+            ends_in_pose = frac > 1e-9 && frac < 1.0 - 1e-9;
+          }
+        }
+        if (ends_in_pose && point_surely_collides<MASKED>(A.obs, A.grid, ex, ey, A.robot_radius)) decided = 1;
+      }
     }
   }
-  PolylineWalker W;
-  double x0 = 0.0, y0 = 0.0, x1 = 0.0, y1 = 0.0;
-  bool test = false;
-  if (decided < 0) {
-    W.start(&P, A.r_min, false);
-    test = W.next(&x0, &y0) && W.next(&x1, &y1);
-  }
-  if (warp_segments_vs_obstacles<MASKED>(A.obs, A.grid, test, x0, y0, x1, y1, A.robot_radius, ws, lane))
-    decided = 1;
-  test = false;
-  if (decided < 0) test = W.last_segment(&P, A.r_min, &x0, &y0, &x1, &y1);
-  if (warp_segments_vs_obstacles<MASKED>(A.obs, A.grid, test, x0, y0, x1, y1, A.robot_radius, ws, lane))
-    decided = 1;
   if (valid && decided >= 0) A.verdict[e] = (uint8_t)decided;
   // warp-aggregated append of the undecided edges
   const unsigned m = __ballot_sync(0xffffffffu, decided < 0);
@@ -380,28 +423,28 @@ __device__ __forceinline__ void finish_path_impl(const EdgeArgs &A, bool valid, 
 }
 
 __device__ __forceinline__ void finish_path(const EdgeArgs &A, bool valid, int64_t e, DubinsPath &P,
-                                            DubinsPath *paths, unsigned long long *work, WarpScratch *ws) {
-  if (A.obs.mask) finish_path_impl<true>(A, valid, e, P, paths, work, ws);
-  else finish_path_impl<false>(A, valid, e, P, paths, work, ws);
+                                            double sx, double sy, double ex, double ey,
+                                            DubinsPath *paths, unsigned long long *work) {
+  if (A.obs.mask) finish_path_impl<true>(A, valid, e, P, sx, sy, ex, ey, paths, work);
+  else finish_path_impl<false>(A, valid, e, P, sx, sy, ex, ey, paths, work);
 }
 
 // K4a: Edge::NewEdge + the candidate solve of CalculateTrajectory, one thread per edge, all
 // six candidates in double (small batches; the ranked pipeline below is the fast path)
 __global__ void __launch_bounds__(EDGE_T)
 dubins_solve_kernel(EdgeArgs A, DubinsPath *paths, unsigned long long *work) {
-  __shared__ WarpScratch s_ws[EDGE_T / 32];
   const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
   const bool valid = e < A.n;
   DubinsPath P;
   P.kinds = 0;
+  double sx = 0, sy = 0, st = 0, ex = 0, ey = 0, et = 0;
   if (valid) {
-    double sx, sy, st, ex, ey, et;
     load_pose(A, e, false, sx, sy, st);
     load_pose(A, e, true, ex, ey, et);
     double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
     dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
   }
-  finish_path(A, valid, e, P, paths, work, &s_ws[threadIdx.x >> 5]);
+  finish_path(A, valid, e, P, sx, sy, ex, ey, paths, work);
 }
 
 // K4a, ranked: the double-precision solve of all six Dubins words costs ~5800 instructions per
@@ -472,9 +515,8 @@ template <int MASK>
 __global__ void __launch_bounds__(EDGE_T)
 dubins_solve_bin_kernel(EdgeArgs A, DubinsPath *paths, const uint32_t *perm, const uint8_t *masks,
                         const unsigned long long *bin_state, int bin, unsigned long long *work) {
-  __shared__ WarpScratch s_ws[EDGE_T / 32];
   const unsigned long long lo = bin_state[8 + bin], hi = bin_state[8 + bin + 1];
-  // whole warps stay in the loop (finish_path is warp-cooperative)
+  // whole warps stay in the loop (finish_path appends with a warp-wide ballot)
   for (unsigned long long w0 = lo + (unsigned long long)blockIdx.x * EDGE_T + (threadIdx.x & ~31u); w0 < hi;
        w0 += (unsigned long long)gridDim.x * EDGE_T) {
     const unsigned long long i = w0 + (threadIdx.x & 31u);
@@ -482,15 +524,15 @@ dubins_solve_bin_kernel(EdgeArgs A, DubinsPath *paths, const uint32_t *perm, con
     int64_t e = 0;
     DubinsPath P;
     P.kinds = 0;
+    double sx = 0, sy = 0, st = 0, ex = 0, ey = 0, et = 0;
     if (valid) {
       e = perm[i];
-      double sx, sy, st, ex, ey, et;
       load_pose(A, e, false, sx, sy, st);
       load_pose(A, e, true, ex, ey, et);
       double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
       dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P, MASK ? MASK : (int)masks[e]);
     }
-    finish_path(A, valid, e, P, paths, work, &s_ws[threadIdx.x >> 5]);
+    finish_path(A, valid, e, P, sx, sy, ex, ey, paths, work);
   }
 }
 

@@ -515,33 +515,6 @@ struct PolylineWalker {
     path = p; r_min = r; part = 0; i = 0; n = 0; kind = PART_NONE; fresh = true; skip_idle = skip;
     begin_part();
   }
-  // The LAST segment of the polyline (the final two points of its last part) without walking
-  // the path: the angle recurrence of the last arc runs without sin/cos up to its last two
-  // entries, which next() then emits.  false when there is no such segment (empty path, or a
-  // last part of a single point).  Leaves the walker at the end of the path.
-  __device__ __forceinline__ bool last_segment(const DubinsPath *p, double r, double *x0, double *y0,
-                                               double *x1, double *y1) {
-    int kl = -1;
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-      if (p->kind(k) != PART_NONE) kl = k;
-    if (kl < 0) return false;
-    path = p; r_min = r; part = kl; i = 0; n = 0; kind = PART_NONE; fresh = true; skip_idle = false;
-    begin_part();
-    if (part != kl || n < 2) return false;
-    if (kind != PART_LINE) {
-      if (equal) return false;
-      for (; i < n - 2; i++) {
-        if (ended) continue;
-        bool in = (kind == PART_ARC_R) ? (val >= phi_end) : (val <= phi_end);
-        if (in) { if (kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
-        else ended = true;
-      }
-    }
-    next(x0, y0);
-    next(x1, y1);
-    return true;
-  }
   __device__ __forceinline__ bool done() const { return part >= 3; }
   // *connects: the segment from the previous point to this one is part of the polyline to test
   __device__ __forceinline__ bool next(double *x, double *y, bool *connects = nullptr) {
