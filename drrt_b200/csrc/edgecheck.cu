@@ -196,7 +196,8 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
   for (int k = 0; k < 4; k++) {
     st[k] = 0; ln[k] = 0;
     if (!wide && k < ncells) {
-      int c = (cx0 + k / ncy) * G.ny + (cy0 + k % ncy);
+      const int kx = (k >= ncy) + (k >= 2 * ncy) + (k >= 3 * ncy);  // k / ncy for k < 4
+      int c = (cx0 + kx) * G.ny + (cy0 + k - kx * ncy);
       st[k] = G.off[c];
       ln[k] = G.off[c + 1] - st[k];
     }
@@ -206,8 +207,8 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
   if (!__any_sync(0xffffffffu, total > 0 || wide)) return false;
 #pragma unroll
   for (int k = 0; k < 4; k++) { ws->start[lane][k] = st[k]; ws->len[lane][k] = ln[k]; }
-  double dx = p1x - p0x, dy = p1y - p0y;
-  double far = (radius + sqrt(dx * dx + dy * dy)) * (1.0 + 1e-9) + 1e-9;
+  // cull distance: radius + an upper bound of the segment's length (|dx| + |dy|, no sqrt)
+  double far = (radius + (fabs(p1x - p0x) + fabs(p1y - p0y))) * (1.0 + 1e-9) + 1e-9;
   ws->seg[lane][0] = p0x; ws->seg[lane][1] = p0y; ws->seg[lane][2] = p1x; ws->seg[lane][3] = p1y;
   ws->seg[lane][4] = far * far;
   int inc = total;
@@ -418,6 +419,7 @@ __device__ __forceinline__ void finish_path_impl(const EdgeArgs &A, bool valid, 
     if (lane == leader) base = atomicAdd(&work[1], (unsigned long long)__popc(m));
     base = __shfl_sync(m, base, leader);
     P.dist = __longlong_as_double((long long)e);
+    PolylineWalker::prepare(P);
     paths[base + __popc(m & ((1u << lane) - 1u))] = P;
   }
 }
@@ -568,7 +570,7 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
       e = en;
       en = -1;
       cur ^= 1;
-      W.start(&s_path[cur][threadIdx.x], A.r_min, true);
+      W.start(&s_path[cur][threadIdx.x], A.r_min, true, true);
       have_prev = false;
     }
     // lanes without a next edge take one from the warp's reserve of claimed edges and start its

@@ -487,6 +487,31 @@ struct PolylineWalker {
   double val, phi_end;
   bool ended, equal;
   bool skip_idle;  // fast-forward parts flagged idle to their last point
+  bool prepared;   // the record went through prepare(): end angles adjusted, entry counts in `type`
+
+  // end angle after the +-2pi adjustment and number of entries of an arc (:484-502 and siblings)
+  __device__ __forceinline__ static void arc_extent(int kind, double a, double &pe, int &n) {
+    if (kind == PART_ARC_R) { if (pe > a) pe -= 2.0 * DRRT_PI; }
+    else { if (pe < a) pe += 2.0 * DRRT_PI; }
+    n = (int)(ceil(fabs(pe - a) / 0.1) + 1);
+    if (n > DRRT_TRAJ_MAX) n = DRRT_TRAJ_MAX;
+  }
+  // Does begin_part's arithmetic once, where every lane has a path (the solve kernels), instead of
+  // in the walk, where a lane entering a new part runs it alone: every arc's `b` becomes its
+  // adjusted end angle and `type` (which the walk does not read) its entry counts, 8 bits a part.
+  __device__ __forceinline__ static void prepare(DubinsPath &P) {
+    int packed = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int kind = P.kind(k);
+      if (kind == PART_ARC_R || kind == PART_ARC_L) {
+        int cnt;
+        arc_extent(kind, P.part[k].a, P.part[k].b, cnt);
+        packed |= cnt << (8 * k);
+      }
+    }
+    P.type = packed;
+  }
   bool fresh;      // the next point does not continue a tested polyline segment
 
   __device__ __forceinline__ void begin_part() {
@@ -497,11 +522,12 @@ struct PolylineWalker {
         cx = P.cx; cy = P.cy; a = P.a; b = P.b;
         if (kind == PART_LINE) { n = 2; i = 0; return; }
         double pe = b;
-        if (kind == PART_ARC_R) { if (pe > a) pe -= 2.0 * DRRT_PI; }
-        else { if (pe < a) pe += 2.0 * DRRT_PI; }
+        if (prepared) {
+          n = (path->type >> (8 * part)) & 0xff;
+        } else {
+          arc_extent(kind, a, pe, n);
+        }
         phi_end = pe;
-        n = (int)(ceil(fabs(pe - a) / 0.1) + 1);
-        if (n > DRRT_TRAJ_MAX) n = DRRT_TRAJ_MAX;
         equal = (pe == a);
         val = a;
         ended = false;
@@ -511,8 +537,9 @@ struct PolylineWalker {
       part++;
     }
   }
-  __device__ __forceinline__ void start(const DubinsPath *p, double r, bool skip = false) {
+  __device__ __forceinline__ void start(const DubinsPath *p, double r, bool skip = false, bool prep = false) {
     path = p; r_min = r; part = 0; i = 0; n = 0; kind = PART_NONE; fresh = true; skip_idle = skip;
+    prepared = prep;
     begin_part();
   }
   __device__ __forceinline__ bool done() const { return part >= 3; }
