@@ -201,3 +201,64 @@ def test_long_straight_edges(drrt, po):
     e[:10_000] = s[:10_000] + rng.normal(0, 0.01, (10_000, 3))   # very short ones too
     e[10_000:10_050] = s[10_000:10_050]                          # zero length
     _compare(t, ro, s, e, kind=1)
+
+
+def test_dubins_edges_poses_at_the_robot_radius(drrt, po):
+    """The early decision of the solve kernels (a pose closer than radius - 1e-9 to a listed polygon
+    edge decides the edge, edgecheck.cu point_surely_collides): start / end poses placed at
+    radius + {0, +-1e-12 ... +-0.2} from polygon edges and vertices -- for polygons whose radius_
+    covers them, polygons whose radius_ does not (the bounding reject of obstacle.cpp:765-779 can
+    then veto a near edge) and kind-1 balls.  Verdicts may differ from the oracle's only inside the
+    1e-6 band; both the ranked pipeline and the small-batch kernel are exercised."""
+    o = synth.obstacles(48, 91)
+    o["radius"][::3] *= 0.5
+    o["kind"][::5] = 1
+    t, ro = _obs(drrt, po, o)
+    rng = np.random.default_rng(92)
+    verts, voff = o["verts"], o["vert_off"]
+    offs = np.array([0.0, 1e-12, -1e-12, 1e-10, -1e-10, 1e-8, -1e-8, 2e-6, -2e-6, 1e-3, -1e-3, 0.2, -0.2])
+    pts, out = [], []   # points at the radius and the direction pointing away from the boundary there
+    for i in range(len(voff) - 1):
+        P = verts[voff[i]:voff[i + 1]]
+        for k in range(len(P)):
+            a, b = P[k - 1], P[k]
+            d = b - a
+            nrm = np.array([d[1], -d[0]]) / np.hypot(d[0], d[1])
+            for tpar in (0.0, 0.3, 1.0):
+                for off in offs:
+                    for sgn in (1.0, -1.0):
+                        pts.append(a + tpar * d + sgn * (0.5 + off) * nrm)
+                        out.append(sgn * nrm)
+    for i in range(0, len(voff) - 1, 5):   # the balls: reach = robot radius + radius_
+        for off in offs:
+            ang = rng.uniform(0, 2 * np.pi)
+            u = np.array([np.cos(ang), np.sin(ang)])
+            pts.append(o["origin"][i] + (0.5 + o["radius"][i] + off) * u)
+            out.append(u)
+    pts, out = np.array(pts), np.array(out)
+    n = len(pts)
+    # (a) random headings, partner pose nearby: mostly loops that collide somewhere
+    near = np.concatenate([pts, rng.uniform(0, synth.TWO_PI, (n, 1))], 1)
+    other = near.copy()
+    other[:, :2] += rng.uniform(-0.45, 0.45, (n, 2))
+    other[:, 2] = rng.uniform(0, synth.TWO_PI, n)
+    # (b) straight runs away from / towards the boundary: the pose at the radius is the only
+    # part of the path that can touch it, so the verdict hangs on that pose alone
+    ang = np.mod(np.arctan2(out[:, 1], out[:, 0]), synth.TWO_PI)
+    far = pts + out * rng.uniform(0.1, 0.6, (n, 1))
+    away_s = np.concatenate([pts, ang[:, None]], 1)
+    away_e = np.concatenate([far, ang[:, None]], 1)
+    back = np.mod(ang + np.pi, synth.TWO_PI)
+    to_s = np.concatenate([far, back[:, None]], 1)
+    to_e = np.concatenate([pts, back[:, None]], 1)
+    s = np.concatenate([near, other, away_s, to_s])
+    e = np.concatenate([other, near, away_e, to_e])
+    assert len(s) > 16384
+    rv, rln, clr = ro.edge_check_batch(s, e, want_clearance=True)
+    for lo, hi in ((0, len(s)), (0, 6000)):
+        v, ln = t.ExplicitEdgeCheck(s[lo:hi], e[lo:hi])
+        diff = lo + np.nonzero(v != rv[lo:hi])[0]
+        assert (clr[diff] < BAND).all(), "verdicts differ outside the 1e-6 band: %s" % diff[:10]
+    assert 0.2 < rv.mean() < 0.9 and 0.1 < rv[2 * n:].mean() < 0.8
+    # poses a full 2e-6 or more outside every boundary are never decided by the shortcut alone:
+    # whatever the device answers for them already matched the oracle's walk above
