@@ -108,13 +108,93 @@ def cpu_range_baseline(radius, nthreads, budget_s=20.0):
                   "hits_per_query": float(counts.mean())}
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "drrt_ref")
+
+
+def reference_binary_rate(radius, q_per_proc, warm, timed, procs=None):
+    """Times the REFERENCE'S OWN kdtree.cpp / ghostpoint.cpp / jlist.cpp (oracle/_ref/drrt_ref, built
+    by `make -C oracle ref` from the unmodified sources under /root/reference): one KDFindWithinRange
+    + EmptyRangeList per query.  The reference serialises every tree call under tree_mutex_ and marks
+    found nodes in_heap_, so one tree serves one thread: to use all host cores, one process per core
+    builds its own 1 M-node tree (~1.4 GB, ~5 s) and answers its own slice of the queries; the rates
+    of the concurrently running processes are added.  None when the binary is absent."""
+    if not os.path.exists(REF_BIN):
+        return None
+    import struct
+    import tempfile
+    import numpy as np
+    from drrt_b200 import synth
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = procs or cores
+    try:
+        import psutil
+        procs = max(1, min(procs, int(psutil.virtual_memory().available // (2 << 30))))
+    except Exception:
+        pass
+    pos = synth.nodes(N_NODES)
+    q = synth.queries(N_QUERIES)
+    q_per_proc = max(1, min(q_per_proc, N_QUERIES // procs))
+    with tempfile.TemporaryDirectory() as tmp:
+        jobs = []
+        for p in range(procs):
+            qs = np.ascontiguousarray(q[p * q_per_proc:(p + 1) * q_per_proc])
+            fin, fout = os.path.join(tmp, "in%d.bin" % p), os.path.join(tmp, "out%d.bin" % p)
+            with open(fin, "wb") as f:
+                f.write(struct.pack("<iiqq", 0, 1, N_NODES, len(qs)))   # R2S1 metric, theta wraps
+                f.write(pos.tobytes())
+                f.write(qs.tobytes())
+                f.write(np.full(len(qs), radius).tobytes())
+                f.write(struct.pack("<ii", warm, timed))
+            jobs.append((fout, len(qs)))
+        t0 = time.perf_counter()
+        running = [subprocess.Popen([REF_BIN, "range_time", os.path.join(tmp, "in%d.bin" % p), jobs[p][0]],
+                                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                   for p in range(procs)]
+        rcs = [r.wait() for r in running]
+        wall = time.perf_counter() - t0
+        if any(rcs):
+            return None
+        rate, hits, nq, longest = 0.0, 0, 0, 0.0
+        for fout, n in jobs:
+            h, secs = struct.unpack("<qd", open(fout, "rb").read(16))
+            rate += n * timed / secs
+            hits += h
+            nq += n
+            longest = max(longest, secs)
+    return {"value": rate, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": "%d processes x %d config-2a queries x %d timed passes (+%d warm-up), each process the "
+                      "reference's own KDFindWithinRange + EmptyRangeList on its own 1 M-node KDTree "
+                      "(oracle/_ref/drrt_ref: kdtree.cpp, ghostpoint.cpp, jlist.cpp unmodified, Eigen "
+                      "stand-in); slowest process %.1f s of queries, %.1f s wall with the tree builds"
+                      % (procs, q_per_proc, timed, warm, longest, wall),
+            "hits_per_query": hits / max(nq, 1), "queries_per_pass": nq,
+            "ms_per_pass": 1e3 * longest / max(timed, 1)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyoracle as po
     from drrt_b200 import synth
     radius = synth.shrinking_radius(N_NODES, synth.GAMMA_REF)
+    total_steps = max(1, args.steps + args.warmup)
+    # (a) the reference's own compiled sources, when they were built (oracle/_ref travels with the
+    # repo); ~0.36 s per query and process: size the per-step sample for ~100 s of queries
+    per_proc = int(max(2, min(64, 100.0 / (0.4 * total_steps))))
+    ref = reference_binary_rate(radius, per_proc, args.warmup, max(1, args.steps))
+    if ref is not None:
+        line = {"impl": "reference", "metric": METRIC, "value": ref["value"], "unit": UNIT,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ref["ms_per_pass"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "config2a range-ball: 1M nodes, r=%.6f (gamma=100), %d-query sample "
+                                       "per step" % (radius, ref["queries_per_pass"])},
+                "cpu_baseline": {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample", "hits_per_query")},
+                "e2e": {"value": ref["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+    # (b) the oracle port (plain-C restatement, bit-identical results), all host threads
+    from oracle import pyoracle as po
     threads = po.num_threads()
     tree = po.RefTree()
     tree.insert(synth.nodes(N_NODES))
@@ -123,7 +203,6 @@ def run_reference(args):
     t0 = time.perf_counter()
     tree.range_counts(q[:256], radius)
     per_q = (time.perf_counter() - t0) / 256
-    total_steps = args.steps + args.warmup
     sample = int(min(N_QUERIES, max(256, 120.0 / max(per_q * total_steps, 1e-9))))
     sample = max(256, (sample // 256) * 256)
     for _ in range(args.warmup):
@@ -382,6 +461,13 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         _, cpu = cpu_range_baseline(r2a, 0)
+        if N_NODES == 1_000_000:
+            # beside the port: the reference's own compiled sources on the same queries (what
+            # `--impl reference` times at length), a short sample
+            refbin = reference_binary_rate(r2a, 8, 0, 1)
+            if refbin is not None:
+                cpu["reference_binary"] = {k: refbin[k] for k in ("value", "unit", "cores", "kind", "sample",
+                                                                  "hits_per_query")}
         if "dubins_edge_check" in extra:
             # the oracle's CalculateTrajectory + ExplicitEdgeCheck on a bounded sample of config-3 edges
             from oracle import pyoracle as po

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -143,6 +144,29 @@ static int cmd_tree(const char *cmd, Reader &in, Writer &out) {
     }
     out.put<int64_t>((int64_t)ids.size());
     out.arr(counts); out.arr(ids); out.arr(dist);
+    return 0;
+  }
+  if (!strcmp(cmd, "range_time")) {
+    // bench.py --impl reference: the reference's own KDFindWithinRange on its own tree, one call
+    // per query followed by the caller's EmptyRangeList (drrt.cpp:233, 356), timed as a whole;
+    // `warm` untimed passes over the queries, then `timed` timed ones
+    int warm = in.get<int32_t>(), timed = in.get<int32_t>();
+    int64_t hits = 0;
+    double secs = 0.0;
+    for (int rep = 0; rep < warm + timed; rep++) {
+      struct timespec t0, t1;
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      for (int64_t i = 0; i < nq; i++) {
+        shared_ptr<JList> S = make_shared<JList>(true);
+        T->KDFindWithinRange(S, rad[i], vec3(&q[3 * i]));  // kdtree.cpp:794-820
+        if (rep == warm) hits += S->length_;
+        T->EmptyRangeList(S);                              // kdtree.cpp:692-701
+      }
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if (rep >= warm) secs += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    }
+    out.put<int64_t>(hits);
+    out.put<double>(secs);
     return 0;
   }
   if (!strcmp(cmd, "nearest")) {
@@ -374,7 +398,8 @@ int main(int argc, char **argv) {
   Reader in(argv[2]);
   Writer out(argv[3]);
   const char *cmd = argv[1];
-  if (!strcmp(cmd, "range") || !strcmp(cmd, "nearest") || !strcmp(cmd, "structure") || !strcmp(cmd, "ghosts"))
+  if (!strcmp(cmd, "range") || !strcmp(cmd, "range_time") || !strcmp(cmd, "nearest") || !strcmp(cmd, "structure") ||
+      !strcmp(cmd, "ghosts"))
     return cmd_tree(cmd, in, out);
   if (!strcmp(cmd, "traj") || !strcmp(cmd, "edgecheck") || !strcmp(cmd, "edgecheck_gpu"))
     return cmd_edges(cmd, in, out);
