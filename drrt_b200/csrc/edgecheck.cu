@@ -26,7 +26,8 @@
 // under radius^2 for that segment.  A listed edge farther from the segment's
 // first point than (radius + segment length) is skipped; the rest get the
 // reference's SegmentDistSqrd and, on a hit, its obstacle's bounding reject
-// (:765-779) verbatim -- the verdict is the same OR over obstacles.  The obstacle table is staged in shared memory when it fits.
+// (:765-779) verbatim -- the verdict is the same OR over obstacles.  The grid entries are 32-byte records read with one
+// 256-bit ld.global.nc each (L1/L2 resident); staging the table in shared memory measured slower.
 #include <math.h>
 
 #include <algorithm>
