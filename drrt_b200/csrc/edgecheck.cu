@@ -13,12 +13,12 @@
 // kind 3 (polygon) that are used and alive can ever report a hit
 // (:761, :781-804); the host packs those into the "active" table.
 //
-// Dubins edges take two kernels.  dubins_solve_kernel (one thread per edge,
-// uniform work) solves the six candidates and leaves a 112-byte path record.
-// dubins_walk_kernel is persistent: every lane walks one edge's 0.1-rad polyline
-// a segment per iteration and, when its edge is decided (first hit, or end of
-// path), takes the next unclaimed edge, so lanes of a warp stay busy although
-// polylines have 3..191 segments and three quarters of them end early on a hit.
+// Dubins edges take two stages.  The solve kernels (one thread per edge; ranked and binned by
+// Dubins word for large batches) find the path, decide the edges a pose of which surely collides
+// (finish_path) and append a 112-byte path record of every undecided edge to a work list.
+// dubins_walk_kernel is persistent: every lane walks one listed edge's 0.1-rad polyline a segment
+// per iteration and, when its edge is decided (first hit, or end of path), takes the next
+// unclaimed record, so lanes of a warp stay busy although polylines have 3..191 segments.
 // Straight (LineCheck) edges have 50 segments each and use one kernel.
 // Each segment looks up the cells of a uniform grid its bounding box touches; a
 // cell lists the polygon EDGES (and kind-1 balls) that come within the robot
