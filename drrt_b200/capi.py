@@ -110,7 +110,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.drrt_abi_version() != 2:
+        if lib.drrt_abi_version() != 3:
             raise ImportError("drrt_b200: ABI version mismatch")
         _lib = lib
     return _lib

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DRRT_ABI_VERSION 2
+#define DRRT_ABI_VERSION 3 /* 3: drrt_range_batch_into, DRRT_ERR_CAPACITY */
 
 #if defined(__GNUC__)
 #define DRRT_API __attribute__((visibility("default")))
