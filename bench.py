@@ -171,6 +171,58 @@ def reference_binary_rate(radius, q_per_proc, warm, timed, procs=None):
             "ms_per_pass": 1e3 * longest / max(timed, 1)}
 
 
+def reference_binary_edge_rate(s_h, e_h, obstacles, per_proc, procs=None):
+    """The reference's own Edge::NewEdge + DubinsEdge::CalculateTrajectory + analytic ExplicitEdgeCheck per
+    edge (oracle/_ref/drrt_ref edgecheck_time: dubinsedge.cpp, obstacle.cpp, distancefunctions.cpp
+    unmodified), one process per core on its own slice of the edges.  None when the binary is absent."""
+    if not os.path.exists(REF_BIN):
+        return None
+    import struct
+    import tempfile
+    import numpy as np
+    from drrt_b200 import synth
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = procs or cores
+    per_proc = max(1, min(per_proc, len(s_h) // procs))
+    o = obstacles
+    head = struct.pack("<idd", 0, synth.R_MIN, synth.ROBOT_RADIUS)
+    head += struct.pack("<i", len(o["kind"]))
+    head += np.ascontiguousarray(o["kind"], dtype=np.int32).tobytes()
+    head += np.ascontiguousarray(o["used"], dtype=np.uint8).tobytes()
+    head += np.ascontiguousarray(o["life_span"], dtype=np.float64).tobytes()
+    head += np.ascontiguousarray(o["origin"], dtype=np.float64).tobytes()
+    head += np.ascontiguousarray(o["radius"], dtype=np.float64).tobytes()
+    head += np.ascontiguousarray(o["vert_off"], dtype=np.int32).tobytes()
+    head += np.ascontiguousarray(o["verts"], dtype=np.float64).tobytes()
+    with tempfile.TemporaryDirectory() as tmp:
+        outs = []
+        for p in range(procs):
+            lo, hi = p * per_proc, (p + 1) * per_proc
+            fin, fout = os.path.join(tmp, "in%d.bin" % p), os.path.join(tmp, "out%d.bin" % p)
+            with open(fin, "wb") as f:
+                f.write(head)
+                f.write(struct.pack("<q", hi - lo))
+                f.write(np.ascontiguousarray(s_h[lo:hi]).tobytes())
+                f.write(np.ascontiguousarray(e_h[lo:hi]).tobytes())
+            outs.append(fout)
+        running = [subprocess.Popen([REF_BIN, "edgecheck_time", os.path.join(tmp, "in%d.bin" % p), outs[p]],
+                                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                   for p in range(procs)]
+        if any(r.wait() for r in running):
+            return None
+        rate, hits, longest = 0.0, 0, 0.0
+        for fout in outs:
+            h, secs = struct.unpack("<qd", open(fout, "rb").read(16))
+            rate += per_proc / secs
+            hits += h
+            longest = max(longest, secs)
+    return {"value": rate, "unit": "edges/s", "cores": procs, "kind": "reference",
+            "sample": "%d processes x %d config-3 edges, the reference's own NewEdge + CalculateTrajectory + "
+                      "ExplicitEdgeCheck2D loop per edge (oracle/_ref/drrt_ref, Eigen stand-in), slowest process "
+                      "%.1f s" % (procs, per_proc, longest),
+            "collision_rate": hits / float(procs * per_proc)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -481,6 +533,9 @@ def main():
                 "value": len(s_h) / dt, "unit": "edges/s", "cores": po.num_threads(), "kind": "port",
                 "sample": "%d config-3 edges, oracle Dubins solve + polyline + ExplicitEdgeCheck2D with "
                           "first-hit exit, %.1f s" % (len(s_h), dt)}
+            refbin = reference_binary_edge_rate(s_h, e_h, synth.obstacles(), 2000)
+            if refbin is not None:
+                extra["dubins_edge_check"]["cpu_baseline"]["reference_binary"] = refbin
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,

@@ -268,6 +268,8 @@ static int cmd_edges(const char *cmd, Reader &in, Writer &out) {
   std::vector<int32_t> npts(n);
   std::vector<uint8_t> verdict(n, 0);
   bool want_traj = !strcmp(cmd, "traj");
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   for (int64_t i = 0; i < n; i++) {
     shared_ptr<KDTreeNode> a = make_shared<KDTreeNode>(vec3(&s[3 * i]));
     shared_ptr<KDTreeNode> b = make_shared<KDTreeNode>(vec3(&e[3 * i]));
@@ -302,6 +304,15 @@ static int cmd_edges(const char *cmd, Reader &in, Writer &out) {
       dist[i] = edge->dist_;
     }
 #endif
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (!strcmp(cmd, "edgecheck_time")) {
+    // bench.py: NewEdge + CalculateTrajectory + the analytic edge check per edge, timed as a whole
+    int64_t hits = 0;
+    for (int64_t i = 0; i < n; i++) hits += verdict[i];
+    out.put<int64_t>(hits);
+    out.put<double>((double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+    return 0;
   }
   out.arr(types); out.arr(dist); out.arr(npts); out.arr(verdict);
   if (want_traj) out.arr(xy);
@@ -401,7 +412,7 @@ int main(int argc, char **argv) {
   if (!strcmp(cmd, "range") || !strcmp(cmd, "range_time") || !strcmp(cmd, "nearest") || !strcmp(cmd, "structure") ||
       !strcmp(cmd, "ghosts"))
     return cmd_tree(cmd, in, out);
-  if (!strcmp(cmd, "traj") || !strcmp(cmd, "edgecheck") || !strcmp(cmd, "edgecheck_gpu"))
+  if (!strcmp(cmd, "traj") || !strcmp(cmd, "edgecheck") || !strcmp(cmd, "edgecheck_gpu") || !strcmp(cmd, "edgecheck_time"))
     return cmd_edges(cmd, in, out);
   if (!strcmp(cmd, "points")) return cmd_points(in, out);
   if (!strcmp(cmd, "obsfile")) return cmd_obsfile(cmd, in, out);
