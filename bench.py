@@ -120,10 +120,10 @@ def reference_binary_rate(radius, q_per_proc, warm, timed, procs=None):
     of the concurrently running processes are added.  None when the binary is absent."""
     if not os.path.exists(REF_BIN):
         return None
-    import struct
     import tempfile
     import numpy as np
     from drrt_b200 import synth
+    from oracle import pyref
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     procs = procs or cores
     try:
@@ -140,11 +140,7 @@ def reference_binary_rate(radius, q_per_proc, warm, timed, procs=None):
             qs = np.ascontiguousarray(q[p * q_per_proc:(p + 1) * q_per_proc])
             fin, fout = os.path.join(tmp, "in%d.bin" % p), os.path.join(tmp, "out%d.bin" % p)
             with open(fin, "wb") as f:
-                f.write(struct.pack("<iiqq", 0, 1, N_NODES, len(qs)))   # R2S1 metric, theta wraps
-                f.write(pos.tobytes())
-                f.write(qs.tobytes())
-                f.write(np.full(len(qs), radius).tobytes())
-                f.write(struct.pack("<ii", warm, timed))
+                f.write(pyref.range_time_payload(pos, qs, radius, warm, timed))   # R2S1 metric, theta wraps
             jobs.append((fout, len(qs)))
         t0 = time.perf_counter()
         running = [subprocess.Popen([REF_BIN, "range_time", os.path.join(tmp, "in%d.bin" % p), jobs[p][0]],
@@ -156,7 +152,7 @@ def reference_binary_rate(radius, q_per_proc, warm, timed, procs=None):
             return None
         rate, hits, nq, longest = 0.0, 0, 0, 0.0
         for fout, n in jobs:
-            h, secs = struct.unpack("<qd", open(fout, "rb").read(16))
+            h, secs = pyref.parse_time(open(fout, "rb").read(16))
             rate += n * timed / secs
             hits += h
             nq += n
@@ -177,33 +173,19 @@ def reference_binary_edge_rate(s_h, e_h, obstacles, per_proc, procs=None):
     unmodified), one process per core on its own slice of the edges.  None when the binary is absent."""
     if not os.path.exists(REF_BIN):
         return None
-    import struct
     import tempfile
-    import numpy as np
     from drrt_b200 import synth
+    from oracle import pyref
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     procs = procs or cores
     per_proc = max(1, min(per_proc, len(s_h) // procs))
-    o = obstacles
-    head = struct.pack("<idd", 0, synth.R_MIN, synth.ROBOT_RADIUS)
-    head += struct.pack("<i", len(o["kind"]))
-    head += np.ascontiguousarray(o["kind"], dtype=np.int32).tobytes()
-    head += np.ascontiguousarray(o["used"], dtype=np.uint8).tobytes()
-    head += np.ascontiguousarray(o["life_span"], dtype=np.float64).tobytes()
-    head += np.ascontiguousarray(o["origin"], dtype=np.float64).tobytes()
-    head += np.ascontiguousarray(o["radius"], dtype=np.float64).tobytes()
-    head += np.ascontiguousarray(o["vert_off"], dtype=np.int32).tobytes()
-    head += np.ascontiguousarray(o["verts"], dtype=np.float64).tobytes()
     with tempfile.TemporaryDirectory() as tmp:
         outs = []
         for p in range(procs):
             lo, hi = p * per_proc, (p + 1) * per_proc
             fin, fout = os.path.join(tmp, "in%d.bin" % p), os.path.join(tmp, "out%d.bin" % p)
             with open(fin, "wb") as f:
-                f.write(head)
-                f.write(struct.pack("<q", hi - lo))
-                f.write(np.ascontiguousarray(s_h[lo:hi]).tobytes())
-                f.write(np.ascontiguousarray(e_h[lo:hi]).tobytes())
+                f.write(pyref.edge_time_payload(s_h[lo:hi], e_h[lo:hi], obstacles, synth.R_MIN, synth.ROBOT_RADIUS))
             outs.append(fout)
         running = [subprocess.Popen([REF_BIN, "edgecheck_time", os.path.join(tmp, "in%d.bin" % p), outs[p]],
                                     stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
@@ -212,7 +194,7 @@ def reference_binary_edge_rate(s_h, e_h, obstacles, per_proc, procs=None):
             return None
         rate, hits, longest = 0.0, 0, 0.0
         for fout in outs:
-            h, secs = struct.unpack("<qd", open(fout, "rb").read(16))
+            h, secs = pyref.parse_time(open(fout, "rb").read(16))
             rate += per_proc / secs
             hits += h
             longest = max(longest, secs)

@@ -144,3 +144,29 @@ def obstacle_file_edges(path, start, end, r_min=1.0, robot_radius=0.5, metric=0)
     verdict = np.frombuffer(raw, dtype=np.uint8, count=len(s), offset=4).copy()
     dist = np.frombuffer(raw, dtype=np.float64, count=len(s), offset=4 + len(s)).copy()
     return n_obs, verdict, dist
+
+
+# ---- timing commands (bench.py: the reference itself as the CPU baseline) ------------------
+def range_time_payload(pos, q, rad, warm, timed, metric=0, wrap=True):
+    payload, _, _ = _tree_payload(pos, q, rad, metric, wrap)
+    return payload + struct.pack("<ii", int(warm), int(timed))
+
+
+def edge_time_payload(start, end, obstacles, r_min=1.0, robot_radius=0.5, metric=0):
+    s = np.ascontiguousarray(start, dtype=np.float64).reshape(-1, 3)
+    e = np.ascontiguousarray(end, dtype=np.float64).reshape(-1, 3)
+    return (struct.pack("<idd", metric, r_min, robot_radius) + _obs_payload(obstacles or EMPTY_OBS)
+            + struct.pack("<q", len(s)) + _f64(s) + _f64(e))
+
+
+def parse_time(raw):
+    """-> (hits, seconds) written by `range_time` (hits of the first timed pass) / `edgecheck_time`"""
+    return struct.unpack_from("<qd", raw, 0)
+
+
+def range_time(pos, q, rad, warm=0, timed=1, metric=0, wrap=True):
+    return parse_time(_run("range_time", range_time_payload(pos, q, rad, warm, timed, metric, wrap)))
+
+
+def edge_time(start, end, obstacles, r_min=1.0, robot_radius=0.5, metric=0):
+    return parse_time(_run("edgecheck_time", edge_time_payload(start, end, obstacles, r_min, robot_radius, metric)))

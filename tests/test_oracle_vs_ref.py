@@ -129,3 +129,23 @@ def test_live_against_compiled_reference(po):
     assert np.array_equal(v, r["verdict"]) and np.array_equal(ln, r["dist"])
     pts = synth.box_points(3000, 0xC5)
     assert np.array_equal(pyref.points(pts, o), po.RefObstacles(**o).point_check_batch(pts))
+
+
+def test_timing_commands_of_the_reference_driver(po):
+    """`range_time` / `edgecheck_time` (what bench.py --impl reference runs) do the same work as the
+    commands checked above: their hit counts equal the oracle's"""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built here")
+    pos = synth.box_points(5000, 0xD1)
+    q = synth.box_points(40, 0xD2)
+    t = po.RefTree()
+    t.insert(pos)
+    off, _, _ = t.range_batch(q, 2.2)
+    hits, secs = pyref.range_time(pos, q, 2.2, warm=1, timed=2)
+    assert hits == off[-1] and secs > 0.0
+    o = synth.obstacles(32, 0xD3)
+    s, e = synth.random_edges(400, 0xD4, max_len=1.0)
+    v, _ = po.RefObstacles(**o).edge_check_batch(s, e)
+    hits, secs = pyref.edge_time(s, e, o)
+    assert hits == int(v.sum()) and secs > 0.0
