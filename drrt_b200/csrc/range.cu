@@ -462,7 +462,10 @@ static constexpr int CTA_NW = CTA_NB / 4;
 #endif
 static constexpr int CTA_UNR = DRRT_CTA_UNR;
 static constexpr int CTA_CROWDED = 32;  // larger buckets are not insertion-sorted (bytes must not wrap)
-static constexpr int CTA_CHUNK = 8;     // consecutive queries per arena slice (fewer when the batch is small)
+#ifndef DRRT_CTA_CHUNK
+#define DRRT_CTA_CHUNK 8
+#endif
+static constexpr int CTA_CHUNK = DRRT_CTA_CHUNK;  // consecutive queries per arena slice (fewer when the batch is small)
 // dynamic shared memory layout (bytes)
 static constexpr int CTA_OFF_DIST = 0;
 static constexpr int CTA_OFF_ID = CTA_OFF_DIST + CTA_STAGE * 8;
