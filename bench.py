@@ -536,9 +536,9 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak,
                              # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel
-                             # on the default workload (ncu --set full, profiles/r01v5_range_cta_kernel.txt);
+                             # on the default workload (ncu --set full, profiles/r01v12_range_cta_kernel.txt);
                              # not captured for other store sizes
-                             "traffic": 3.627e9 if N_NODES == 1_000_000 else None,
+                             "traffic": 3.450e9 if N_NODES == 1_000_000 else None,
                              "traffic_unit": "bytes/launch",
                              "peak_kind": peak_kind,
                              "kernel": "range_cta_kernel<R2S1> (CTA per query)",
