@@ -222,8 +222,8 @@ __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, 
 // A whole CTA of NWARPS warps visits ALL candidate columns of query Q: every
 // thread resolves one column, a CTA-wide prefix sum lists the non-empty runs,
 // each warp takes an equal contiguous slice of the candidate numbers and every
-// lane handles UNR candidates per trip (i, i+32, ...); the run of a candidate is found by a
-// binary search over a 32-run window held in the warp's registers.  runs holds 2*T+1
+// lane handles UNR candidates per trip (i, i+32, ...); the run of a candidate is found from a
+// 32-run window held in the warp's registers (one REDUX.OR + POPC).  runs holds 2*T+1
 // entries, tmp64 NWARPS words.
 // f(valid[UNR], x[UNR], y[UNR], theta[UNR], id[UNR]) is called converged.
 template <int NWARPS, int UNR, class F>
@@ -274,9 +274,9 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
       }
       int jl = hi;
       // jl is warp-uniform: the run holding the first candidate of the next 32.  Runs are never
-      // empty, so those 32 candidates lie in runs jl .. jl+31: every lane fetches one of them and
-      // finds its own by a binary search over the warp's registers (no divergent walk, no chain of
-      // dependent shared-memory loads).
+      // empty, so those 32 candidates lie in runs jl .. jl+31: every lane fetches one of them, one
+      // warp-wide OR marks where runs end, and a lane's run is a population count away (no
+      // divergent walk, no chain of dependent shared-memory loads or shuffles).
       for (int base = c0; base < c1; base += 32 * UNR) {
         bool valid[UNR];
         double nx[UNR], ny[UNR], nt[UNR];
@@ -288,15 +288,15 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
           nx[u] = ny[u] = nt[u] = 0.0;
           id[u] = 0;
           const int2 e = runs[min(jl + lane, nent)];  // runs[nent] is the sentinel
-          int k = 0;  // runs of this window that end at or before candidate i (at most `lane`)
-#pragma unroll
-          for (int s = 16; s > 0; s >>= 1) {
-            const int t = __shfl_sync(0xffffffffu, e.x, k + s - 1);
-            if (t <= i) k += s;
-          }
-          const int ex = __shfl_sync(0xffffffffu, e.x, k), ey = __shfl_sync(0xffffffffu, e.y, k);
+          // bit b of `ends`: some run of the window ends (exclusively) at candidate i0 + b.  Run jl
+          // holds i0, so b >= 1, and runs are never empty, so the bits are distinct.
+          const int i0 = base + u * 32;
+          const unsigned rel = (unsigned)(e.x - i0);
+          const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+          const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
+          const int ey = __shfl_sync(0xffffffffu, e.y, k);
           if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u]);
-          jl += __shfl_sync(0xffffffffu, k + (ex <= i + 1 ? 1 : 0), 31);
+          jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
         }
         f(valid, nx, ny, nt, id);
       }
