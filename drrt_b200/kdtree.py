@@ -102,7 +102,8 @@ class KDTree:
 
     def KDInsert_dev(self, positions):
         """positions: torch.float64 CUDA tensor (n,3) on this store's device."""
-        assert positions.is_cuda and positions.dtype.is_floating_point and positions.is_contiguous()
+        import torch
+        assert positions.is_cuda and positions.dtype == torch.float64 and positions.is_contiguous()
         first = C.c_int32()
         check(self._lib.drrt_store_insert_dev(self._h, positions.shape[0], _dev_ptr(positions),
                                               _torch_stream(), C.byref(first)))
