@@ -702,7 +702,9 @@ int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const double *
 
 int drrt_extend_fetch(drrt_store *h, int32_t *ids, double *dist, uint8_t *unsafe, double *length) {
   ENTER(h);
-  if (S->last_extend_total < 0) return set_error(DRRT_ERR_STATE, "fetch: no extend batch on this handle");
+  if (S->last_extend_total < 0 || (S->last_extend_total > 0 && (!S->csr_ids || !S->csr_dist)))
+    return set_error(DRRT_ERR_STATE, "fetch: no extend batch on this handle (or a later range call "
+                                     "replaced its rows)");
   cudaStream_t st = S->stream;
   const int64_t t = S->last_extend_total;
   if (t > 0) {

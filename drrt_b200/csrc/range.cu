@@ -727,38 +727,37 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
 
 static constexpr int WARP_SMEM = WARP_STAGE * WARP_MODE_WARPS * 18;
 
-// resident CTAs of the persistent kernels (occupancy x SMs), per metric and kernel
-static int kernel_grid(int metric, bool block_mode, int *grid) {
-  static int per_sm[2][2] = {{0, 0}, {0, 0}}, sms = 0;
-  const int mi = metric == DRRT_METRIC_EUCLID ? 1 : 0, ki = block_mode ? 1 : 0;
-  if (!per_sm[mi][ki]) {
-    int dev = 0, v = 0;
-    DRRT_CUDA(cudaGetDevice(&dev));
-    DRRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (block_mode) {
-      if (mi) {
-        DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<DRRT_METRIC_EUCLID>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
-        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &v, range_cta_kernel<DRRT_METRIC_EUCLID>, CTA_T, CTA_SMEM));
-      } else {
-        DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<DRRT_METRIC_R2S1_WRAP>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
-        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &v, range_cta_kernel<DRRT_METRIC_R2S1_WRAP>, CTA_T, CTA_SMEM));
-      }
-    } else {
-      if (mi)
-        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &v, range_warp_kernel<DRRT_METRIC_EUCLID>, WARP_MODE_WARPS * 32, WARP_SMEM));
-      else
-        DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &v, range_warp_kernel<DRRT_METRIC_R2S1_WRAP>, WARP_MODE_WARPS * 32, WARP_SMEM));
-    }
-    if (v < 1) return set_error(DRRT_ERR_CUDA, "range: kernel does not fit an SM");
-    per_sm[mi][ki] = v;
+// resident CTAs of the persistent kernels (occupancy x SMs).  Cached in the Store: the opt-in to
+// > 48 KB of dynamic shared memory (cudaFuncSetAttribute) is a PER-DEVICE attribute and the SM
+// count belongs to the store's device, so a process-wide cache would launch the CTA kernel
+// without the opt-in on the second device of a multi-GPU process (and race between handles).
+template <int METRIC>
+static int kernel_grid_of(bool block_mode, int *per_sm) {
+  if (block_mode) {
+    DRRT_CUDA(cudaFuncSetAttribute(range_cta_kernel<METRIC>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, CTA_SMEM));
+    DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, range_cta_kernel<METRIC>, CTA_T,
+                                                            CTA_SMEM));
+  } else {
+    DRRT_CUDA(cudaFuncSetAttribute(range_warp_kernel<METRIC>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, WARP_SMEM));
+    DRRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, range_warp_kernel<METRIC>,
+                                                            WARP_MODE_WARPS * 32, WARP_SMEM));
   }
-  *grid = per_sm[mi][ki] * sms;
+  return DRRT_OK;
+}
+
+static int kernel_grid(Store *S, bool block_mode, int *grid) {
+  const int ki = block_mode ? 1 : 0;
+  if (!S->range_grid[ki]) {
+    int sms = 0, v = 0;
+    DRRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device));
+    if (S->metric == DRRT_METRIC_EUCLID) DRRT_CHECK(kernel_grid_of<DRRT_METRIC_EUCLID>(block_mode, &v));
+    else DRRT_CHECK(kernel_grid_of<DRRT_METRIC_R2S1_WRAP>(block_mode, &v));
+    if (v < 1 || sms < 1) return set_error(DRRT_ERR_CUDA, "range: kernel does not fit an SM");
+    S->range_grid[ki] = v * sms;
+  }
+  *grid = S->range_grid[ki];
   return DRRT_OK;
 }
 
@@ -875,6 +874,12 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
   S->last_nq = -1;
   S->last_packed = true;
   S->last_packed_in_alt = false;
+  // the rows of an earlier fused Extend live in the arenas this call overwrites (or frees when
+  // they grow): a late drrt_extend_fetch must fail with DRRT_ERR_STATE, not copy from them
+  S->last_extend_total = -1;
+  S->csr_off = nullptr;
+  S->csr_ids = nullptr;
+  S->csr_dist = nullptr;
   DRRT_CHECK(S->r_offsets.reserve(nq + 1, st));
   DRRT_CHECK(S->r_counts.reserve(nq + 1, st));
   if (nq == 0 || S->n == 0) {
@@ -916,7 +921,7 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
   // neighbourhood; a small batch takes shorter slices so that every resident CTA (warp) still
   // gets several of them.
   int grid = 0;
-  DRRT_CHECK(kernel_grid(S->metric, block_mode, &grid));
+  DRRT_CHECK(kernel_grid(S, block_mode, &grid));
   const int64_t workers = block_mode ? grid : (int64_t)grid * WARP_MODE_WARPS;
   const int chunk_len = (int)std::max<int64_t>(1, std::min<int64_t>(CTA_CHUNK, nq / (4 * workers)));
   const int64_t nchunks = (nq + chunk_len - 1) / chunk_len;

@@ -84,6 +84,7 @@ struct Store {
   cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   int32_t *d_ticket = nullptr;
   unsigned long long *d_totals = nullptr;  // inside the d_ticket allocation
+  int range_grid[2] = {0, 0};  // resident grid of range_warp_kernel / range_cta_kernel on THIS device
   int64_t last_nq = -1, last_total = 0, last_extent = 0;
   bool last_packed = true;          // the primary arena is a plain CSR
   bool last_packed_in_alt = false;  // a packed copy exists in r_*2

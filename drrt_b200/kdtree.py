@@ -39,19 +39,22 @@ class _DevView:
                                          "data": (int(ptr), False), "version": 2}
 
 
-def dev_tensor(ptr, n, typestr):
-    """torch view (no copy) of n items at device pointer ptr; typestr e.g. '<i4', '<i8', '<f8'"""
+def dev_tensor(ptr, n, typestr, device=None):
+    """torch view (no copy) of n items at device pointer ptr; typestr e.g. '<i4', '<i8', '<f8';
+    device: index of the GPU that owns the buffer (default: torch's current device)"""
     import torch
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
     if n == 0:
         return torch.empty(0, dtype={"<i4": torch.int32, "<i8": torch.int64, "<f8": torch.float64,
                                   "|u1": torch.uint8}[typestr],
-                           device="cuda")
-    return torch.as_tensor(_DevView(ptr, n, typestr), device="cuda")
+                           device=dev)
+    return torch.as_tensor(_DevView(ptr, n, typestr), device=dev)
 
 
-def _torch_stream():
+def _torch_stream(device=None):
+    """torch's current stream ON THE STORE'S DEVICE (not on torch's current device)"""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class KDTree:
@@ -74,6 +77,30 @@ class KDTree:
         # batch + fetch is a two-call protocol on the handle: keep the pair together when several
         # host threads share one tree (the reference's callers hold tree_mutex_ for the same reason)
         self._lock = threading.Lock()
+
+    def _check_dev(self, t, dtype, what, min_numel=0, optional=False):
+        """A *_dev entry point hands raw data_ptr()s to the C ABI: a tensor of the wrong dtype,
+        a strided view or a tensor on another GPU would be read / written as something else."""
+        import torch
+        if t is None:
+            if optional:
+                return None
+            raise TypeError("%s: tensor required" % what)
+        if not torch.is_tensor(t) or not t.is_cuda:
+            raise TypeError("%s: CUDA tensor required" % what)
+        if t.dtype != dtype:
+            raise TypeError("%s: dtype %s required, got %s" % (what, dtype, t.dtype))
+        if not t.is_contiguous():
+            raise ValueError("%s: contiguous tensor required" % what)
+        if t.device.index != self.device:
+            raise ValueError("%s: tensor lives on cuda:%s, the store on cuda:%d"
+                             % (what, t.device.index, self.device))
+        if t.numel() < min_numel:
+            raise ValueError("%s: %d elements required, got %d" % (what, min_numel, t.numel()))
+        return t
+
+    def _stream(self):
+        return _torch_stream(self.device)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -103,10 +130,11 @@ class KDTree:
     def KDInsert_dev(self, positions):
         """positions: torch.float64 CUDA tensor (n,3) on this store's device."""
         import torch
-        assert positions.is_cuda and positions.dtype == torch.float64 and positions.is_contiguous()
+        self._check_dev(positions, torch.float64, "KDInsert_dev positions")
+        assert positions.dim() == 2 and positions.shape[1] == 3
         first = C.c_int32()
         check(self._lib.drrt_store_insert_dev(self._h, positions.shape[0], _dev_ptr(positions),
-                                              _torch_stream(), C.byref(first)))
+                                              self._stream(), C.byref(first)))
         return first.value
 
     def structure(self, first=0, n=None):
@@ -188,17 +216,18 @@ class KDTree:
     def KDFindWithinRange_dev(self, range_, query_points):
         """torch in / torch views out (valid until the next range call)."""
         import torch
-        q = query_points
-        assert q.is_cuda and q.dtype == torch.float64 and q.is_contiguous()
+        q = self._check_dev(query_points, torch.float64, "KDFindWithinRange_dev queries")
+        nq = q.numel() // 3
         rad_t = None
         r_all = 0.0
         if torch.is_tensor(range_):
-            rad_t = range_
+            rad_t = self._check_dev(range_, torch.float64, "KDFindWithinRange_dev radii", nq)
         else:
             r_all = float(range_)
         res = capi.RangeResult()
-        check(self._lib.drrt_range_batch_dev(self._h, q.shape[0], _dev_ptr(q), _dev_ptr(rad_t),
-                                             r_all, _torch_stream(), C.byref(res)))
+        check(self._lib.drrt_range_batch_dev(self._h, nq, _dev_ptr(q), _dev_ptr(rad_t),
+                                             r_all, self._stream(), C.byref(res)))
+        res.device = self.device
         return res
 
     def range_pack(self):
@@ -206,7 +235,8 @@ class KDTree:
         offsets = exclusive prefix sum of the counts); a device-side copy when the
         result was written in slices (res.packed == 0)."""
         res = capi.RangeResult()
-        check(self._lib.drrt_range_pack(self._h, _torch_stream(), C.byref(res)))
+        check(self._lib.drrt_range_pack(self._h, self._stream(), C.byref(res)))
+        res.device = self.device
         return res
 
     @staticmethod
@@ -215,12 +245,13 @@ class KDTree:
         library-owned result of the last KDFindWithinRange_dev; row q is
         [offsets[q], offsets[q] + counts[q]) -- see range_result_counts.  For a plain
         CSR (extent == total) call range_pack() first."""
-        return (dev_tensor(res.offsets_dev, res.nq + 1, "<i8"), dev_tensor(res.ids_dev, res.extent, "<i4"),
-                dev_tensor(res.dist_dev, res.extent, "<f8"))
+        d = getattr(res, "device", None)
+        return (dev_tensor(res.offsets_dev, res.nq + 1, "<i8", d), dev_tensor(res.ids_dev, res.extent, "<i4", d),
+                dev_tensor(res.dist_dev, res.extent, "<f8", d))
 
     @staticmethod
     def range_result_counts(res):
-        return dev_tensor(res.counts_dev, res.nq, "<i4")
+        return dev_tensor(res.counts_dev, res.nq, "<i4", getattr(res, "device", None))
 
     # -- KDTree::KDFindNearest kdtree.cpp:264-307
     def KDFindNearest(self, query_points):
@@ -243,8 +274,13 @@ class KDTree:
         return ids, dist
 
     def KDFindKNearest_dev(self, k, q, ids_out, dist_out):
-        check(self._lib.drrt_knn_batch_dev(self._h, q.shape[0], _dev_ptr(q), int(k),
-                                           _dev_ptr(ids_out), _dev_ptr(dist_out), _torch_stream()))
+        import torch
+        self._check_dev(q, torch.float64, "KDFindKNearest_dev queries")
+        nq = q.numel() // 3
+        self._check_dev(ids_out, torch.int32, "KDFindKNearest_dev ids_out", nq * int(k))
+        self._check_dev(dist_out, torch.float64, "KDFindKNearest_dev dist_out", nq * int(k))
+        check(self._lib.drrt_knn_batch_dev(self._h, nq, _dev_ptr(q), int(k),
+                                           _dev_ptr(ids_out), _dev_ptr(dist_out), self._stream()))
 
     # ---- ConfigSpace::obstacles_ + the edge / node checks (obstacle.h:252-282) ----
     def SetObstacles(self, kind, used, life_span, origin, radius, vert_off, verts):
@@ -332,12 +368,19 @@ class KDTree:
     def ExplicitEdgeCheck_dev(self, verdict_out, start=None, end=None, start_ids=None,
                               end_ids=None, robot_radius=0.5, r_min=1.0, edge_kind=EDGE_DUBINS,
                               length_out=None):
+        import torch
+        self._check_dev(verdict_out, torch.uint8, "ExplicitEdgeCheck_dev verdict_out")
         n = verdict_out.shape[0]
+        self._check_dev(start, torch.float64, "ExplicitEdgeCheck_dev start", 3 * n, optional=True)
+        self._check_dev(end, torch.float64, "ExplicitEdgeCheck_dev end", 3 * n, optional=True)
+        self._check_dev(start_ids, torch.int32, "ExplicitEdgeCheck_dev start_ids", n, optional=True)
+        self._check_dev(end_ids, torch.int32, "ExplicitEdgeCheck_dev end_ids", n, optional=True)
+        self._check_dev(length_out, torch.float64, "ExplicitEdgeCheck_dev length_out", n, optional=True)
         check(self._lib.drrt_edgecheck_batch_dev(self._h, n, _dev_ptr(start), _dev_ptr(end),
                                                  _dev_ptr(start_ids), _dev_ptr(end_ids), edge_kind,
                                                  float(robot_radius), float(r_min),
                                                  _dev_ptr(verdict_out), _dev_ptr(length_out),
-                                                 _torch_stream()))
+                                                 self._stream()))
 
     # -- Extend's hot path fused (drrt.cpp:194-362): neighbours, both edges, best parent
     def Extend(self, range_, new_points, lmc=None, robot_radius=0.5, r_min=1.0, in_warmup=False):
@@ -351,6 +394,9 @@ class KDTree:
         best = np.full(nq, -1, dtype=np.int32) if lmc is not None else None
         cost = np.zeros(nq, dtype=np.float64) if lmc is not None else None
         lm = _f64(lmc) if lmc is not None else None
+        if lm is not None and lm.size != self.tree_size_:
+            # the C side uploads tree_size_ doubles from this array
+            raise ValueError("Extend: lmc has %d entries, the store %d nodes" % (lm.size, self.tree_size_))
         with self._lock:
             check(self._lib.drrt_extend_batch(self._h, nq, _ptr(q, c_dp),
                                               _ptr(rad, c_dp) if rad is not None else None, r_all,
@@ -375,16 +421,23 @@ class KDTree:
         """device-resident Extend: torch tensors in; returns (RangeResult rows, unsafe u8[2*total],
         length f64[2*total]) as views of library-owned buffers (valid until the next call)."""
         import torch
-        q = new_points
+        q = self._check_dev(new_points, torch.float64, "Extend_dev new_points")
+        nq = q.numel() // 3
         rad_t, r_all = (range_, 0.0) if torch.is_tensor(range_) else (None, float(range_))
+        self._check_dev(rad_t, torch.float64, "Extend_dev radii", nq, optional=True)
+        self._check_dev(lmc, torch.float64, "Extend_dev lmc", self.tree_size_, optional=True)
+        self._check_dev(best_parent, torch.int32, "Extend_dev best_parent", nq, optional=True)
+        self._check_dev(best_cost, torch.float64, "Extend_dev best_cost", nq, optional=True)
         res = capi.RangeResult()
         u = C.c_void_p()
         ln = C.c_void_p()
-        check(self._lib.drrt_extend_batch_dev(self._h, q.shape[0], _dev_ptr(q), _dev_ptr(rad_t), r_all,
+        check(self._lib.drrt_extend_batch_dev(self._h, nq, _dev_ptr(q), _dev_ptr(rad_t), r_all,
                                               float(robot_radius), float(r_min), _dev_ptr(lmc),
-                                              _torch_stream(), C.byref(res), C.byref(u), C.byref(ln),
+                                              self._stream(), C.byref(res), C.byref(u), C.byref(ln),
                                               _dev_ptr(best_parent), _dev_ptr(best_cost)))
-        return res, dev_tensor(u.value, 2 * res.total, "|u1"), dev_tensor(ln.value, 2 * res.total, "<f8")
+        res.device = self.device
+        return (res, dev_tensor(u.value, 2 * res.total, "|u1", self.device),
+                dev_tensor(ln.value, 2 * res.total, "<f8", self.device))
 
     # -- LineCheck obstacle.cpp:1092-1143
     def LineCheck(self, node1, node2, robot_radius=0.5):

@@ -53,6 +53,17 @@ int metric_of(double (*f)(Eigen::VectorXd, Eigen::VectorXd)) {
 ShimState &state_of(KDTree *t) {
   std::lock_guard<std::mutex> lock(g_mu);
   ShimState &s = g_state[t];
+  // The state is keyed by the tree's address and the reference's KDTree has no destructor to
+  // hook (kdtree.h:13-45).  ThetaStar builds a fresh local tree on every run (thetastar.cpp:50-51,
+  // re-entered from obstacle.cpp:526), and the allocator likes to hand the old address out again:
+  // a tree that says it is empty while this state still holds nodes is a NEW tree -- drop the old
+  // device store and node table instead of answering from them.
+  if (t->tree_size_ == 0 && !s.by_id.empty()) {
+    if (s.h) drrt_store_destroy(s.h);
+    s.h = nullptr;
+    s.by_id.clear();
+    s.failed = false;
+  }
   if (!s.h && !s.failed) {
     int metric = metric_of(t->distanceFunction);
     int wrap_dims[4] = {0, 0, 0, 0};

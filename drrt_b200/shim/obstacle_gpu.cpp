@@ -4,6 +4,10 @@
 
 #include <iostream>
 
+// Failure convention: the checks FAIL CLOSED.  When the device store is missing or a call
+// fails (out of memory, a sticky CUDA fault, a stale obstacle table), every edge / node of the
+// call is reported as colliding -- a planner that keeps running must never be told that an
+// unchecked edge is free -- and the batch entry points return false.
 namespace {
 bool ok(int rc, const char *what) {
   if (rc == DRRT_OK) return true;
@@ -49,7 +53,7 @@ bool ExplicitEdgeCheckBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
                                std::vector<unsigned char> &unsafe) {
   drrt_store *h = DrrtGpuHandle(t);
   const size_t n = edges.size();
-  unsafe.assign(n, 0);
+  unsafe.assign(n, 1);  // fail closed until the device has answered
   if (!h || n == 0) return h != nullptr;
   std::vector<double> s(3 * n), e(3 * n), len(n);
   for (size_t i = 0; i < n; i++)
@@ -60,8 +64,10 @@ bool ExplicitEdgeCheckBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
   if (!ok(drrt_edgecheck_batch(h, (int64_t)n, s.data(), e.data(), DRRT_EDGE_DUBINS,
                                C->robot_radius_, C->min_turn_radius_, C->in_warmup_time_ ? 1 : 0,
                                unsafe.data(), len.data()),
-          "ExplicitEdgeCheck"))
+          "ExplicitEdgeCheck")) {
+    unsafe.assign(n, 1);
     return false;
+  }
   for (size_t i = 0; i < n; i++) {  // dubinsedge.cpp:726, 808, 829
     edges[i]->dist_ = len[i];
     edges[i]->w_dist_ = len[i];
@@ -78,7 +84,7 @@ static bool edge_check_subset(std::shared_ptr<ConfigSpace> &C, KDTree *t,
                               std::vector<unsigned char> &unsafe, Take take) {
   drrt_store *h = DrrtGpuHandle(t);
   const size_t n = edges.size();
-  unsafe.assign(n, 0);
+  unsafe.assign(n, 1);  // fail closed until the device has answered
   if (!h || n == 0) return h != nullptr;
   std::vector<uint8_t> mask;
   {
@@ -92,10 +98,14 @@ static bool edge_check_subset(std::shared_ptr<ConfigSpace> &C, KDTree *t,
       s[3 * i + k] = edges[i]->start_node_->position_(k);
       e[3 * i + k] = edges[i]->end_node_->position_(k);
     }
-  return ok(drrt_edgecheck_subset_batch(h, (int64_t)n, s.data(), e.data(), nullptr, nullptr,
-                                        DRRT_EDGE_DUBINS, C->robot_radius_, C->min_turn_radius_,
-                                        mask.data(), (int32_t)mask.size(), unsafe.data(), nullptr),
-            "ExplicitEdgeCheck(obstacle)");
+  if (!ok(drrt_edgecheck_subset_batch(h, (int64_t)n, s.data(), e.data(), nullptr, nullptr,
+                                      DRRT_EDGE_DUBINS, C->robot_radius_, C->min_turn_radius_,
+                                      mask.data(), (int32_t)mask.size(), unsafe.data(), nullptr),
+          "ExplicitEdgeCheck(obstacle)")) {
+    unsafe.assign(n, 1);
+    return false;
+  }
+  return true;
 }
 
 bool ExplicitEdgeCheckObstacleBatchGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
@@ -121,30 +131,33 @@ bool ExplicitEdgeCheckOtherObstaclesBatchGpu(std::shared_ptr<ConfigSpace> &C, KD
 bool ExplicitEdgeCheckGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t, std::shared_ptr<Edge> &edge) {
   std::vector<std::shared_ptr<Edge>> one(1, edge);
   std::vector<unsigned char> unsafe;
-  ExplicitEdgeCheckBatchGpu(C, t, one, unsafe);
-  return !unsafe.empty() && unsafe[0];
+  if (!ExplicitEdgeCheckBatchGpu(C, t, one, unsafe)) return true;  // unchecked == unsafe
+  return unsafe.empty() || unsafe[0];
 }
 
 bool LineCheckGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t, std::shared_ptr<KDTreeNode> node1,
                   std::shared_ptr<KDTreeNode> node2) {
   drrt_store *h = DrrtGpuHandle(t);
-  if (!h) return false;
+  if (!h) return true;  // unchecked == unsafe
   double s[3] = {node1->position_(0), node1->position_(1), node1->position_(2)};
   double e[3] = {node2->position_(0), node2->position_(1), node2->position_(2)};
-  uint8_t unsafe = 0;
-  ok(drrt_edgecheck_batch(h, 1, s, e, DRRT_EDGE_STRAIGHT, C->robot_radius_, C->min_turn_radius_,
-                          C->in_warmup_time_ ? 1 : 0, &unsafe, nullptr),
-     "LineCheck");
+  uint8_t unsafe = 1;
+  if (!ok(drrt_edgecheck_batch(h, 1, s, e, DRRT_EDGE_STRAIGHT, C->robot_radius_, C->min_turn_radius_,
+                               C->in_warmup_time_ ? 1 : 0, &unsafe, nullptr),
+          "LineCheck"))
+    return true;
   return unsafe != 0;
 }
 
 bool ExplicitNodeCheckGpu(std::shared_ptr<ConfigSpace> &C, KDTree *t,
                           std::shared_ptr<KDTreeNode> node) {
+  if (C->in_warmup_time_) return false;  // obstacle.cpp:1065
   drrt_store *h = DrrtGpuHandle(t);
-  if (!h || C->in_warmup_time_) return false;  // obstacle.cpp:1065
+  if (!h) return true;  // unchecked == in collision
   double p[3] = {node->position_(0), node->position_(1), node->position_(2)};
-  uint8_t hit = 0;
-  ok(drrt_pointcheck_batch(h, 1, p, C->robot_radius_, C->collision_distance_, &hit),
-     "ExplicitNodeCheck");
+  uint8_t hit = 1;
+  if (!ok(drrt_pointcheck_batch(h, 1, p, C->robot_radius_, C->collision_distance_, &hit),
+          "ExplicitNodeCheck"))
+    return true;
   return hit != 0;
 }

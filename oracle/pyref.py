@@ -64,6 +64,29 @@ def range_batch(pos, q, rad, metric=0, wrap=True):
     return off, ids, dist
 
 
+def recreate(pos, q, rad, metric=0, wrap=True):
+    """Tree A over the first half of pos is queried and destroyed, tree B over all of pos is
+    built and queried (ThetaStar's create / destroy / create pattern).  -> two dicts
+    (root id, tree_size_, offsets, ids with each row sorted by id)."""
+    payload, n, nq = _tree_payload(pos, q, rad, metric, wrap)
+    raw = _run("recreate", payload)
+    o = 0
+    out = []
+    for _ in range(2):
+        total, root, size = struct.unpack_from("<qii", raw, o)
+        o += 16
+        counts = np.frombuffer(raw, dtype=np.int32, count=nq, offset=o)
+        o += 4 * nq
+        ids = np.frombuffer(raw, dtype=np.int32, count=total, offset=o).copy()
+        o += 4 * total
+        off = np.zeros(nq + 1, dtype=np.int64)
+        np.cumsum(counts, out=off[1:])
+        for i in range(nq):
+            ids[off[i]:off[i + 1]].sort()
+        out.append(dict(root=root, size=size, off=off, ids=ids))
+    return out
+
+
 def nearest_batch(pos, q, metric=0, wrap=True):
     payload, n, nq = _tree_payload(pos, q, 0.0, metric, wrap)
     raw = _run("nearest", payload)

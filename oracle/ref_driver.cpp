@@ -106,6 +106,41 @@ static int cmd_tree(const char *cmd, Reader &in, Writer &out) {
   int metric = in.get<int32_t>(), wrap = in.get<int32_t>();
   int64_t n = in.get<int64_t>(), nq = in.get<int64_t>();
   std::vector<double> pos = in.arr<double>(3 * n), q = in.arr<double>(3 * nq), rad = in.arr<double>(nq);
+  if (!strcmp(cmd, "recreate")) {
+    // ThetaStar builds a fresh local KDTree on every run (thetastar.cpp:50-51, re-entered from
+    // obstacle.cpp:526) and lets the old one die: tree A over the first half of the nodes is
+    // queried and destroyed, tree B over all of them is built (the allocator usually hands A's
+    // address out again) and queried -- B must answer from its own nodes only
+    for (int pass = 0; pass < 2; pass++) {
+      const int64_t m = pass == 0 ? n / 2 : n;
+      shared_ptr<KDTree> T = make_tree(metric, wrap);
+      std::unordered_map<KDTreeNode *, int> id_of;
+      std::vector<shared_ptr<KDTreeNode>> nodes;
+      for (int64_t i = 0; i < m; i++) {
+        shared_ptr<KDTreeNode> nd = make_shared<KDTreeNode>(vec3(&pos[3 * i]));
+        T->KDInsert(nd);
+        id_of[nd.get()] = (int)i;
+        nodes.push_back(nd);
+      }
+      std::vector<int32_t> counts(nq), ids;
+      for (int64_t i = 0; i < nq; i++) {
+        shared_ptr<JList> S = make_shared<JList>(true);
+        T->KDFindWithinRange(S, rad[i], vec3(&q[3 * i]));
+        counts[i] = S->length_;
+        shared_ptr<KDTreeNode> t = make_shared<KDTreeNode>();
+        shared_ptr<double> k = make_shared<double>(0);
+        while (S->length_ > 0) {
+          T->PopFromRangeList(S, t, k);
+          ids.push_back(id_of[t.get()]);
+        }
+      }
+      out.put<int64_t>((int64_t)ids.size());
+      out.put<int32_t>(T->root ? id_of[T->root.get()] : -1);
+      out.put<int32_t>(T->tree_size_);
+      out.arr(counts); out.arr(ids);
+    }
+    return 0;
+  }
   shared_ptr<KDTree> T = make_tree(metric, wrap);
   std::unordered_map<KDTreeNode *, int> id_of;
   std::vector<shared_ptr<KDTreeNode>> nodes;
@@ -410,7 +445,7 @@ int main(int argc, char **argv) {
   Writer out(argv[3]);
   const char *cmd = argv[1];
   if (!strcmp(cmd, "range") || !strcmp(cmd, "range_time") || !strcmp(cmd, "nearest") || !strcmp(cmd, "structure") ||
-      !strcmp(cmd, "ghosts"))
+      !strcmp(cmd, "ghosts") || !strcmp(cmd, "recreate"))
     return cmd_tree(cmd, in, out);
   if (!strcmp(cmd, "traj") || !strcmp(cmd, "edgecheck") || !strcmp(cmd, "edgecheck_gpu") || !strcmp(cmd, "edgecheck_time"))
     return cmd_edges(cmd, in, out);

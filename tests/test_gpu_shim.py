@@ -49,6 +49,22 @@ def test_reference_objects_over_gpu_tree(shim, gold):
     assert off.tolist() == g["off"] and ids.tolist() == g["ids"]
 
 
+def test_tree_destroyed_and_recreated(shim, po):
+    """ThetaStar's pattern (thetastar.cpp:50-51 re-entered from obstacle.cpp:526): a local KDTree
+    dies and the next make_shared<KDTree> usually gets its address back.  The shim keys its state
+    by that address; the second tree must start from an empty device store (root = its own first
+    node, ids from 0) and answer from its own nodes only."""
+    I = gen.inputs()
+    a, b = shim.recreate(I["pos"], I["q"], I["rad"])
+    n = len(I["pos"])
+    for got, m in ((a, n // 2), (b, n)):
+        ref = po.RefTree()
+        ref.insert(I["pos"][:m])
+        roff, rids, _ = ref.range_batch(I["q"], I["rad"])
+        assert got["root"] == 0 and got["size"] == m
+        assert np.array_equal(got["off"], roff) and np.array_equal(got["ids"], rids)
+
+
 def test_reference_edges_over_gpu_checker(shim, po, gold):
     I = gen.inputs()
     r = shim.edges(I["s"], I["e"], I["o"], cmd="edgecheck_gpu")

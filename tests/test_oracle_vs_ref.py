@@ -131,6 +131,24 @@ def test_live_against_compiled_reference(po):
     assert np.array_equal(pyref.points(pts, o), po.RefObstacles(**o).point_check_batch(pts))
 
 
+def test_recreate_command_of_the_reference_driver(po):
+    """the create / destroy / create sequence the shim's lifetime test replays
+    (tests/test_gpu_shim.py), here over the reference's own kdtree.cpp"""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref/drrt_ref not built")
+    from drrt_b200 import synth
+    pos = synth.box_points(600, 0x51)
+    q = synth.box_points(40, 0x52)
+    a, b = pyref.recreate(pos, q, 4.0)
+    for got, m in ((a, 300), (b, 600)):
+        t = po.RefTree()
+        t.insert(pos[:m])
+        roff, rids, _ = t.range_batch(q, 4.0)
+        assert got["root"] == 0 and got["size"] == m
+        assert np.array_equal(got["off"], roff) and np.array_equal(got["ids"], rids)
+
+
 def test_timing_commands_of_the_reference_driver(po):
     """`range_time` / `edgecheck_time` (what bench.py --impl reference runs) do the same work as the
     commands checked above: their hit counts equal the oracle's"""
