@@ -15,6 +15,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM, ERR_NO_DEVICE, ERR_STATE,
 METRIC_R2S1_WRAP, METRIC_EUCLID = 0, 1
 EDGE_DUBINS, EDGE_STRAIGHT = 0, 1
 TRAJ_MAX = 200
+ABI_VERSION = 4
 PI = 3.1415926536  # include/DRRT/distancefunctions.h:22
 INF = 1000000000000.0
 
@@ -22,6 +23,7 @@ c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
 c_u8p = C.POINTER(C.c_uint8)
 c_i64p = C.POINTER(C.c_int64)
+c_fp = C.POINTER(C.c_float)
 
 
 class RangeResult(C.Structure):
@@ -54,6 +56,38 @@ SIGNATURES = {
     "drrt_range_fetch": (C.c_int, [C.c_void_p, c_ip, c_dp]),
     "drrt_range_batch_into": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_int64,
                                         c_i64p, c_ip, c_dp, c_i64p]),
+    "drrt_range_batch_into_f32": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_int64,
+                                            c_i64p, c_ip, C.POINTER(C.c_float), c_i64p]),
+    "drrt_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "drrt_host_free": (C.c_int, [C.c_void_p]),
+    "drrt_lmc_write": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_dp]),
+    "drrt_lmc_scatter": (C.c_int, [C.c_void_p, C.c_int64, c_ip, c_dp]),
+    "drrt_lmc_read": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_dp]),
+    "drrt_comm_init": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_int), c_dp,
+                                 C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "drrt_comm_destroy": (C.c_int, [C.c_void_p]),
+    "drrt_comm_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "drrt_comm_store": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "drrt_comm_broadcast_bytes": (C.c_int64, [C.c_void_p]),
+    "drrt_comm_insert": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_ip]),
+    "drrt_comm_obstacles_set": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_u8p, c_dp, c_dp, c_dp, c_ip,
+                                          c_dp]),
+    "drrt_comm_range_batch_into": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_int64,
+                                             c_i64p, c_ip, c_dp, c_i64p]),
+    "drrt_comm_range_batch_into_f32": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double,
+                                                 C.c_int64, c_i64p, c_ip, C.POINTER(C.c_float), c_i64p]),
+    "drrt_comm_nearest_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_ip, c_dp]),
+    "drrt_comm_knn_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, C.c_int, c_ip, c_dp]),
+    "drrt_comm_edgecheck_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_int, C.c_double,
+                                            C.c_double, C.c_int, c_u8p, c_dp]),
+    "drrt_comm_edgecheck_ids_batch": (C.c_int, [C.c_void_p, C.c_int64, c_ip, c_ip, C.c_int, C.c_double,
+                                                C.c_double, C.c_int, c_u8p, c_dp]),
+    "drrt_comm_pointcheck_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, C.c_double, C.c_double,
+                                             c_u8p]),
+    "drrt_comm_lmc_write": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_dp]),
+    "drrt_comm_lmc_scatter": (C.c_int, [C.c_void_p, C.c_int64, c_ip, c_dp]),
+    "drrt_comm_extend_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_double,
+                                         C.c_double, C.c_int, c_dp, c_ip, c_i64p, c_ip, c_dp]),
     "drrt_range_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_void_p, C.POINTER(RangeResult)]),
     "drrt_range_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RangeResult)]),
@@ -110,7 +144,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
             fn.restype = res
             fn.argtypes = args
-        if lib.drrt_abi_version() != 3:
+        if lib.drrt_abi_version() != ABI_VERSION:
             raise ImportError("drrt_b200: ABI version mismatch")
         _lib = lib
     return _lib

@@ -61,8 +61,8 @@ static int download(void *dst, const void *src, size_t bytes, cudaStream_t st) {
   return DRRT_OK;
 }
 
-static int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist,
-                    bool nearest = false) {
+int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist,
+                    bool nearest) {
   if (nq < 0 || k < 1 || (nq > 0 && (!q || !ids)))
     return set_error(DRRT_ERR_INVALID, "knn: arguments");
   cudaStream_t st = S->stream;
@@ -83,44 +83,139 @@ static int put(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t st) {
   return upload(v.data(), b.p, v.size() * sizeof(T), st);
 }
 
-static int edge_host(Store *S, int64_t n, const double *start, const double *end,
-                     const int32_t *sid, const int32_t *eid, int edge_kind, double robot_radius,
-                     double r_min, int in_warmup, uint8_t *verdict, double *length) {
+// Host-buffer leg of the edge checks.  Large pose batches are PIPELINED: the poses of chunk
+// k + 1 cross PCIe (48 B per edge, the dominant cost: 480 MB for config 3's 10 M edges against
+// 8 ms of kernels) while chunk k is solved and walked, and the verdicts / lengths of chunk k - 1
+// leave on a third stream -- the call costs max(H2D, kernels) + one chunk instead of their sum.
+static constexpr int64_t EDGE_CHUNK = 1 << 20;
+
+static int edge_streams(Store *S) {
+  if (S->ev_up[0]) return DRRT_OK;
+  if (!S->copy_stream) DRRT_CUDA(cudaStreamCreateWithFlags(&S->copy_stream, cudaStreamNonBlocking));
+  if (!S->down_stream) DRRT_CUDA(cudaStreamCreateWithFlags(&S->down_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_done[b], cudaEventDisableTiming));
+    DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_up[b], cudaEventDisableTiming));
+  }
+  return DRRT_OK;
+}
+
+int edge_host(Store *S, int64_t n, const double *start, const double *end,
+              const int32_t *sid, const int32_t *eid, int edge_kind, double robot_radius,
+              double r_min, int in_warmup, uint8_t *verdict, double *length) {
   if (n < 0 || (n > 0 && !verdict)) return set_error(DRRT_ERR_INVALID, "edgecheck: arguments");
   bool by_id = sid && eid;
   if (n > 0 && !by_id && !(start && end)) return set_error(DRRT_ERR_INVALID, "edgecheck: endpoints");
   if (n == 0) return DRRT_OK;
   cudaStream_t st = S->stream;
-  const double *sd = nullptr, *ed = nullptr;
-  const int32_t *si = nullptr, *ei = nullptr;
-  if (by_id) {
+  if (by_id)
     for (int64_t i = 0; i < n; i++)
       if (sid[i] < 0 || sid[i] >= S->n || eid[i] < 0 || eid[i] >= S->n)
         return set_error(DRRT_ERR_INVALID, "edgecheck: node id out of range at edge %lld", (long long)i);
-    DRRT_CHECK(S->i_stage.reserve(n, st));
-    DRRT_CHECK(S->i_stage2.reserve(n, st));
-    DRRT_CHECK(upload(sid, S->i_stage.p, n * sizeof(int32_t), st));
-    DRRT_CHECK(upload(eid, S->i_stage2.p, n * sizeof(int32_t), st));
-    si = S->i_stage.p; ei = S->i_stage2.p;
-  } else {
-    DRRT_CHECK(S->d_stage.reserve(3 * n, st));
-    DRRT_CHECK(S->d_stage2.reserve(3 * n, st));
-    DRRT_CHECK(upload(start, S->d_stage.p, 3 * n * sizeof(double), st));
-    DRRT_CHECK(upload(end, S->d_stage2.p, 3 * n * sizeof(double), st));
-    sd = S->d_stage.p; ed = S->d_stage2.p;
-  }
+  // in_warmup_time_ (obstacle.cpp:883): no obstacle is consulted, lengths still computed
+  const bool saved = S->has_obstacles;
+  struct Restore {
+    Store *S; bool v;
+    ~Restore() { S->has_obstacles = v; }
+  } restore{S, saved};
+  if (in_warmup) S->has_obstacles = false;
   DRRT_CHECK(S->b_stage.reserve(n, st));
   if (length) DRRT_CHECK(S->d_stage3.reserve(n, st));
-  // in_warmup_time_ (obstacle.cpp:883): no obstacle is consulted, lengths still computed
-  bool saved = S->has_obstacles;
-  if (in_warmup) S->has_obstacles = false;
-  int rc = edgecheck_batch_dev(S, n, sd, ed, si, ei, edge_kind, robot_radius, r_min, S->b_stage.p,
-                               length ? S->d_stage3.p : nullptr, st);
-  S->has_obstacles = saved;
-  DRRT_CHECK(rc);
-  DRRT_CHECK(download(verdict, S->b_stage.p, n, st));
-  if (length) DRRT_CHECK(download(length, S->d_stage3.p, n * sizeof(double), st));
-  DRRT_CUDA(cudaStreamSynchronize(st));
+
+  if (n < 2 * EDGE_CHUNK) {
+    const double *sd = nullptr, *ed = nullptr;
+    const int32_t *si = nullptr, *ei = nullptr;
+    if (by_id) {
+      DRRT_CHECK(S->i_stage.reserve(n, st));
+      DRRT_CHECK(S->i_stage2.reserve(n, st));
+      DRRT_CHECK(upload(sid, S->i_stage.p, n * sizeof(int32_t), st));
+      DRRT_CHECK(upload(eid, S->i_stage2.p, n * sizeof(int32_t), st));
+      si = S->i_stage.p; ei = S->i_stage2.p;
+    } else {
+      DRRT_CHECK(S->d_stage.reserve(3 * n, st));
+      DRRT_CHECK(S->d_stage2.reserve(3 * n, st));
+      DRRT_CHECK(upload(start, S->d_stage.p, 3 * n * sizeof(double), st));
+      DRRT_CHECK(upload(end, S->d_stage2.p, 3 * n * sizeof(double), st));
+      sd = S->d_stage.p; ed = S->d_stage2.p;
+    }
+    DRRT_CHECK(edgecheck_batch_dev(S, n, sd, ed, si, ei, edge_kind, robot_radius, r_min, S->b_stage.p,
+                                   length ? S->d_stage3.p : nullptr, st));
+    DRRT_CHECK(download(verdict, S->b_stage.p, n, st));
+    if (length) DRRT_CHECK(download(length, S->d_stage3.p, n * sizeof(double), st));
+    DRRT_CUDA(cudaStreamSynchronize(st));
+    return DRRT_OK;
+  }
+
+  DRRT_CHECK(edge_streams(S));
+  cudaStream_t up = S->copy_stream, down = S->down_stream;
+  const int64_t CH = EDGE_CHUNK;
+  if (by_id) {
+    DRRT_CHECK(S->i_stage.reserve(2 * CH, st));
+    DRRT_CHECK(S->i_stage2.reserve(2 * CH, st));
+  } else {
+    DRRT_CHECK(S->d_stage.reserve(2 * 3 * CH, st));
+    DRRT_CHECK(S->d_stage2.reserve(2 * 3 * CH, st));
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));  // the staging buffers may have been reallocated
+  int rc = DRRT_OK;
+  bool used[2] = {false, false};
+  auto chunk = [&](int64_t k0, int64_t m, int b) -> int {
+    if (used[b]) DRRT_CUDA(cudaStreamWaitEvent(up, S->ev_done[b], 0));  // half b is free again
+    const double *sd = nullptr, *ed = nullptr;
+    const int32_t *si = nullptr, *ei = nullptr;
+    if (by_id) {
+      DRRT_CHECK(upload(sid + k0, S->i_stage.p + b * CH, m * sizeof(int32_t), up));
+      DRRT_CHECK(upload(eid + k0, S->i_stage2.p + b * CH, m * sizeof(int32_t), up));
+      si = S->i_stage.p + b * CH; ei = S->i_stage2.p + b * CH;
+    } else {
+      DRRT_CHECK(upload(start + 3 * k0, S->d_stage.p + b * 3 * CH, 3 * m * sizeof(double), up));
+      DRRT_CHECK(upload(end + 3 * k0, S->d_stage2.p + b * 3 * CH, 3 * m * sizeof(double), up));
+      sd = S->d_stage.p + b * 3 * CH; ed = S->d_stage2.p + b * 3 * CH;
+    }
+    DRRT_CUDA(cudaEventRecord(S->ev_up[b], up));
+    DRRT_CUDA(cudaStreamWaitEvent(st, S->ev_up[b], 0));
+    DRRT_CHECK(edgecheck_batch_dev(S, m, sd, ed, si, ei, edge_kind, robot_radius, r_min,
+                                   S->b_stage.p + k0, length ? S->d_stage3.p + k0 : nullptr, st));
+    DRRT_CUDA(cudaEventRecord(S->ev_done[b], st));
+    DRRT_CUDA(cudaStreamWaitEvent(down, S->ev_done[b], 0));
+    DRRT_CHECK(download(verdict + k0, S->b_stage.p + k0, m, down));
+    if (length) DRRT_CHECK(download(length + k0, S->d_stage3.p + k0, m * sizeof(double), down));
+    used[b] = true;
+    return DRRT_OK;
+  };
+  for (int64_t k0 = 0, k = 0; k0 < n && rc == DRRT_OK; k0 += CH, k++)
+    rc = chunk(k0, std::min(CH, n - k0), (int)(k & 1));
+  // copies into the caller's buffers are always waited for, error or not
+  cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(down);
+  if (rc != DRRT_OK) return rc;
+  DRRT_CUDA(e1);
+  DRRT_CUDA(e2);
+  DRRT_CUDA(e3);
+  return DRRT_OK;
+}
+
+__global__ void fill_f64_kernel(double *p, int64_t n, double v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+__global__ void scatter_f64_kernel(double *dst, int64_t n, const int32_t *ids, const double *v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[ids[i]] = v[i];
+}
+
+// The device mirror of KDTreeNode::rrt_LMC_ covers every node of the store: nodes the caller
+// has not written yet hold INF, the value a new node carries until FindBestParent gives it a
+// parent (drrt.cpp:391).
+int lmc_mirror_cover(Store *S, cudaStream_t st) {
+  if (S->lmc_n >= S->n) return DRRT_OK;
+  DRRT_CHECK(S->x_lmc.reserve((size_t)S->n + 1, st, true, (size_t)S->lmc_n));
+  const int64_t fresh = S->n - S->lmc_n;
+  fill_f64_kernel<<<(unsigned)std::min<int64_t>((fresh + 255) / 256, 148 * 8), 256, 0, st>>>(
+      S->x_lmc.p + S->lmc_n, fresh, DRRT_INF);
+  DRRT_LAUNCHED();
+  DRRT_CUDA(cudaGetLastError());
+  S->lmc_n = S->n;
   return DRRT_OK;
 }
 
@@ -238,6 +333,11 @@ int drrt_store_destroy(drrt_store *h) {
       if (S->ev_packed[b]) cudaEventDestroy(S->ev_packed[b]);
       if (S->ev_copied[b]) cudaEventDestroy(S->ev_copied[b]);
     }
+    for (int b = 0; b < 2; b++) {
+      if (S->ev_up[b]) cudaEventDestroy(S->ev_up[b]);
+      if (S->ev_done[b]) cudaEventDestroy(S->ev_done[b]);
+    }
+    if (S->down_stream) cudaStreamDestroy(S->down_stream);
     if (S->copy_stream) cudaStreamDestroy(S->copy_stream);
     if (S->stream) cudaStreamDestroy(S->stream);
   }
@@ -359,13 +459,67 @@ int drrt_range_fetch(drrt_store *h, int32_t *ids, double *dist) {
 // full-length slices on every resident CTA, small enough that the first rows leave early.
 static constexpr int64_t INTO_SUB = 16384;
 
-int drrt_range_batch_into(drrt_store *h, int64_t nq, const double *q, const double *radius,
-                          double radius_all, int64_t cap, int64_t *offsets, int32_t *ids,
-                          double *dist, int64_t *total) {
-  ENTER(h);
+}  // extern "C"
+
+namespace drrt {
+
+// The streamed host query behind drrt_range_batch_into[_f32] (and the per-GPU leg of
+// drrt_comm_range_batch_into).  dist_kind picks what crosses PCIe per hit beside the 4-byte id:
+// the double key (8 B, bit-exact), a float key (4 B) or nothing.
+int range_into(Store *S, int64_t nq, const double *q, const double *radius, double radius_all,
+               int64_t cap, int64_t *offsets, int32_t *ids, void *dist, int dist_kind,
+               int64_t *total) {
   if (nq < 0 || cap < 0 || (nq > 0 && (!q || !offsets)) || (cap > 0 && !ids))
     return set_error(DRRT_ERR_INVALID, "range_into: arguments");
+  if (!dist) dist_kind = DIST_NONE;
+  const size_t dsz = dist_kind == DIST_F64 ? sizeof(double) : (dist_kind == DIST_F32 ? sizeof(float) : 0);
   cudaStream_t st = S->stream;
+  DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
+  DRRT_CHECK(upload(q, S->q_stage.p, 3 * nq * sizeof(double), st));
+  if (radius) {
+    DRRT_CHECK(S->rad_stage.reserve(nq + 1, st));
+    DRRT_CHECK(upload(radius, S->rad_stage.p, nq * sizeof(double), st));
+  }
+  if (offsets) offsets[0] = 0;
+  if (nq <= INTO_SUB + INTO_SUB / 2) {
+    // One sub-batch (the planner's own call is nq == 1, src/drrt.cpp:213-216): nothing to overlap,
+    // so everything stays on the handle's stream -- one kernel, one completion wait inside
+    // range_batch_dev, the copies, one wait.  A lone slice is already a plain CSR and its double
+    // rows leave straight from the arena.
+    drrt_range_result res{};
+    int rc = range_batch_dev(S, nq, S->q_stage.p, radius ? S->rad_stage.p : nullptr, radius_all, st, &res);
+    if (rc == DRRT_OK && nq > 0) {
+      const bool fits = res.total <= cap;
+      if (res.packed && dist_kind != DIST_F32) {
+        rc = download(offsets, res.offsets_dev, (nq + 1) * sizeof(int64_t), st);
+        if (rc == DRRT_OK && fits && res.total > 0) {
+          rc = download(ids, res.ids_dev, res.total * sizeof(int32_t), st);
+          if (rc == DRRT_OK && dsz) rc = download(dist, res.dist_dev, res.total * dsz, st);
+        }
+      } else {
+        const size_t need = (size_t)res.total + 1;
+        rc = S->p_off[0].reserve(nq + 1, st);
+        if (rc == DRRT_OK) rc = S->p_ids[0].reserve(need, st);
+        if (rc == DRRT_OK && dsz) rc = S->p_dist[0].reserve(need, st);
+        if (rc == DRRT_OK)
+          rc = range_pack_to(S, st, S->p_off[0].p, S->p_ids[0].p, S->p_dist[0].p, dist_kind, 0);
+        if (rc == DRRT_OK) rc = download(offsets, S->p_off[0].p, (nq + 1) * sizeof(int64_t), st);
+        if (rc == DRRT_OK && fits && res.total > 0) {
+          rc = download(ids, S->p_ids[0].p, res.total * sizeof(int32_t), st);
+          if (rc == DRRT_OK && dsz) rc = download(dist, S->p_dist[0].p, res.total * dsz, st);
+        }
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    S->last_nq = -1;
+    if (rc != DRRT_OK) return rc;
+    DRRT_CUDA(e);
+    if (total) *total = res.total;
+    if (res.total > cap)
+      return set_error(DRRT_ERR_CAPACITY, "range_into: %lld hits, caller buffers hold %lld",
+                       (long long)res.total, (long long)cap);
+    return DRRT_OK;
+  }
   if (!S->copy_stream) {
     DRRT_CUDA(cudaStreamCreateWithFlags(&S->copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {
@@ -374,20 +528,13 @@ int drrt_range_batch_into(drrt_store *h, int64_t nq, const double *q, const doub
     }
   }
   cudaStream_t cs = S->copy_stream;
-  DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
-  DRRT_CHECK(upload(q, S->q_stage.p, 3 * nq * sizeof(double), st));
-  if (radius) {
-    DRRT_CHECK(S->rad_stage.reserve(nq + 1, st));
-    DRRT_CHECK(upload(radius, S->rad_stage.p, nq * sizeof(double), st));
-  }
-  if (offsets) offsets[0] = 0;
-  const int64_t sub = nq > INTO_SUB + INTO_SUB / 2 ? INTO_SUB : std::max<int64_t>(nq, 1);
-  std::vector<int64_t> bases;
+  const int64_t sub = INTO_SUB;
   int64_t base = 0;
   int rc = DRRT_OK;
   bool used[2] = {false, false};
-  // one sub-batch: query, pack into buffer b, queue the copies; an error leaves the loop but the
-  // copies already queued into the caller's buffers are always waited for below
+  // one sub-batch: query, pack into buffer b (offsets already global: the scan starts at `base`),
+  // queue the copies; an error leaves the loop but the copies already queued into the caller's
+  // buffers are always waited for below
   auto sub_batch = [&](int64_t k0, int64_t nb, int b) -> int {
     drrt_range_result res{};
     DRRT_CHECK(range_batch_dev(S, nb, S->q_stage.p + 3 * k0, radius ? S->rad_stage.p + k0 : nullptr,
@@ -396,26 +543,25 @@ int drrt_range_batch_into(drrt_store *h, int64_t nq, const double *q, const doub
     // old block, so wait on the host in that case; otherwise the stream waits)
     const size_t need = (size_t)res.total + 1;
     if (used[b]) {
-      if (need > S->p_ids[b].cap || need > S->p_dist[b].cap || (size_t)nb + 1 > S->p_off[b].cap)
+      if (need > S->p_ids[b].cap || (dsz && need > S->p_dist[b].cap) || (size_t)nb + 1 > S->p_off[b].cap)
         DRRT_CUDA(cudaEventSynchronize(S->ev_copied[b]));
       else
         DRRT_CUDA(cudaStreamWaitEvent(st, S->ev_copied[b], 0));
     }
     DRRT_CHECK(S->p_off[b].reserve(nb + 1, st));
     DRRT_CHECK(S->p_ids[b].reserve(need, st));
-    DRRT_CHECK(S->p_dist[b].reserve(need, st));
-    DRRT_CHECK(range_pack_to(S, st, S->p_off[b].p, S->p_ids[b].p, S->p_dist[b].p));
+    if (dsz) DRRT_CHECK(S->p_dist[b].reserve(need, st));
+    DRRT_CHECK(range_pack_to(S, st, S->p_off[b].p, S->p_ids[b].p, S->p_dist[b].p, dist_kind, base));
     DRRT_CUDA(cudaEventRecord(S->ev_packed[b], st));
     DRRT_CUDA(cudaStreamWaitEvent(cs, S->ev_packed[b], 0));
-    // offsets of the sub-batch are relative to its first row; the base is added below
+    // (the entry a sub-batch shares with its successor is written twice with the same value)
     DRRT_CHECK(download(offsets + k0, S->p_off[b].p, (nb + 1) * sizeof(int64_t), cs));
     if (base + res.total <= cap && res.total > 0) {
       DRRT_CHECK(download(ids + base, S->p_ids[b].p, res.total * sizeof(int32_t), cs));
-      if (dist) DRRT_CHECK(download(dist + base, S->p_dist[b].p, res.total * sizeof(double), cs));
+      if (dsz) DRRT_CHECK(download((char *)dist + base * dsz, S->p_dist[b].p, res.total * dsz, cs));
     }
     DRRT_CUDA(cudaEventRecord(S->ev_copied[b], cs));
     used[b] = true;
-    bases.push_back(base);
     base += res.total;
     return DRRT_OK;
   };
@@ -426,17 +572,29 @@ int drrt_range_batch_into(drrt_store *h, int64_t nq, const double *q, const doub
   if (rc != DRRT_OK) return rc;
   DRRT_CUDA(e1);
   DRRT_CUDA(e2);
-  // (the entry a sub-batch shares with its successor was overwritten by the successor's 0)
-  for (size_t k = 1; k < bases.size(); k++) {
-    const int64_t k0 = (int64_t)k * sub, nb = std::min(sub, nq - k0);
-    for (int64_t i = 0; i < nb; i++) offsets[k0 + i] += bases[k];
-  }
-  if (nq > 0) offsets[nq] = base;
   if (total) *total = base;
   if (base > cap)
     return set_error(DRRT_ERR_CAPACITY, "range_into: %lld hits, caller buffers hold %lld",
                      (long long)base, (long long)cap);
   return DRRT_OK;
+}
+
+}  // namespace drrt
+
+extern "C" {
+
+int drrt_range_batch_into(drrt_store *h, int64_t nq, const double *q, const double *radius,
+                          double radius_all, int64_t cap, int64_t *offsets, int32_t *ids,
+                          double *dist, int64_t *total) {
+  ENTER(h);
+  return range_into(S, nq, q, radius, radius_all, cap, offsets, ids, dist, DIST_F64, total);
+}
+
+int drrt_range_batch_into_f32(drrt_store *h, int64_t nq, const double *q, const double *radius,
+                              double radius_all, int64_t cap, int64_t *offsets, int32_t *ids,
+                              float *dist, int64_t *total) {
+  ENTER(h);
+  return range_into(S, nq, q, radius, radius_all, cap, offsets, ids, dist, DIST_F32, total);
 }
 
 int drrt_range_pack(drrt_store *h, void *stream, drrt_range_result *out) {
@@ -466,7 +624,7 @@ int drrt_nearest_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, int32
 }
 int drrt_knn_batch(drrt_store *h, int64_t nq, const double *q, int k, int32_t *ids, double *dist) {
   ENTER(h);
-  return knn_host(S, nq, q, k, ids, dist);
+  return knn_host(S, nq, q, k, ids, dist, false);
 }
 int drrt_knn_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
                        double *dist_dev, void *stream) {
@@ -658,7 +816,6 @@ int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const double *
                       double *best_cost) {
   ENTER(h);
   if (nq < 0 || (nq > 0 && (!q || !counts))) return set_error(DRRT_ERR_INVALID, "extend: arguments");
-  if (best_parent && !lmc) return set_error(DRRT_ERR_INVALID, "extend: best_parent needs lmc");
   cudaStream_t st = S->stream;
   S->last_extend_total = -1;
   DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
@@ -670,9 +827,17 @@ int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const double *
     rad_dev = S->rad_stage.p;
   }
   const double *lmc_dev = nullptr;
-  if (lmc && best_parent) {
-    DRRT_CHECK(S->x_lmc.reserve(S->n + 1, st));
-    DRRT_CHECK(upload(lmc, S->x_lmc.p, S->n * sizeof(double), st));
+  if (best_parent) {
+    if (lmc) {
+      // the whole array from the host (the mirror now equals it)
+      DRRT_CHECK(S->x_lmc.reserve(S->n + 1, st));
+      DRRT_CHECK(upload(lmc, S->x_lmc.p, S->n * sizeof(double), st));
+      S->lmc_n = S->n;
+    } else {
+      // the device-resident mirror kept current by drrt_lmc_write / drrt_lmc_scatter:
+      // nothing store-sized crosses PCIe
+      DRRT_CHECK(lmc_mirror_cover(S, st));
+    }
     DRRT_CHECK(S->x_best.reserve(nq + 1, st));
     DRRT_CHECK(S->x_best_cost.reserve(nq + 1, st));
     lmc_dev = S->x_lmc.p;
@@ -730,6 +895,70 @@ int drrt_extend_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, const 
                               pick(S, stream), rows, &u, &l, best_parent_dev, best_cost_dev));
   if (unsafe_dev) *unsafe_dev = u;
   if (length_dev) *length_dev = l;
+  return DRRT_OK;
+}
+
+// ---- device mirror of rrt_LMC_ ---------------------------------------------
+
+int drrt_lmc_write(drrt_store *h, int64_t first, int64_t n, const double *values) {
+  ENTER(h);
+  if (first < 0 || n < 0 || first + n > S->n || (n > 0 && !values))
+    return set_error(DRRT_ERR_INVALID, "lmc_write: range [%lld, %lld) of a %lld-node store",
+                     (long long)first, (long long)(first + n), (long long)S->n);
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(lmc_mirror_cover(S, st));
+  DRRT_CHECK(upload(values, S->x_lmc.p + first, n * sizeof(double), st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+int drrt_lmc_scatter(drrt_store *h, int64_t n, const int32_t *ids, const double *values) {
+  ENTER(h);
+  if (n < 0 || (n > 0 && (!ids || !values))) return set_error(DRRT_ERR_INVALID, "lmc_scatter: arguments");
+  for (int64_t i = 0; i < n; i++)
+    if (ids[i] < 0 || ids[i] >= S->n)
+      return set_error(DRRT_ERR_INVALID, "lmc_scatter: node id %d at %lld", ids[i], (long long)i);
+  if (n == 0) return DRRT_OK;
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(lmc_mirror_cover(S, st));
+  DRRT_CHECK(S->i_stage.reserve(n, st));
+  DRRT_CHECK(S->d_stage.reserve(n, st));
+  DRRT_CHECK(upload(ids, S->i_stage.p, n * sizeof(int32_t), st));
+  DRRT_CHECK(upload(values, S->d_stage.p, n * sizeof(double), st));
+  scatter_f64_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(
+      S->x_lmc.p, n, S->i_stage.p, S->d_stage.p);
+  DRRT_LAUNCHED();
+  DRRT_CUDA(cudaGetLastError());
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+int drrt_lmc_read(drrt_store *h, int64_t first, int64_t n, double *values) {
+  ENTER(h);
+  if (first < 0 || n < 0 || first + n > S->n || (n > 0 && !values))
+    return set_error(DRRT_ERR_INVALID, "lmc_read: range");
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(lmc_mirror_cover(S, st));
+  DRRT_CHECK(download(values, S->x_lmc.p + first, n * sizeof(double), st));
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+// ---- pinned host memory for callers without a CUDA toolchain (the shim) -------
+
+int drrt_host_alloc(size_t bytes, void **out) {
+  if (!out) return set_error(DRRT_ERR_INVALID, "host_alloc: out == NULL");
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(DRRT_ERR_NOMEM, "host_alloc(%zu): %s", bytes, cudaGetErrorString(e));
+  }
+  return DRRT_OK;
+}
+
+int drrt_host_free(void *p) {
+  if (p) DRRT_CUDA(cudaFreeHost(p));
   return DRRT_OK;
 }
 

@@ -775,13 +775,13 @@ __global__ void max_radius_kernel(const double *r, int64_t n, unsigned long long
 // ---------------------------------------------------------------------------
 // packing: rows of a sliced result -> plain CSR (exclusive prefix sum of counts)
 
-// single CTA; out[0..n] = exclusive prefix sums of counts (out[n] = total)
-__global__ void scan_counts_kernel(const int32_t *counts, int64_t n, int64_t *out) {
+// single CTA; out[0..n] = base + exclusive prefix sums of counts (out[n] = base + total)
+__global__ void scan_counts_kernel(const int32_t *counts, int64_t n, int64_t *out, long long base) {
   constexpr int T = 1024;
   __shared__ long long s_w[32];
   __shared__ long long s_carry;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) s_carry = 0;
+  if (tid == 0) s_carry = base;
   __syncthreads();
   for (int64_t b = 0; b < n; b += T) {
     const int64_t i = b + tid;
@@ -809,15 +809,18 @@ __global__ void scan_counts_kernel(const int32_t *counts, int64_t n, int64_t *ou
   if (tid == 0) out[n] = s_carry;
 }
 
+// DT: double (the reference's JList key, bit-exact), float (narrow rows: the north star asks
+// for distances within 1e-5 relative) or void (ids only)
+template <typename DT>
 __global__ void pack_rows_kernel(int64_t nq, const int64_t *src_off, const int32_t *counts,
-                                 const int64_t *dst_off, const int32_t *ids, const double *dist,
-                                 int32_t *ids_out, double *dist_out) {
+                                 const int64_t *dst_off, int64_t dst_base, const int32_t *ids,
+                                 const double *dist, int32_t *ids_out, DT *dist_out) {
   for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
-    const int64_t s = src_off[q], d = dst_off[q];
+    const int64_t s = src_off[q], d = dst_off[q] - dst_base;
     const int c = counts[q];
     for (int i = threadIdx.x; i < c; i += blockDim.x) {
       ids_out[d + i] = ids[s + i];
-      dist_out[d + i] = dist[s + i];
+      if constexpr (!std::is_void<DT>::value) dist_out[d + i] = (DT)dist[s + i];
     }
   }
 }
@@ -834,18 +837,27 @@ static void fill_result(Store *S, drrt_range_result *out) {
   out->extent = out->packed ? S->last_total : S->last_extent;
 }
 
-int range_pack_to(Store *S, cudaStream_t st, int64_t *off_out, int32_t *ids_out, double *dist_out) {
+int range_pack_to(Store *S, cudaStream_t st, int64_t *off_out, int32_t *ids_out, void *dist_out,
+                  int dist_kind, int64_t base) {
   if (S->last_nq < 0) return set_error(DRRT_ERR_STATE, "pack: no range batch on this handle");
   const int64_t nq = S->last_nq;
   if (nq == 0) return DRRT_OK;
-  scan_counts_kernel<<<1, 1024, 0, st>>>(S->r_counts.p, nq, off_out);
+  scan_counts_kernel<<<1, 1024, 0, st>>>(S->r_counts.p, nq, off_out, (long long)base);
   DRRT_LAUNCHED();
   if (S->last_total > 0) {
     const int32_t *ids = S->last_packed_in_alt ? S->r_ids2.p : S->r_ids.p;
     const double *dist = S->last_packed_in_alt ? S->r_dist2.p : S->r_dist.p;
     const int64_t *off = S->last_packed_in_alt ? S->r_offsets2.p : S->r_offsets.p;
-    pack_rows_kernel<<<(unsigned)std::min<int64_t>(nq, 148 * 16), 256, 0, st>>>(
-        nq, off, S->r_counts.p, off_out, ids, dist, ids_out, dist_out);
+    const unsigned grid = (unsigned)std::min<int64_t>(nq, 148 * 16);
+    if (dist_kind == DIST_F64 && dist_out)
+      pack_rows_kernel<double><<<grid, 256, 0, st>>>(nq, off, S->r_counts.p, off_out, base, ids, dist,
+                                                     ids_out, (double *)dist_out);
+    else if (dist_kind == DIST_F32 && dist_out)
+      pack_rows_kernel<float><<<grid, 256, 0, st>>>(nq, off, S->r_counts.p, off_out, base, ids, dist,
+                                                    ids_out, (float *)dist_out);
+    else
+      pack_rows_kernel<void><<<grid, 256, 0, st>>>(nq, off, S->r_counts.p, off_out, base, ids, dist,
+                                                   ids_out, (void *)nullptr);
     DRRT_LAUNCHED();
   }
   DRRT_CUDA(cudaGetLastError());
@@ -860,7 +872,7 @@ int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out) {
     DRRT_CHECK(S->r_offsets2.reserve(nq + 1, st));
     DRRT_CHECK(S->r_ids2.reserve(S->last_total + 1, st));
     DRRT_CHECK(S->r_dist2.reserve(S->last_total + 1, st));
-    DRRT_CHECK(range_pack_to(S, st, S->r_offsets2.p, S->r_ids2.p, S->r_dist2.p));
+    DRRT_CHECK(range_pack_to(S, st, S->r_offsets2.p, S->r_ids2.p, S->r_dist2.p, DIST_F64, 0));
     S->last_packed_in_alt = true;
   }
   fill_result(S, out);
@@ -962,7 +974,8 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
       S->last_nq = nq;
       S->last_total = total;
       S->last_extent = extent;
-      S->last_packed = A.chunk_base != nullptr;
+      // exact slices are back to back; a lone slice starts at 0 with its rows back to back
+      S->last_packed = A.chunk_base != nullptr || nchunks == 1;
       fill_result(S, out);
       return DRRT_OK;
     }

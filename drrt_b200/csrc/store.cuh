@@ -82,6 +82,9 @@ struct Store {
   DevBuf<double> p_dist[2];
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  // pipelined host edge checks: poses up on copy_stream, kernels on stream, verdicts down on down_stream
+  cudaStream_t down_stream = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   int32_t *d_ticket = nullptr;
   unsigned long long *d_totals = nullptr;  // inside the d_ticket allocation
   int range_grid[2] = {0, 0};  // resident grid of range_warp_kernel / range_cta_kernel on THIS device
@@ -128,6 +131,7 @@ struct Store {
   const double *csr_dist = nullptr;
   int64_t csr_nq = 0;
   int64_t last_extend_total = -1;
+  int64_t lmc_n = 0;  // entries of x_lmc that are current (the rest of the store reads INF once covered)
   // solved Dubins paths handed from the solve kernel to the walk kernel
   DevBuf<unsigned char> edge_paths;
   // ranked solve: candidate list per edge, edges permuted by list, bin counters
@@ -153,8 +157,19 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
                     double radius_all, cudaStream_t st, drrt_range_result *out);
 int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out);
 // rows of the last result written back to back into caller-chosen device buffers
-// (off_out: nq + 1 exclusive prefix sums of the counts); the handle's result state is untouched
-int range_pack_to(Store *S, cudaStream_t st, int64_t *off_out, int32_t *ids_out, double *dist_out);
+// (off_out: nq + 1 entries, base + exclusive prefix sums of the counts); dist_out holds double,
+// float or nothing (dist_kind); the handle's result state is untouched
+enum { DIST_F64 = 0, DIST_F32 = 1, DIST_NONE = 2 };
+int range_pack_to(Store *S, cudaStream_t st, int64_t *off_out, int32_t *ids_out, void *dist_out,
+                  int dist_kind, int64_t base);
+// capi.cu: host-buffer legs; the caller holds S->mu and has the store's device current
+int range_into(Store *S, int64_t nq, const double *q, const double *radius, double radius_all,
+               int64_t cap, int64_t *offsets, int32_t *ids, void *dist, int dist_kind, int64_t *total);
+int edge_host(Store *S, int64_t n, const double *start, const double *end, const int32_t *sid,
+              const int32_t *eid, int edge_kind, double robot_radius, double r_min, int in_warmup,
+              uint8_t *verdict, double *length);
+int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist, bool nearest);
+int lmc_mirror_cover(Store *S, cudaStream_t st);
 // knn.cu
 int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
                   double *dist_dev, cudaStream_t st, bool nearest = false);

@@ -1,15 +1,18 @@
-"""Multi-GPU plumbing for the hot path: one process per GPU.
+"""Multi-GPU plumbing for the hot path, ONE PROCESS PER GPU (the one-process
+form is drrt_b200.comm / drrt_comm_* in the C ABI).
 
-The node store and obstacle table are REPLICATED -- rank `src` (where the host
-planner lives) broadcasts each insert batch / obstacle table over
-torch.distributed (NCCL over NVLink on GPUs), every rank applies it to its local
-store.  Query and edge batches are SHARDED into contiguous index ranges, one
-per rank, with no collective on the data path; results are gathered back in
-global index order, so answers do not depend on the number of ranks.
+The node store and obstacle table are REPLICATED -- rank `src` (where the host planner lives)
+broadcasts each insert batch / obstacle table over torch.distributed (NCCL over NVLink on
+GPUs) and every rank applies it to its local store straight from the received device tensor.
+Query and edge batches are SHARDED into contiguous index ranges, one per rank, with no
+collective on the data path; the rows are then GATHERED TO `src` ONLY, in global index order
+(point-to-point sends of exactly each shard's size: nothing is padded and nothing is delivered
+to ranks that do not consume it), so answers do not depend on the number of ranks.
 
-The local back end is any object with the KDTree host interface
-(drrt_b200.KDTree on a GPU box).  Collectives use CUDA tensors under NCCL and
-CPU tensors under gloo.
+The local back end is any object with the KDTree host interface (drrt_b200.KDTree on a GPU
+box; when it also offers the `*_dev` methods and the backend is NCCL, rows stay on the device
+from the kernel to the gather).  Collectives use CUDA tensors under NCCL and CPU tensors under
+gloo.
 """
 import numpy as np
 import torch
@@ -29,8 +32,14 @@ def _device():
     return torch.device("cpu")
 
 
-def broadcast_array(arr, src=0, dtype=np.float64):
-    """numpy array from rank src to every rank (shape travels first)"""
+def _as_tensor(a, dev):
+    if torch.is_tensor(a):
+        return a if a.device == dev else a.to(dev)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def broadcast_tensor(arr, src=0, dtype=np.float64):
+    """array held by rank src -> the same tensor on every rank's device (shape travels first)"""
     dev = _device()
     rank = dist.get_rank()
     if rank == src:
@@ -48,41 +57,62 @@ def broadcast_array(arr, src=0, dtype=np.float64):
         t = torch.empty(shape, dtype=torch.from_numpy(np.empty(0, dtype=dtype)).dtype, device=dev)
     if t.numel():
         dist.broadcast(t, src=src)
-    return t.cpu().numpy()
+    return t
 
 
-def all_gather_varlen(arr):
-    """concatenation over ranks (rank order) of 1-D/2-D arrays with different leading sizes"""
+def broadcast_array(arr, src=0, dtype=np.float64):
+    return broadcast_tensor(arr, src, dtype).cpu().numpy()
+
+
+def gather_rows(t, dst=0):
+    """Concatenation over ranks (rank order) of tensors with different leading sizes, delivered
+    to rank dst ONLY (None elsewhere).  The sizes travel in one tiny all_gather; the payload in
+    one send per rank of exactly its size."""
     dev = _device()
-    world = dist.get_world_size()
-    arr = np.ascontiguousarray(arr)
-    n = torch.tensor([arr.shape[0]], dtype=torch.int64, device=dev)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    t = _as_tensor(t, dev).contiguous()
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, n)
     sizes = [int(s.item()) for s in sizes]
-    mx = max(sizes) if sizes else 0
-    pad = np.zeros((mx,) + arr.shape[1:], dtype=arr.dtype)
-    pad[:arr.shape[0]] = arr
-    t = torch.from_numpy(pad).to(dev)
-    outs = [torch.empty_like(t) for _ in range(world)]
-    if mx:
-        dist.all_gather(outs, t)
-    return np.concatenate([o.cpu().numpy()[:s] for o, s in zip(outs, sizes)], axis=0)
+    if rank != dst:
+        if sizes[rank]:
+            dist.send(t, dst)
+        return None
+    out = torch.empty((sum(sizes),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+    at = 0
+    for r, s in enumerate(sizes):
+        if s:
+            if r == rank:
+                out[at:at + s] = t
+            else:
+                dist.recv(out[at:at + s], r)
+        at += s
+    return out
+
+
+def _host(t):
+    return None if t is None else t.cpu().numpy()
 
 
 class ReplicatedKDTree:
-    """The reference's KDTree interface over N replicas of the node store."""
+    """The reference's KDTree interface over N replicas of the node store.  Every rank passes
+    the same global batch to the query methods; rank `src` gets the global answer, the other
+    ranks get None."""
 
     def __init__(self, local_tree, src=0):
         self.local = local_tree
         self.src = src
         self.rank = dist.get_rank()
         self.world = dist.get_world_size()
+        self.on_device = dist.get_backend() == "nccl" and hasattr(local_tree, "KDFindWithinRange_dev")
 
-    # KDTree::KDInsert on every replica: NCCL broadcast of the insert batch
+    # KDTree::KDInsert on every replica: NCCL broadcast of the insert batch, consumed in place
     def KDInsert(self, positions=None):
-        pos = broadcast_array(positions if self.rank == self.src else None, self.src)
-        return self.local.KDInsert(pos)
+        t = broadcast_tensor(positions if self.rank == self.src else None, self.src).reshape(-1, 3)
+        if self.on_device:
+            return self.local.KDInsert_dev(t.contiguous())
+        return self.local.KDInsert(t.cpu().numpy())
 
     def SetObstacles(self, table=None):
         keys = ("kind", "used", "life_span", "origin", "radius", "vert_off", "verts")
@@ -94,29 +124,42 @@ class ReplicatedKDTree:
 
     # KDTree::KDFindWithinRange, query batch sharded by contiguous index range
     def KDFindWithinRange(self, range_, query_points):
-        """every rank passes the same global batch; returns the global CSR"""
         q = np.ascontiguousarray(query_points, dtype=np.float64).reshape(-1, 3)
         lo, hi = shard_bounds(len(q), self.rank, self.world)
         r = range_ if np.ndim(range_) == 0 else np.asarray(range_, dtype=np.float64)[lo:hi]
-        off, ids, dst = self.local.KDFindWithinRange(r, q[lo:hi])
-        counts = all_gather_varlen(np.diff(off).astype(np.int64))
-        ids = all_gather_varlen(ids)
-        dst = all_gather_varlen(dst)
-        goff = np.zeros(len(q) + 1, dtype=np.int64)
-        np.cumsum(counts, out=goff[1:])
-        return goff, ids, dst
+        if self.on_device:
+            dev = _device()
+            rq = torch.from_numpy(np.ascontiguousarray(q[lo:hi])).to(dev)
+            rr = r if np.ndim(r) == 0 else torch.from_numpy(np.ascontiguousarray(r)).to(dev)
+            self.local.KDFindWithinRange_dev(rr, rq)
+            res = self.local.range_pack()
+            _, ids_t, dst_t = self.local.range_result_tensors(res)
+            counts_t = self.local.range_result_counts(res).to(torch.int64)
+            ids_t, dst_t = ids_t[:res.total], dst_t[:res.total]
+        else:
+            off, ids_t, dst_t = self.local.KDFindWithinRange(r, q[lo:hi])
+            counts_t = np.diff(off).astype(np.int64)
+        counts = gather_rows(counts_t, self.src)
+        ids = gather_rows(ids_t, self.src)
+        dst = gather_rows(dst_t, self.src)
+        if self.rank != self.src:
+            return None
+        goff = torch.zeros(len(q) + 1, dtype=torch.int64, device=counts.device)
+        torch.cumsum(counts, 0, out=goff[1:])
+        return _host(goff), _host(ids), _host(dst)
+
+    def _sharded(self, fn, query_points):
+        q = np.ascontiguousarray(query_points, dtype=np.float64).reshape(-1, 3)
+        lo, hi = shard_bounds(len(q), self.rank, self.world)
+        outs = fn(q[lo:hi])
+        got = [gather_rows(o, self.src) for o in outs]
+        return None if self.rank != self.src else tuple(_host(g) for g in got)
 
     def KDFindNearest(self, query_points):
-        q = np.ascontiguousarray(query_points, dtype=np.float64).reshape(-1, 3)
-        lo, hi = shard_bounds(len(q), self.rank, self.world)
-        ids, dst = self.local.KDFindNearest(q[lo:hi])
-        return all_gather_varlen(ids), all_gather_varlen(dst)
+        return self._sharded(self.local.KDFindNearest, query_points)
 
     def KDFindKNearest(self, k, query_points):
-        q = np.ascontiguousarray(query_points, dtype=np.float64).reshape(-1, 3)
-        lo, hi = shard_bounds(len(q), self.rank, self.world)
-        ids, dst = self.local.KDFindKNearest(k, q[lo:hi])
-        return all_gather_varlen(ids), all_gather_varlen(dst)
+        return self._sharded(lambda q: self.local.KDFindKNearest(k, q), query_points)
 
     # ExplicitEdgeCheck over a sharded edge batch
     def ExplicitEdgeCheck(self, start, end, **kw):
@@ -124,4 +167,5 @@ class ReplicatedKDTree:
         e = np.ascontiguousarray(end, dtype=np.float64).reshape(-1, 3)
         lo, hi = shard_bounds(len(s), self.rank, self.world)
         v, ln = self.local.ExplicitEdgeCheck(s[lo:hi], e[lo:hi], **kw)
-        return all_gather_varlen(v), all_gather_varlen(ln)
+        gv, gl = gather_rows(v, self.src), gather_rows(ln, self.src)
+        return None if self.rank != self.src else (_host(gv), _host(gl))

@@ -177,7 +177,8 @@ class KDTree:
 
     def KDFindWithinRangeInto(self, range_, query_points, offsets, ids, dist=None):
         """The same query in one streamed call into caller buffers (numpy arrays or pinned
-        CPU torch tensors: offsets int64[nq+1], ids int32[cap], dist f64[cap] or None).
+        CPU torch tensors: offsets int64[nq+1], ids int32[cap], dist f64[cap], f32[cap] -- the
+        narrow rows of drrt_range_batch_into_f32 -- or None for the id sets alone).
         -> total hits.  Raises DrrtError(ERR_CAPACITY) when the rows do not fit; offsets
         are complete then, so the retry can be sized."""
         q = _f64(query_points, (-1, 3))
@@ -200,13 +201,16 @@ class KDTree:
 
         op, on = host_ptr(offsets, capi.c_i64p, np.int64)
         ip, cap = host_ptr(ids, c_ip, np.int32)
-        dp, dn = host_ptr(dist, c_dp, np.float64)
+        # dist: float64 (the reference's JList key, bit-exact) or float32 (narrow rows) or None
+        f32 = dist is not None and (dist.dtype == np.float32 if isinstance(dist, np.ndarray)
+                                    else str(dist.dtype) == "torch.float32")
+        dp, dn = host_ptr(dist, capi.c_fp if f32 else c_dp, np.float32 if f32 else np.float64)
         assert on >= nq + 1 and (dist is None or dn >= cap)
         total = C.c_int64()
+        fn = self._lib.drrt_range_batch_into_f32 if f32 else self._lib.drrt_range_batch_into
         with self._lock:
-            check(self._lib.drrt_range_batch_into(self._h, nq, _ptr(q, c_dp),
-                                                  _ptr(rad, c_dp) if rad is not None else None,
-                                                  r_all, cap, op, ip, dp, C.byref(total)))
+            check(fn(self._h, nq, _ptr(q, c_dp), _ptr(rad, c_dp) if rad is not None else None,
+                     r_all, cap, op, ip, dp, C.byref(total)))
         return total.value
 
     # KDFindMoreWithinRange kdtree.cpp:822-851 is the same search; the caller's
@@ -415,6 +419,43 @@ class KDTree:
         np.cumsum(counts, out=off[1:])
         return dict(offsets=off, ids=ids, dist=dist, unsafe=unsafe, length=length, best_parent=best,
                     best_cost=cost)
+
+    # -- device mirror of KDTreeNode::rrt_LMC_ (kdtreenode.h:35-73), read by Extend(lmc=None)
+    def WriteLMC(self, first, values):
+        v = _f64(values)
+        check(self._lib.drrt_lmc_write(self._h, int(first), v.size, _ptr(v, c_dp)))
+
+    def ScatterLMC(self, ids, values):
+        i = np.ascontiguousarray(ids, dtype=np.int32)
+        v = _f64(values)
+        assert i.size == v.size
+        check(self._lib.drrt_lmc_scatter(self._h, i.size, _ptr(i, c_ip), _ptr(v, c_dp)))
+
+    def ReadLMC(self, first=0, n=None):
+        n = self.tree_size_ - first if n is None else n
+        v = np.empty(n, dtype=np.float64)
+        check(self._lib.drrt_lmc_read(self._h, int(first), n, _ptr(v, c_dp)))
+        return v
+
+    def ExtendParents(self, range_, new_points, robot_radius=0.5, r_min=1.0, in_warmup=False):
+        """What FindBestParent needs back on the host (drrt.cpp:367-460) and nothing else: the
+        neighbour COUNT, the best parent and its cost per new node, reduced against the device
+        mirror of rrt_LMC_ -- the neighbour rows and their 2 x hits edge verdicts never cross PCIe.
+        -> (counts int32[nq], best_parent int32[nq], best_cost f64[nq], total)"""
+        q = _f64(new_points, (-1, 3))
+        nq = q.shape[0]
+        rad, r_all = (None, float(range_)) if np.ndim(range_) == 0 else (_f64(range_, (nq,)), 0.0)
+        counts = np.zeros(nq, dtype=np.int32)
+        best = np.full(nq, -1, dtype=np.int32)
+        cost = np.zeros(nq, dtype=np.float64)
+        total = C.c_int64()
+        with self._lock:
+            check(self._lib.drrt_extend_batch(self._h, nq, _ptr(q, c_dp),
+                                              _ptr(rad, c_dp) if rad is not None else None, r_all,
+                                              float(robot_radius), float(r_min), int(in_warmup), None,
+                                              _ptr(counts, c_ip), C.byref(total), _ptr(best, c_ip),
+                                              _ptr(cost, c_dp)))
+        return counts, best, cost, total.value
 
     def Extend_dev(self, range_, new_points, lmc=None, best_parent=None, best_cost=None,
                    robot_radius=0.5, r_min=1.0):

@@ -31,7 +31,44 @@ struct ShimState {
   drrt_store *h = nullptr;
   std::vector<std::shared_ptr<KDTreeNode>> by_id;  // device id -> host node
   bool failed = false;
-  std::mutex pair_mu;  // drrt_range_batch + drrt_range_fetch travel together
+  std::mutex row_mu;  // guards the reusable result row below
+  // One reusable PINNED result row (drrt_host_alloc): the planner asks one query per
+  // iteration (mainloop.cpp:204-210, drrt.cpp:213-216), so the whole call is one
+  // drrt_range_batch_into -- one kernel, the row DMA'd straight into this buffer.
+  double *q_pin = nullptr;
+  int64_t *off_pin = nullptr;
+  int32_t *ids_pin = nullptr;
+  double *dist_pin = nullptr;
+  int64_t cap = 0;
+
+  bool reserve_row(int64_t need) {
+    if (need <= cap && q_pin) return true;
+    int64_t ncap = cap ? cap : 4096;
+    while (ncap < need) ncap *= 2;
+    void *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr;
+    if (drrt_host_alloc((size_t)ncap * sizeof(int32_t), &a) != DRRT_OK ||
+        drrt_host_alloc((size_t)ncap * sizeof(double), &b) != DRRT_OK ||
+        (!q_pin && (drrt_host_alloc(4 * sizeof(double), &c) != DRRT_OK ||
+                    drrt_host_alloc(2 * sizeof(int64_t), &d) != DRRT_OK))) {
+      drrt_host_free(a); drrt_host_free(b); drrt_host_free(c); drrt_host_free(d);
+      return false;
+    }
+    drrt_host_free(ids_pin);
+    drrt_host_free(dist_pin);
+    ids_pin = (int32_t *)a;
+    dist_pin = (double *)b;
+    if (!q_pin) { q_pin = (double *)c; off_pin = (int64_t *)d; }
+    cap = ncap;
+    return true;
+  }
+  void release() {
+    if (h) drrt_store_destroy(h);
+    h = nullptr;
+    drrt_host_free(q_pin); drrt_host_free(off_pin); drrt_host_free(ids_pin); drrt_host_free(dist_pin);
+    q_pin = nullptr; off_pin = nullptr; ids_pin = nullptr; dist_pin = nullptr;
+    cap = 0;
+    by_id.clear();
+  }
 };
 
 std::mutex g_mu;
@@ -59,9 +96,7 @@ ShimState &state_of(KDTree *t) {
   // a tree that says it is empty while this state still holds nodes is a NEW tree -- drop the old
   // device store and node table instead of answering from them.
   if (t->tree_size_ == 0 && !s.by_id.empty()) {
-    if (s.h) drrt_store_destroy(s.h);
-    s.h = nullptr;
-    s.by_id.clear();
+    s.release();
     s.failed = false;
   }
   if (!s.h && !s.failed) {
@@ -288,15 +323,24 @@ void KDTree::EmptyRangeList(std::shared_ptr<JList> &S) {
 void KDTree::KDFindWithinRange(std::shared_ptr<JList> &S, double range, Eigen::VectorXd queryPoint) {
   ShimState &s = state_of(this);
   if (s.failed) return;
-  double q[3] = {queryPoint(0), queryPoint(1), queryPoint(2)};
-  std::lock_guard<std::mutex> pair(s.pair_mu);
-  int32_t count = 0;
-  int64_t total = 0;
-  if (!ok(drrt_range_batch(s.h, 1, q, nullptr, range, &count, &total), "KDFindWithinRange")) return;
-  std::vector<int32_t> ids((size_t)total);
-  std::vector<double> dist((size_t)total);
-  if (!ok(drrt_range_fetch(s.h, ids.data(), dist.data()), "KDFindWithinRange")) return;
-  for (int64_t i = 0; i < total; i++) AddToRangeList(S, s.by_id[ids[i]], dist[i]);
+  std::lock_guard<std::mutex> row(s.row_mu);
+  if (!s.reserve_row(1)) { std::cout << "drrt_gpu: KDFindWithinRange: " << drrt_last_error() << std::endl; return; }
+  s.q_pin[0] = queryPoint(0); s.q_pin[1] = queryPoint(1); s.q_pin[2] = queryPoint(2);
+  // ONE C-ABI call per query; the row buffer grows (rarely: the RRTx ball shrinks as the
+  // tree grows, drrt.cpp:16-27) when the call reports how many hits there are
+  for (int attempt = 0; attempt < 2; attempt++) {
+    int64_t total = 0;
+    int rc = drrt_range_batch_into(s.h, 1, s.q_pin, nullptr, range, s.cap, s.off_pin, s.ids_pin,
+                                   s.dist_pin, &total);
+    if (rc == DRRT_ERR_CAPACITY && attempt == 0) {
+      if (!s.reserve_row(total)) break;
+      continue;
+    }
+    if (!ok(rc, "KDFindWithinRange")) return;
+    for (int64_t i = 0; i < total; i++) AddToRangeList(S, s.by_id[s.ids_pin[i]], s.dist_pin[i]);
+    return;
+  }
+  std::cout << "drrt_gpu: KDFindWithinRange: " << drrt_last_error() << std::endl;
 }
 
 // kdtree.cpp:822-851: same search, accumulating into the caller's list
@@ -331,6 +375,6 @@ void DrrtGpuRelease(KDTree *t) {
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_state.find(t);
   if (it == g_state.end()) return;
-  if (it->second.h) drrt_store_destroy(it->second.h);
+  it->second.release();
   g_state.erase(it);
 }

@@ -24,13 +24,15 @@
 #ifndef DRRT_GPU_H
 #define DRRT_GPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define DRRT_ABI_VERSION 3 /* 3: drrt_range_batch_into, DRRT_ERR_CAPACITY */
+#define DRRT_ABI_VERSION 4 /* 4: narrow rows, rrt_LMC_ mirror, drrt_comm_* (N GPUs, one process),
+                             stored-edge CSR, obstacle moves; 3: drrt_range_batch_into */
 
 #if defined(__GNUC__)
 #define DRRT_API __attribute__((visibility("default")))
@@ -126,6 +128,19 @@ DRRT_API int drrt_range_batch_into(drrt_store *h, int64_t nq, const double *q,
                           const double *radius, double radius_all, int64_t cap,
                           int64_t *offsets, int32_t *ids, double *dist,
                           int64_t *total);
+
+/* Narrow rows, opt-in: the same call with the distances rounded to float (ids bit-exact;
+ * the north star asks for distances within 1e-5 relative, a float carries 6e-8) -- 8 instead
+ * of 12 bytes per hit cross PCIe, which is what bounds the host call.  dist == NULL in either
+ * form returns the id sets alone (4 bytes per hit). */
+DRRT_API int drrt_range_batch_into_f32(drrt_store *h, int64_t nq, const double *q,
+                              const double *radius, double radius_all, int64_t cap,
+                              int64_t *offsets, int32_t *ids, float *dist, int64_t *total);
+
+/* pinned (page-locked, portable) host memory for callers without a CUDA toolchain, e.g. the
+ * C++ shim: result buffers in it are written by DMA straight from the device */
+DRRT_API int drrt_host_alloc(size_t bytes, void **out);
+DRRT_API int drrt_host_free(void *p);
 
 /* device-resident variant: queries/radii on the device; results stay in
  * library-owned device buffers valid until the next range call on h.
@@ -238,13 +253,24 @@ DRRT_API int drrt_obstacle_conflict_batch(drrt_store *h, int32_t n_sel,
  * collision-checked, and the parent chosen as the safe new->near edge that
  * minimises near.rrt_LMC_ + edge.dist_ (:444-449).  Here for nq new nodes at
  * once, the neighbour lists never leaving the device between the two stages.
- *   lmc          rrt_LMC_ of every node in the store (host array, store-size
- *                entries) or NULL to skip the parent reduction
+ *   lmc          rrt_LMC_ of every node in the store (host array, store-size entries,
+ *                uploaded whole), or NULL: use the device mirror (drrt_lmc_write /
+ *                drrt_lmc_scatter); with best_parent == NULL no reduction is done
  *   counts/total as drrt_range_batch
  *   best_parent  node id per query (-1: no safe neighbour), best_cost its
  *                near.lmc + length (INF = 1e12 when none); ties: smaller id
  * drrt_extend_fetch returns the rows (ids, dist as drrt_range_fetch) and, per
  * neighbour t, unsafe[2t], length[2t] for new->near and [2t+1] for near->new. */
+/* Device mirror of KDTreeNode::rrt_LMC_ (include/DRRT/kdtreenode.h:35-73; read by
+ * FindBestParent src/drrt.cpp:444-446, written by RecalculateLMC / Rewire :570-780).  One
+ * entry per node of the store; nodes never written hold INF = 1e12, the value a new node
+ * carries until it gets a parent (drrt.cpp:391).  The planner sends the entries it changed
+ * (write: a contiguous id range, scatter: listed ids) instead of the whole array per call;
+ * drrt_extend_batch with lmc == NULL and best_parent != NULL reduces against the mirror. */
+DRRT_API int drrt_lmc_write(drrt_store *h, int64_t first, int64_t n, const double *values);
+DRRT_API int drrt_lmc_scatter(drrt_store *h, int64_t n, const int32_t *ids, const double *values);
+DRRT_API int drrt_lmc_read(drrt_store *h, int64_t first, int64_t n, double *values);
+
 DRRT_API int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const double *radius,
                       double radius_all, double robot_radius, double r_min, int in_warmup,
                       const double *lmc, int32_t *counts, int64_t *total,
@@ -275,6 +301,56 @@ DRRT_API int drrt_pointcheck_batch(drrt_store *h, int64_t n, const double *pts,
 DRRT_API int drrt_pointcheck_batch_dev(drrt_store *h, int64_t n, const double *pts_dev,
                               double robot_radius, double collision_distance,
                               uint8_t *verdict_dev, void *stream);
+
+/* ---- N GPUs behind one handle, one host process --------------------
+ * The reference planner is one process whose threads share one KDTree and one ConfigSpace
+ * (src/smalltest.cpp:37-39, 132-142).  drrt_comm keeps one REPLICA of the node store (and of the
+ * obstacle table and the rrt_LMC_ mirror) per GPU:
+ *   - drrt_comm_insert / drrt_comm_lmc_*: the data crosses PCIe once, to the first GPU, and
+ *     reaches the others by ncclBroadcast over NVLink (ncclCommInitAll, one communicator per GPU
+ *     in this process; libnccl.so.2 is loaded at run time);
+ *   - query and edge batches are SHARDED into contiguous index ranges, one per GPU, with no
+ *     exchange step inside a query or an edge check; every GPU copies its rows straight into
+ *     the caller's buffers at its global offset (the sum of the preceding shards' hit totals).
+ * Results are identical for every GPU count (ids are insertion indices, rows sorted by id).
+ * devices == NULL: GPUs 0 .. n_gpus-1.  The other arguments are drrt_store_create's.  Calls on
+ * one comm are serialised; the entry points mirror the single-store ones of the same name. */
+typedef struct drrt_comm drrt_comm;
+DRRT_API int drrt_comm_init(int n_gpus, const int *devices, int dims, int n_wraps,
+                   const int *wrap_dims, const double *wrap_points, int metric,
+                   int64_t capacity_hint, drrt_comm **out);
+DRRT_API int drrt_comm_destroy(drrt_comm *c);
+DRRT_API int drrt_comm_size(drrt_comm *c, int *n_gpus);
+DRRT_API drrt_store *drrt_comm_store(drrt_comm *c, int rank); /* replica `rank` (owned by c) */
+DRRT_API int64_t drrt_comm_broadcast_bytes(drrt_comm *c);     /* bytes delivered by ncclBroadcast so far */
+DRRT_API int drrt_comm_insert(drrt_comm *c, int64_t n, const double *pos, int32_t *first_id);
+DRRT_API int drrt_comm_obstacles_set(drrt_comm *c, int32_t n_obs, const int32_t *kind,
+                   const uint8_t *used, const double *life_span, const double *origin_xy,
+                   const double *radius, const int32_t *vert_off, const double *verts_xy);
+DRRT_API int drrt_comm_range_batch_into(drrt_comm *c, int64_t nq, const double *q,
+                   const double *radius, double radius_all, int64_t cap, int64_t *offsets,
+                   int32_t *ids, double *dist, int64_t *total);
+DRRT_API int drrt_comm_range_batch_into_f32(drrt_comm *c, int64_t nq, const double *q,
+                   const double *radius, double radius_all, int64_t cap, int64_t *offsets,
+                   int32_t *ids, float *dist, int64_t *total);
+DRRT_API int drrt_comm_nearest_batch(drrt_comm *c, int64_t nq, const double *q, int32_t *ids,
+                   double *dist);
+DRRT_API int drrt_comm_knn_batch(drrt_comm *c, int64_t nq, const double *q, int k, int32_t *ids,
+                   double *dist);
+DRRT_API int drrt_comm_edgecheck_batch(drrt_comm *c, int64_t n, const double *start,
+                   const double *end, int edge_kind, double robot_radius, double r_min,
+                   int in_warmup, uint8_t *verdict, double *length);
+DRRT_API int drrt_comm_edgecheck_ids_batch(drrt_comm *c, int64_t n, const int32_t *start_id,
+                   const int32_t *end_id, int edge_kind, double robot_radius, double r_min,
+                   int in_warmup, uint8_t *verdict, double *length);
+DRRT_API int drrt_comm_pointcheck_batch(drrt_comm *c, int64_t n, const double *pts,
+                   double robot_radius, double collision_distance, uint8_t *verdict);
+DRRT_API int drrt_comm_lmc_write(drrt_comm *c, int64_t first, int64_t n, const double *values);
+DRRT_API int drrt_comm_lmc_scatter(drrt_comm *c, int64_t n, const int32_t *ids, const double *values);
+DRRT_API int drrt_comm_extend_batch(drrt_comm *c, int64_t nq, const double *q, const double *radius,
+                   double radius_all, double robot_radius, double r_min, int in_warmup,
+                   const double *lmc, int32_t *counts, int64_t *total, int32_t *best_parent,
+                   double *best_cost);
 
 #ifdef __cplusplus
 }

@@ -193,3 +193,23 @@ def range_time(pos, q, rad, warm=0, timed=1, metric=0, wrap=True):
 
 def edge_time(start, end, obstacles, r_min=1.0, robot_radius=0.5, metric=0):
     return parse_time(_run("edgecheck_time", edge_time_payload(start, end, obstacles, r_min, robot_radius, metric)))
+
+
+def loop_time(obstacles, iters, mode=0, seed=0xD2270011, delta=5.0, gamma=100.0, r_min=1.0,
+              robot_radius=0.5, metric=0, binary=None):
+    """`loop_time`: the planner iteration of BASELINE config 1 over the reference's own objects
+    (ref_driver.cpp cmd_loop).  binary: BIN (all-CPU reference) or SHIM_BIN (tree calls and
+    checks on the GPU; mode 0 = one ExplicitEdgeCheck call per edge, 1 = one call per iteration).
+    -> dict(nodes, hits, edges, collisions, blocked, key_sum, len_sum, seconds)"""
+    global BIN
+    payload = (struct.pack("<idd", metric, r_min, robot_radius) + _obs_payload(obstacles or EMPTY_OBS)
+               + struct.pack("<iiqdd", int(iters), int(mode), int(seed), delta, gamma))
+    old = BIN
+    if binary:
+        BIN = binary
+    try:
+        raw = _run("loop_time", payload)
+    finally:
+        BIN = old
+    v = struct.unpack_from("<qqqqqqdd", raw, 0)
+    return dict(zip(("nodes", "hits", "edges", "collisions", "blocked", "key_sum", "len_sum", "seconds"), v))

@@ -21,6 +21,7 @@
 #include <DRRT/drrt.h>
 #include <DRRT/thetastar.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -401,6 +402,116 @@ static int cmd_obsfile(const char *cmd, Reader &in, Writer &out) {
   return 0;
 }
 
+// ---- config 1: the planner iteration, timed (bench.py / benchmarks/inloop.py) -----------
+// One iteration = what RrtMainLoop + Extend do on the hot path (mainloop.cpp:204-256,
+// drrt.cpp:213-293): sample -> KDFindNearest -> Edge::Saturate -> ExplicitNodeCheck ->
+// KDFindWithinRange -> for every neighbour NewEdge + CalculateTrajectory + ExplicitEdgeCheck in
+// both directions -> KDInsert -> EmptyRangeList, over the reference's own KDTree / JList / Edge
+// objects with the parameter block of src/smalltest.cpp:180-220.  drrt_ref runs the reference's
+// kdtree.cpp and the analytic checker; drrt_shim runs the SAME loop with kdtree.cpp swapped for
+// the shim (every tree call lands in the CUDA library) and the checks through the shim's
+// ExplicitEdgeCheckGpu (mode 0: one call per edge, the unchanged planner) or
+// ExplicitEdgeCheckBatchGpu (mode 1: the 2|N| edges of an iteration in one call, the
+// INTEGRATION.md patch).  The RNG is a fixed xorshift (the reference's sampler is unseedable).
+static uint64_t g_rng;
+static double urand() {
+  g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17;
+  return (double)(g_rng >> 11) * (1.0 / 9007199254740992.0);
+}
+
+static int cmd_loop(Reader &in, Writer &out) {
+  int metric = in.get<int32_t>();
+  double r_min = in.get<double>(), robot_radius = in.get<double>();
+  shared_ptr<ConfigSpace> C = make_cspace(metric, r_min, robot_radius, 0.1);
+  shared_ptr<KDTree> T = make_tree(metric, 1);
+  std::vector<shared_ptr<Obstacle>> obs = read_obstacles(in, C);
+  int32_t iters = in.get<int32_t>(), mode = in.get<int32_t>();
+  g_rng = (uint64_t)in.get<int64_t>() | 1ull;
+  double delta = in.get<double>(), gamma = in.get<double>();
+  for (size_t o = 0; o < obs.size(); o++) C->obstacles_->ListPush(obs[o]);
+#ifdef DRRT_SHIM
+  // (ListPush prepends: the device table follows the list order, as the checker walks it)
+#endif
+  double root[3] = {0.0, 0.0, -3.0 * PI / 4.0};  // smalltest.cpp:190-196
+  shared_ptr<KDTreeNode> rn = make_shared<KDTreeNode>(vec3(root));
+  T->KDInsert(rn);
+#ifdef DRRT_SHIM
+  DrrtGpuUploadObstacles(T.get(), C);
+#endif
+  int64_t n_hits = 0, n_edges = 0, n_coll = 0, n_blocked = 0, id_sum = 0;
+  double len_sum = 0.0;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int it = 0; it < iters; it++) {
+    const int n = T->tree_size_;
+    double radius = gamma * pow(log(1.0 + n) / (double)n, 1.0 / 3.0);  // the intended exponent
+    if (radius > delta) radius = delta;
+    double sp[3] = {50.0 * urand(), 50.0 * urand(), 2.0 * PI * urand()};
+    shared_ptr<KDTreeNode> nn = make_shared<KDTreeNode>(vec3(sp));
+    shared_ptr<KDTreeNode> closest = make_shared<KDTreeNode>();
+    shared_ptr<double> cd = make_shared<double>(INF);
+    T->KDFindNearest(closest, cd, nn->position_);                       // mainloop.cpp:208
+    double d0 = T->distanceFunction(nn->position_, closest->position_);
+    if (d0 > delta) Edge::Saturate(nn->position_, closest->position_, delta, d0);  // :219
+    bool blocked = false;                                               // :226 ExplicitNodeCheck
+#ifdef DRRT_SHIM
+    blocked = ExplicitNodeCheckGpu(C, T.get(), nn);
+#else
+    for (size_t o = 0; o < obs.size() && !blocked; o++) blocked = QuickCheck2D(C, nn->position_, obs[obs.size() - 1 - o]);
+    for (size_t o = 0; o < obs.size() && !blocked; o++)
+      blocked = ExplicitPointCheck2D(C, obs[obs.size() - 1 - o], nn->position_, C->robot_radius_);
+#endif
+    if (blocked) { n_blocked++; continue; }
+    shared_ptr<JList> S = make_shared<JList>(true);
+    T->KDFindWithinRange(S, radius, nn->position_);                    // drrt.cpp:213-216
+    n_hits += S->length_;
+    std::vector<shared_ptr<Edge>> edges;
+    shared_ptr<JListNode> ln = S->front_;            // drrt.cpp:251-256: length_ steps from front_
+    for (int i = 0; i < S->length_; i++, ln = ln->child_) {
+      shared_ptr<KDTreeNode> near = ln->node_;
+      edges.push_back(Edge::NewEdge(C, T, nn, near));                  // drrt.cpp:405 (FindBestParent)
+      edges.push_back(Edge::NewEdge(C, T, near, nn));                  // drrt.cpp:284
+    }
+    n_edges += (int64_t)edges.size();
+#ifdef DRRT_SHIM
+    if (mode == 1) {
+      std::vector<unsigned char> unsafe;
+      ExplicitEdgeCheckBatchGpu(C, T.get(), edges, unsafe);
+      for (size_t e = 0; e < edges.size(); e++) { n_coll += unsafe[e]; len_sum += edges[e]->dist_; }
+    } else {
+      for (size_t e = 0; e < edges.size(); e++) {
+        n_coll += ExplicitEdgeCheckGpu(C, T.get(), edges[e]) ? 1 : 0;
+        len_sum += edges[e]->dist_;
+      }
+    }
+#else
+    (void)mode;
+    for (size_t e = 0; e < edges.size(); e++) {
+      edges[e]->CalculateTrajectory();                                  // drrt.cpp:411, 286
+      bool hit = false;                                                 // ExplicitEdgeCheck(C, edge) :422, 293
+      shared_ptr<ListNode> on = C->obstacles_->front_;
+      for (int o = 0; o < C->obstacles_->length_ && !hit; o++, on = on->child_)
+        for (int k = 1; k < edges[e]->trajectory_.rows() && !hit; k++)
+          hit = ExplicitEdgeCheck2D(on->obstacle_, edges[e]->trajectory_.row(k - 1), edges[e]->trajectory_.row(k),
+                                    C->robot_radius_);
+      n_coll += hit ? 1 : 0;
+      len_sum += edges[e]->dist_;
+    }
+#endif
+    T->KDInsert(nn);                                                    // drrt.cpp:239-242
+    ln = S->front_;
+    for (int i = 0; i < S->length_; i++, ln = ln->child_) id_sum += (int64_t)(ln->key_ * 1048576.0);
+    T->EmptyRangeList(S);                                               // drrt.cpp:356
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  out.put<int64_t>(T->tree_size_);
+  out.put<int64_t>(n_hits); out.put<int64_t>(n_edges); out.put<int64_t>(n_coll);
+  out.put<int64_t>(n_blocked); out.put<int64_t>(id_sum);
+  out.put<double>(len_sum);
+  out.put<double>((double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec));
+  return 0;
+}
+
 // ---- node validity ------------------------------------------------------------
 static int cmd_points(Reader &in, Writer &out) {
   int metric = in.get<int32_t>();
@@ -450,6 +561,7 @@ int main(int argc, char **argv) {
   if (!strcmp(cmd, "traj") || !strcmp(cmd, "edgecheck") || !strcmp(cmd, "edgecheck_gpu") || !strcmp(cmd, "edgecheck_time"))
     return cmd_edges(cmd, in, out);
   if (!strcmp(cmd, "points")) return cmd_points(in, out);
+  if (!strcmp(cmd, "loop_time")) return cmd_loop(in, out);
   if (!strcmp(cmd, "obsfile")) return cmd_obsfile(cmd, in, out);
   if (!strcmp(cmd, "geom")) return cmd_geom(in, out);
   fprintf(stderr, "unknown command %s\n", cmd);

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(drrt):
         assert hasattr(lib, name), name
     # and the ctypes binding covers the same set
     assert sorted(drrt.capi.SIGNATURES) == declared_symbols()
-    assert lib.drrt_abi_version() == 3
+    assert lib.drrt_abi_version() == drrt.capi.ABI_VERSION == 4
 
 
 def test_library_is_sm100a_cuda_code(drrt):

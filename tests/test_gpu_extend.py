@@ -72,3 +72,49 @@ def test_extend_warmup_and_empty(drrt, po):
     assert out["offsets"][-1] == 0 and (out["best_parent"] == -1).all()
     out = tree.Extend(2.0, new)                               # no lmc: rows only
     assert out["best_parent"] is None and len(out["ids"]) == out["offsets"][-1]
+
+
+def test_extend_against_the_resident_lmc_mirror(drrt, po):
+    """drrt_lmc_write / drrt_lmc_scatter keep a device mirror of rrt_LMC_; drrt_extend_batch with
+    lmc == NULL reduces against it (nothing store-sized crosses PCIe per call) and returns what
+    a whole-array upload returns.  Nodes never written read INF (drrt.cpp:391)."""
+    from drrt_b200 import capi
+    pos = synth.box_points(90_000, 411)
+    tree = drrt.KDTree()
+    tree.KDInsert(pos[:60_000])
+    tree.SetObstacles(**synth.obstacles(96, 412))
+    rng = np.random.default_rng(413)
+    lmc = rng.uniform(0.0, 60.0, 60_000)
+    new = synth.box_points(500, 414)
+    want = tree.Extend(1.2, new, lmc=lmc)
+    # (a) mirror written in two ranges
+    tree.WriteLMC(0, lmc[:25_000])
+    tree.WriteLMC(25_000, lmc[25_000:])
+    assert np.array_equal(tree.ReadLMC(), lmc)
+    cnt, best, cost, total = tree.ExtendParents(1.2, new)
+    assert np.array_equal(cnt, np.diff(want["offsets"])) and total == len(want["ids"])
+    assert np.array_equal(best, want["best_parent"]) and np.array_equal(cost, want["best_cost"])
+    # (b) a rewiring cascade changes some entries: delta update only
+    ch = rng.choice(60_000, 4000, replace=False).astype(np.int32)
+    lmc[ch] = rng.uniform(0.0, 10.0, len(ch))
+    tree.ScatterLMC(ch, lmc[ch])
+    want = tree.Extend(1.2, new, lmc=lmc)
+    cnt, best, cost, _ = tree.ExtendParents(1.2, new)
+    assert np.array_equal(best, want["best_parent"]) and np.array_equal(cost, want["best_cost"])
+    # (c) the store grows: new nodes read INF until written, so they are never chosen
+    tree.KDInsert(pos[60_000:])
+    full = np.concatenate([lmc, np.full(30_000, 1e12)])
+    assert np.array_equal(tree.ReadLMC(), full)
+    want = tree.Extend(1.2, new, lmc=full)
+    cnt, best, cost, _ = tree.ExtendParents(1.2, new)
+    assert np.array_equal(best, want["best_parent"]) and np.array_equal(cost, want["best_cost"])
+    assert (best < 60_000).all()
+    with pytest.raises(drrt.DrrtError):
+        tree.ScatterLMC(np.array([90_000], dtype=np.int32), [1.0])
+    with pytest.raises(ValueError):
+        tree.Extend(1.2, new, lmc=lmc)            # a short host array is refused, not read past its end
+    # a later range call replaces the rows: a late fetch is refused, never served from freed memory
+    tree.Extend(1.2, new, lmc=full)
+    tree.KDFindWithinRange(3.0, new)
+    lib = capi.load()
+    assert lib.drrt_extend_fetch(tree._h, None, None, None, None) == capi.ERR_STATE

@@ -309,3 +309,46 @@ def test_range_streamed_one_call(drrt, po):
     o5 = np.full(1, -1, dtype=np.int64)
     assert t.KDFindWithinRangeInto(1.0, np.empty((0, 3)), o5, np.empty(0, dtype=np.int32), None) == 0
     assert o5[0] == 0
+
+
+def test_range_narrow_rows_and_small_batches(drrt, po):
+    """drrt_range_batch_into_f32 (ids bit-exact, distances rounded to float: 8 B per hit on the
+    wire) and the single-sub-batch path of the host call (the planner's own nq == 1 call,
+    src/drrt.cpp:213-216; rows leave straight from the arena when it is already a plain CSR)."""
+    from drrt_b200 import capi
+    pos = synth.box_points(200_000, 75)
+    t, r = _pair(drrt, po, pos)
+    q = synth.box_points(40_000, 76)                      # streamed: three sub-batches
+    for radius in (0.9, 4.0):
+        nq = len(q) if radius < 1 else 20_000
+        off, ids, dist = t.KDFindWithinRange(radius, q[:nq])
+        o2 = np.full(nq + 1, -1, dtype=np.int64)
+        i2 = np.empty(len(ids), dtype=np.int32)
+        f2 = np.empty(len(ids), dtype=np.float32)
+        assert t.KDFindWithinRangeInto(radius, q[:nq], o2, i2, f2) == len(ids)
+        assert np.array_equal(o2, off) and np.array_equal(i2, ids)
+        assert np.array_equal(f2, dist.astype(np.float32))          # correctly rounded, not truncated
+        assert np.all(np.abs(f2.astype(np.float64) - dist) <= 1e-5 * dist)   # the north star's tolerance
+    # small batches: 1 query (one slice: already packed), 300 warp-mode, 300 CTA-mode queries
+    for nq, radius in ((1, 0.9), (1, 4.0), (300, 0.9), (300, 4.0), (3, 4.0)):
+        roff, rids, rdist = r.range_batch(q[:nq], radius)
+        for dtype in (np.float64, np.float32, None):
+            o = np.full(nq + 1, -1, dtype=np.int64)
+            i = np.empty(len(rids), dtype=np.int32)
+            d = None if dtype is None else np.empty(len(rids), dtype=dtype)
+            assert t.KDFindWithinRangeInto(radius, q[:nq], o, i, d) == len(rids)
+            assert np.array_equal(o, roff) and np.array_equal(i, rids)
+            if dtype is not None:
+                assert np.array_equal(d, rdist.astype(dtype))
+        small = np.empty(max(len(rids) - 1, 0), dtype=np.int32)
+        with pytest.raises(drrt.capi.DrrtError) as ei:
+            t.KDFindWithinRangeInto(radius, q[:nq], o, small, None)
+        assert ei.value.code == capi.ERR_CAPACITY and np.array_equal(o, roff)
+    # per-query radii through the small path
+    rad = np.linspace(0.3, 4.5, 200)
+    roff, rids, rdist = r.range_batch(q[:200], rad)
+    o = np.empty(201, dtype=np.int64)
+    i = np.empty(len(rids), dtype=np.int32)
+    d = np.empty(len(rids), dtype=np.float64)
+    assert t.KDFindWithinRangeInto(rad, q[:200], o, i, d) == len(rids)
+    assert np.array_equal(o, roff) and np.array_equal(i, rids) and np.array_equal(d, rdist)

@@ -92,3 +92,22 @@ def test_obstacle_file_to_device_table(shim, po, tmp_path):
     assert (clr[bad] < 1e-6).all() and len(bad) <= 2
     assert np.allclose(d, rl, rtol=1e-9)
     assert 0.05 < v.mean() < 0.9
+
+
+def test_planner_loop_reference_vs_shim(shim):
+    """BASELINE config 1 through the reference's own objects: the same driver loop (sample ->
+    KDFindNearest -> Saturate -> ExplicitNodeCheck -> KDFindWithinRange -> 2|N| edges -> KDInsert,
+    ref_driver.cpp cmd_loop) once over the reference's kdtree.cpp + analytic checker
+    (oracle/_ref/drrt_ref, all CPU) and once over the shim + libdrrt_b200.so: the same nodes get
+    inserted, every neighbour list has the same keys, the same edges collide."""
+    from drrt_b200 import synth
+    o = synth.obstacles(24, 0xD2270012, lo=8.0, hi=42.0)
+    iters = 1500
+    cpu = shim.loop_time(o, iters, binary=shim.BIN.replace("drrt_shim", "drrt_ref"))
+    for mode in (0, 1):
+        gpu = shim.loop_time(o, iters, mode=mode, binary=shim.SHIM_BIN)
+        for k in ("nodes", "hits", "edges", "blocked", "key_sum"):
+            assert gpu[k] == cpu[k], (mode, k, gpu[k], cpu[k])
+        assert abs(gpu["collisions"] - cpu["collisions"]) <= 2          # edges within 1e-6 of a threshold
+        assert abs(gpu["len_sum"] - cpu["len_sum"]) <= 1e-9 * cpu["len_sum"]
+    assert cpu["nodes"] > 1000 and cpu["edges"] > 20_000 and 0 < cpu["collisions"] < cpu["edges"]
