@@ -517,11 +517,14 @@ def main():
         # ---- config 3: 10 M Dubins edges = the query<->hit pairs of 2b, vs 256 polygons
         off_h, ids_h, _ = tree.KDFindWithinRange(r2b, q_host)
         s_h, e_h = synth.edges_from_neighbours(nodes_h, q_host, off_h, ids_h, N_EDGES)
-        # the same edges named by node id where both ends are nodes: (query -> hit) pairs have a free
-        # pose at one end, so the id form is timed on the hit -> hit' pairs of consecutive hits
+        # the id form needs a node at both ends ((query -> hit) pairs have a free pose at one end): it is
+        # timed on hit -> previous hit of the same 2b row, edges of the same length scale
+        prev = np.arange(len(ids_h), dtype=np.int64) - 1      # the previous hit of the SAME row (cyclic)
+        nz = np.diff(off_h) > 0
+        prev[off_h[:-1][nz]] = off_h[1:][nz] - 1
         ids_a = np.ascontiguousarray(np.resize(ids_h, N_EDGES).astype(np.int32))
-        ids_b = np.ascontiguousarray(np.roll(ids_a, 1))
-        del off_h, ids_h
+        ids_b = np.ascontiguousarray(np.resize(ids_h[prev], N_EDGES).astype(np.int32))
+        del off_h, ids_h, prev, nz
         start = torch.from_numpy(s_h).to(dev)
         end = torch.from_numpy(e_h).to(dev)
         o = synth.obstacles()
@@ -589,7 +592,7 @@ def main():
         e2e["edge_check"] = {"value": world * N_EDGES / sec, "unit": "edges/s", "ms_per_step": 1e3 * sec,
                              "h2d_bytes_per_step": 48 * N_EDGES, "d2h_bytes_per_step": 9 * N_EDGES,
                              "collision_rate": float(v_pin.float().mean().item()),
-                             "call": "drrt_edgecheck_batch (config 3, pinned host poses; 1 Mi-edge chunks: poses up, "
+                             "call": "drrt_edgecheck_batch (config 3, pinned host poses; 2 Mi-edge chunks: poses up, "
                                      "solve + walk, verdicts + lengths down on three streams)"}
         sec = host_timed(e2e_edges_ids, esteps)
         e2e["edge_check_ids"] = {"value": world * N_EDGES / sec, "unit": "edges/s", "ms_per_step": 1e3 * sec,

@@ -46,6 +46,31 @@ def _stamp():
     return h.hexdigest()
 
 
+def build_variant(name, defines):
+    """A/B builds for kernel experiments: the same sources with extra -D flags into
+    drrt_b200/variants/<name>/libdrrt_b200.so (select it with DRRT_B200_LIB=<path>)."""
+    out_dir = os.path.join(HERE, "variants", name)
+    os.makedirs(out_dir, exist_ok=True)
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([nvcc] + NVCC_FLAGS + list(defines) + ["-c", os.path.join(CSRC, src), "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
+    so = os.path.join(out_dir, "libdrrt_b200.so")
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs +
+                          ["-Xcompiler", "-fPIC", "-cudart", "static"])
+    for o in objs:
+        os.remove(o)
+    return so
+
+
 def build(force=False, verbose=False):
     stamp_file = os.path.join(OBJDIR, "stamp")
     stamp = _stamp()
@@ -85,4 +110,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:   # python -m drrt_b200.build --variant NAME -DX=1 -DY=2
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -61,11 +61,39 @@ static int download(void *dst, const void *src, size_t bytes, cudaStream_t st) {
   return DRRT_OK;
 }
 
+int map_reserve(Store *S) {
+  if (S->h_map) return DRRT_OK;
+  cudaError_t e = cudaHostAlloc(&S->h_map, sizeof(MappedRow) + sizeof(MappedSmall),
+                                cudaHostAllocMapped | cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    S->h_map = nullptr;
+    cudaGetLastError();
+    return set_error(DRRT_ERR_NOMEM, "mapped host buffer: %s", cudaGetErrorString(e));
+  }
+  return DRRT_OK;
+}
+
+static MappedSmall *mapped_small(Store *S) {
+  return reinterpret_cast<MappedSmall *>(reinterpret_cast<char *>(S->h_map) + sizeof(MappedRow));
+}
+
 int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist,
                     bool nearest) {
   if (nq < 0 || k < 1 || (nq > 0 && (!q || !ids)))
     return set_error(DRRT_ERR_INVALID, "knn: arguments");
   cudaStream_t st = S->stream;
+  if (nq > 0 && nq * k <= MAP_SMALL) {
+    // the planner asks for ONE nearest node per iteration (mainloop.cpp:204-210): the kernels read
+    // the query from, and write the answer into, mapped host memory -- launches and one wait
+    DRRT_CHECK(map_reserve(S));
+    MappedSmall *M = mapped_small(S);
+    memcpy(M->a, q, 3 * nq * sizeof(double));
+    DRRT_CHECK(knn_batch_dev(S, nq, M->a, k, M->out_i, M->out_d, st, nearest));
+    DRRT_CUDA(cudaStreamSynchronize(st));
+    memcpy(ids, M->out_i, nq * k * sizeof(int32_t));
+    if (dist) memcpy(dist, M->out_d, nq * k * sizeof(double));
+    return DRRT_OK;
+  }
   DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
   DRRT_CHECK(S->i_stage.reserve(nq * k + 1, st));
   DRRT_CHECK(S->d_stage.reserve(nq * k + 1, st));
@@ -87,7 +115,10 @@ static int put(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t st) {
 // k + 1 cross PCIe (48 B per edge, the dominant cost: 480 MB for config 3's 10 M edges against
 // 8 ms of kernels) while chunk k is solved and walked, and the verdicts / lengths of chunk k - 1
 // leave on a third stream -- the call costs max(H2D, kernels) + one chunk instead of their sum.
-static constexpr int64_t EDGE_CHUNK = 1 << 20;
+#ifndef DRRT_EDGE_CHUNK
+#define DRRT_EDGE_CHUNK (1 << 21)
+#endif
+static constexpr int64_t EDGE_CHUNK = DRRT_EDGE_CHUNK;
 
 static int edge_streams(Store *S) {
   if (S->ev_up[0]) return DRRT_OK;
@@ -100,6 +131,26 @@ static int edge_streams(Store *S) {
   return DRRT_OK;
 }
 
+// edge end ids are validated where they are consumed: an id outside the store is clamped (so the
+// edge kernels never read out of bounds) and flagged; the call then fails with DRRT_ERR_INVALID
+__global__ void validate_ids_kernel(int32_t *a, int32_t *b, int64_t n, int32_t n_nodes, int32_t *flag) {
+  bool bad = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t va = a[i], vb = b[i];
+    if (va < 0 || va >= n_nodes) { a[i] = 0; bad = true; }
+    if (vb < 0 || vb >= n_nodes) { b[i] = 0; bad = true; }
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *flag = 1;
+}
+
+static int validate_ids(Store *S, int32_t *a, int32_t *b, int64_t n, int32_t *flag, cudaStream_t st) {
+  if (S->n == 0) return set_error(DRRT_ERR_INVALID, "edgecheck: node ids given, the store is empty");
+  validate_ids_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(a, b, n, (int32_t)S->n, flag);
+  DRRT_LAUNCHED();
+  DRRT_CUDA(cudaGetLastError());
+  return DRRT_OK;
+}
+
 int edge_host(Store *S, int64_t n, const double *start, const double *end,
               const int32_t *sid, const int32_t *eid, int edge_kind, double robot_radius,
               double r_min, int in_warmup, uint8_t *verdict, double *length) {
@@ -108,10 +159,9 @@ int edge_host(Store *S, int64_t n, const double *start, const double *end,
   if (n > 0 && !by_id && !(start && end)) return set_error(DRRT_ERR_INVALID, "edgecheck: endpoints");
   if (n == 0) return DRRT_OK;
   cudaStream_t st = S->stream;
-  if (by_id)
-    for (int64_t i = 0; i < n; i++)
-      if (sid[i] < 0 || sid[i] >= S->n || eid[i] < 0 || eid[i] >= S->n)
-        return set_error(DRRT_ERR_INVALID, "edgecheck: node id out of range at edge %lld", (long long)i);
+  DRRT_CHECK(map_reserve(S));
+  int32_t *flag = &mapped_small(S)->flag;
+  *flag = 0;
   // in_warmup_time_ (obstacle.cpp:883): no obstacle is consulted, lengths still computed
   const bool saved = S->has_obstacles;
   struct Restore {
@@ -122,6 +172,28 @@ int edge_host(Store *S, int64_t n, const double *start, const double *end,
   DRRT_CHECK(S->b_stage.reserve(n, st));
   if (length) DRRT_CHECK(S->d_stage3.reserve(n, st));
 
+  if (n <= MAP_SMALL) {
+    // one edge (or one node's handful) per call, as the unchanged planner asks (drrt.cpp:411-422,
+    // 286-293): poses in and verdicts out through mapped host memory, no copy calls
+    DRRT_CHECK(map_reserve(S));
+    MappedSmall *M = mapped_small(S);
+    if (by_id) {
+      memcpy(M->ia, sid, n * sizeof(int32_t));
+      memcpy(M->ib, eid, n * sizeof(int32_t));
+      DRRT_CHECK(validate_ids(S, M->ia, M->ib, n, flag, st));
+    } else {
+      memcpy(M->a, start, 3 * n * sizeof(double));
+      memcpy(M->b, end, 3 * n * sizeof(double));
+    }
+    DRRT_CHECK(edgecheck_batch_dev(S, n, by_id ? nullptr : M->a, by_id ? nullptr : M->b,
+                                   by_id ? M->ia : nullptr, by_id ? M->ib : nullptr, edge_kind,
+                                   robot_radius, r_min, M->out_b, length ? M->out_d : nullptr, st));
+    DRRT_CUDA(cudaStreamSynchronize(st));
+    if (*flag) return set_error(DRRT_ERR_INVALID, "edgecheck: node id out of range");
+    memcpy(verdict, M->out_b, n);
+    if (length) memcpy(length, M->out_d, n * sizeof(double));
+    return DRRT_OK;
+  }
   if (n < 2 * EDGE_CHUNK) {
     const double *sd = nullptr, *ed = nullptr;
     const int32_t *si = nullptr, *ei = nullptr;
@@ -130,6 +202,7 @@ int edge_host(Store *S, int64_t n, const double *start, const double *end,
       DRRT_CHECK(S->i_stage2.reserve(n, st));
       DRRT_CHECK(upload(sid, S->i_stage.p, n * sizeof(int32_t), st));
       DRRT_CHECK(upload(eid, S->i_stage2.p, n * sizeof(int32_t), st));
+      DRRT_CHECK(validate_ids(S, S->i_stage.p, S->i_stage2.p, n, flag, st));
       si = S->i_stage.p; ei = S->i_stage2.p;
     } else {
       DRRT_CHECK(S->d_stage.reserve(3 * n, st));
@@ -143,6 +216,7 @@ int edge_host(Store *S, int64_t n, const double *start, const double *end,
     DRRT_CHECK(download(verdict, S->b_stage.p, n, st));
     if (length) DRRT_CHECK(download(length, S->d_stage3.p, n * sizeof(double), st));
     DRRT_CUDA(cudaStreamSynchronize(st));
+    if (*flag) return set_error(DRRT_ERR_INVALID, "edgecheck: node id out of range");
     return DRRT_OK;
   }
 
@@ -166,6 +240,9 @@ int edge_host(Store *S, int64_t n, const double *start, const double *end,
     if (by_id) {
       DRRT_CHECK(upload(sid + k0, S->i_stage.p + b * CH, m * sizeof(int32_t), up));
       DRRT_CHECK(upload(eid + k0, S->i_stage2.p + b * CH, m * sizeof(int32_t), up));
+      DRRT_CUDA(cudaEventRecord(S->ev_up[b], up));
+      DRRT_CUDA(cudaStreamWaitEvent(st, S->ev_up[b], 0));
+      DRRT_CHECK(validate_ids(S, S->i_stage.p + b * CH, S->i_stage2.p + b * CH, m, flag, st));
       si = S->i_stage.p + b * CH; ei = S->i_stage2.p + b * CH;
     } else {
       DRRT_CHECK(upload(start + 3 * k0, S->d_stage.p + b * 3 * CH, 3 * m * sizeof(double), up));
@@ -191,6 +268,7 @@ int edge_host(Store *S, int64_t n, const double *start, const double *end,
   DRRT_CUDA(e1);
   DRRT_CUDA(e2);
   DRRT_CUDA(e3);
+  if (*flag) return set_error(DRRT_ERR_INVALID, "edgecheck: node id out of range");
   return DRRT_OK;
 }
 
@@ -328,6 +406,7 @@ int drrt_store_destroy(drrt_store *h) {
     if (S->h_pending) cudaFreeHost(S->h_pending);
     if (S->h_bounds) cudaFreeHost(S->h_bounds);
     if (S->h_scalar) cudaFreeHost(S->h_scalar);
+    if (S->h_map) cudaFreeHost(S->h_map);
     for (int b = 0; b < 2; b++) {
       S->p_off[b].release(); S->p_ids[b].release(); S->p_dist[b].release();
       if (S->ev_packed[b]) cudaEventDestroy(S->ev_packed[b]);
@@ -474,6 +553,28 @@ int range_into(Store *S, int64_t nq, const double *q, const double *radius, doub
   if (!dist) dist_kind = DIST_NONE;
   const size_t dsz = dist_kind == DIST_F64 ? sizeof(double) : (dist_kind == DIST_F32 ? sizeof(float) : 0);
   cudaStream_t st = S->stream;
+  if (nq == 1) {
+    int64_t tot = 0;
+    const int32_t *mi = nullptr;
+    const double *md = nullptr;
+    int rc = range_one_mapped(S, q, radius ? radius[0] : radius_all, &tot, &mi, &md);
+    if (rc == DRRT_OK) {
+      offsets[0] = 0;
+      offsets[1] = tot;
+      if (total) *total = tot;
+      if (tot > cap)
+        return set_error(DRRT_ERR_CAPACITY, "range_into: %lld hits, caller buffers hold %lld",
+                         (long long)tot, (long long)cap);
+      if (tot > 0) {
+        memcpy(ids, mi, tot * sizeof(int32_t));
+        if (dist_kind == DIST_F64) memcpy(dist, md, tot * sizeof(double));
+        else if (dist_kind == DIST_F32)
+          for (int64_t i = 0; i < tot; i++) ((float *)dist)[i] = (float)md[i];
+      }
+      return DRRT_OK;
+    }
+    if (rc != RANGE_NOT_HANDLED) return rc;
+  }
   DRRT_CHECK(S->q_stage.reserve(3 * nq + 1, st));
   DRRT_CHECK(upload(q, S->q_stage.p, 3 * nq * sizeof(double), st));
   if (radius) {
@@ -995,6 +1096,15 @@ int drrt_pointcheck_batch(drrt_store *h, int64_t n, const double *pts, double ro
   if (n < 0 || (n > 0 && (!pts || !verdict))) return set_error(DRRT_ERR_INVALID, "pointcheck: arguments");
   if (n == 0) return DRRT_OK;
   cudaStream_t st = S->stream;
+  if (n <= MAP_SMALL) {  // ExplicitNodeCheck of the one sampled node (mainloop.cpp:226)
+    DRRT_CHECK(map_reserve(S));
+    MappedSmall *M = mapped_small(S);
+    memcpy(M->a, pts, 3 * n * sizeof(double));
+    DRRT_CHECK(pointcheck_batch_dev(S, n, M->a, robot_radius, collision_distance, M->out_b, st));
+    DRRT_CUDA(cudaStreamSynchronize(st));
+    memcpy(verdict, M->out_b, n);
+    return DRRT_OK;
+  }
   DRRT_CHECK(S->d_stage.reserve(3 * n, st));
   DRRT_CHECK(S->b_stage.reserve(n, st));
   DRRT_CHECK(upload(pts, S->d_stage.p, 3 * n * sizeof(double), st));

@@ -44,7 +44,11 @@ __device__ __forceinline__ void load_rec(const NodeRec *r, double &x, double &y,
 }
 
 struct Query {
-  double x, y, t, r, s_hi;
+  double x, y, t, r;
+  // Exact thresholds on the SQUARED sum: with d = fl(sqrt(s)) correctly rounded (and therefore
+  // monotone in s),  d < r  <=>  s < t_lt  and  d <= r  <=>  s < t_le  (sqrt_thresholds below).
+  // The scan decides on s and leaves the sqrt of the hits to the row write.
+  double t_lt, t_le;
   double gt;
   bool has_ghost;
   int ix0, ix1, iy0, iy1;
@@ -91,6 +95,56 @@ __device__ __forceinline__ void theta_runs(const GridParams &g, double key, doub
   }
 }
 
+// t_lt = the smallest double s with fl(sqrt(s)) >= r, t_le = the smallest with fl(sqrt(s)) > r.
+// IEEE sqrt is correctly rounded, hence monotone non-decreasing in s, so for every double s
+//   fl(sqrt(s)) <  r  <=>  s < t_lt        (kdtree.cpp:733, :765:  d < range)
+//   fl(sqrt(s)) <= r  <=>  s < t_le        (kdtree.cpp:800-802: the root, d <= range)
+// Both thresholds lie within a few ulps of r*r; a short walk from fl(r*r) finds them, a
+// bisection over the bit patterns of the non-negative doubles covers radii whose square
+// underflows or overflows.  r <= 0 or NaN: nothing is < r (t_lt = 0); only s == 0 is <= 0.
+__device__ __forceinline__ double f64_next(double v) { return __longlong_as_double(__double_as_longlong(v) + 1); }
+__device__ __forceinline__ double f64_prev(double v) { return __longlong_as_double(__double_as_longlong(v) - 1); }
+
+static __device__ __noinline__ double sqrt_threshold_bisect(double r, bool strict_gt) {
+  // smallest bit pattern b in [0, +inf] with sqrt(b) >= r (or > r)
+  long long lo = 0, hi = 0x7ff0000000000000ll;  // pred(hi) holds unless r is +inf / beyond
+  auto pred = [&](long long b) {
+    const double v = sqrt(__longlong_as_double(b));
+    return strict_gt ? v > r : v >= r;
+  };
+  if (pred(lo)) return __longlong_as_double(lo);
+  if (!pred(hi)) return __longlong_as_double(hi);
+  while (hi - lo > 1) {
+    const long long mid = lo + ((hi - lo) >> 1);
+    if (pred(mid)) hi = mid; else lo = mid;
+  }
+  return __longlong_as_double(hi);
+}
+
+__device__ __forceinline__ void sqrt_thresholds(double r, double &t_lt, double &t_le) {
+  if (!(r > 0.0)) {
+    t_lt = 0.0;
+    t_le = (r == 0.0) ? __longlong_as_double(1) : 0.0;  // d <= 0 only for s == 0
+    return;
+  }
+  double s = r * r;
+  bool ok = s > 0.0 && s < 1.0e300;
+  if (ok) {
+    int guard = 0;
+    while (sqrt(s) < r && guard < 8) { s = f64_next(s); guard++; }
+    while (sqrt(f64_prev(s)) >= r && guard < 16) { s = f64_prev(s); guard++; }
+    double u = s;
+    while (sqrt(u) <= r && guard < 24) { u = f64_next(u); guard++; }
+    ok = guard < 24 && sqrt(s) >= r && sqrt(f64_prev(s)) < r && sqrt(u) > r && sqrt(f64_prev(u)) <= r;
+    t_lt = s;
+    t_le = u;
+  }
+  if (!ok) {
+    t_lt = sqrt_threshold_bisect(r, false);
+    t_le = sqrt_threshold_bisect(r, true);
+  }
+}
+
 // Fills the probe (ghost) and the candidate cell ranges of a query of radius r:
 // every node n with metric(p,n) <= r for a probe p lies in the selected cells.
 template <int METRIC>
@@ -100,7 +154,7 @@ __device__ __forceinline__ void setup_query(const GridView &A, double qx, double
   Q.y = qy;
   Q.t = qt;
   Q.r = r;
-  Q.s_hi = Q.r * Q.r * (1.0 + 1e-12) + 1e-300;
+  sqrt_thresholds(Q.r, Q.t_lt, Q.t_le);
   Q.has_ghost = false;
   Q.gt = 0.0;
   if (A.has_wrap) Q.has_ghost = ghost_of<METRIC>(Q.x, Q.y, Q.t, A.wrap_point, Q.r, &Q.gt);

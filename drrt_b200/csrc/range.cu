@@ -94,32 +94,33 @@ __device__ __forceinline__ GhostBand ghost_band(const Query &Q) {
   return B;
 }
 
-// Candidate test of the CTA kernel: eval_candidate's predicate with the ghost probe behind ghost_band,
-// for UNR candidates at once, written straight-line (selects, no per-candidate
-// branches) so that the FP64 chains of the candidates overlap; the gate[] look-up and the ghost
-// pass stay behind warp-level branches because they are rare.
+// Candidate test: the reference's predicate with the ghost probe behind ghost_band, for UNR
+// candidates at once, written straight-line (selects, no per-candidate branches) so that the
+// FP64 chains of the candidates overlap; the gate[] look-up and the ghost pass stay behind
+// warp-level branches because they are rare.  The decision is taken on the SQUARED sum against
+// the exact thresholds of the query (Query::t_lt / t_le, gridscan.cuh), which is the
+// reference's `sqrt(s) < range` bit for bit; sout receives the squared sum of the admitting
+// probe -- the caller takes the square root when it writes the row, off the scan's
+// dependency chain.
 template <int METRIC, int UNR>
 __device__ __forceinline__ void eval_candidates(const Query &Q, const GhostBand &B, const bool *valid,
                                                 const double *nx, const double *ny, const double *nt,
                                                 const int32_t *id, const double *gate, bool *hit,
-                                                double *dout) {
-  double s[UNR], d[UNR];
+                                                double *sout) {
+  double s[UNR];
   bool askgate[UNR];
 #pragma unroll
   for (int u = 0; u < UNR; u++) s[u] = metric_sum<METRIC>(Q.x, Q.y, Q.t, nx[u], ny[u], nt[u]);
-#pragma unroll
-  for (int u = 0; u < UNR; u++) d[u] = sqrt(s[u]);
   bool anygate = false;
 #pragma unroll
   for (int u = 0; u < UNR; u++) {
-    const bool pre = valid[u] && s[u] < Q.s_hi;
     const bool root = id[u] == 0;
-    const bool in = pre && (root ? d[u] <= Q.r : d[u] < Q.r);     // kdtree.cpp:800-802, :733, :765
+    const bool in = valid[u] && s[u] < (root ? Q.t_le : Q.t_lt);   // kdtree.cpp:800-802, :733, :765
     const bool fast = METRIC == DRRT_METRIC_EUCLID || root || !(Q.t - nt[u] > Q.r);  // walk_reaches, first clause
     hit[u] = in && fast;
     askgate[u] = in && !fast;
     anygate |= askgate[u];
-    dout[u] = d[u];
+    sout[u] = s[u];
   }
   if (METRIC != DRRT_METRIC_EUCLID && __any_sync(0xffffffffu, anygate)) {
 #pragma unroll
@@ -134,17 +135,15 @@ __device__ __forceinline__ void eval_candidates(const Query &Q, const GhostBand 
       any |= needg[u];
     }
     if (__any_sync(0xffffffffu, any)) {
-      double s2[UNR], d2[UNR];
+      double s2[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; u++) s2[u] = metric_sum<METRIC>(Q.x, Q.y, Q.gt, nx[u], ny[u], nt[u]);
 #pragma unroll
-      for (int u = 0; u < UNR; u++) d2[u] = sqrt(s2[u]);
-#pragma unroll
       for (int u = 0; u < UNR; u++) {
-        const bool in = needg[u] && s2[u] < Q.s_hi && d2[u] < Q.r;
+        const bool in = needg[u] && s2[u] < Q.t_lt;   // the ghost walk admits with `<` only (:733, :765)
         bool ok = in;
         if (METRIC != DRRT_METRIC_EUCLID && in && (Q.gt - nt[u] > Q.r)) ok = !(Q.gt - gate[id[u]] > Q.r);
-        if (ok) { hit[u] = true; dout[u] = d2[u]; }
+        if (ok) { hit[u] = true; sout[u] = s2[u]; }
       }
     }
   }
@@ -366,7 +365,7 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, 4) range_warp_kernel(Ran
       __syncwarp();
       auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
         bool hit;
-        double d;
+        double d;  // squared sum of the admitting probe; the key is its square root (taken at the write)
         eval_candidates<METRIC, 1>(Q, GB, &valid, &nx, &ny, &nt, &id, V.gate, &hit, &d);
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (!m) return;
@@ -377,7 +376,7 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, 4) range_warp_kernel(Ran
           const int slot = pos + __popc(m & ltmask);
           if (gids) {
             gids[slot] = id;
-            gdist[slot] = d;
+            gdist[slot] = sqrt(d);
           } else if (slot < STAGE) {
             keys[slot] = ((unsigned long long)(unsigned)id << 32) | (unsigned)slot;
             sdist[slot] = d;
@@ -408,7 +407,7 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, 4) range_warp_kernel(Ran
         for (int i = lane; i < n; i += 32) {
           const int slot = order[i];
           oid[i] = (int32_t)(keys[slot] >> 32);
-          od[i] = sdist[slot];
+          od[i] = sqrt(sdist[slot]);
         }
       } else if (n > 0) {
         // more hits than the staging area: second pass straight into the arena
@@ -572,7 +571,7 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
             const int slot = pos + __popc(m[u] & ltmask);
             if (DIRECT) {
               gids[slot] = id[u];
-              gdist[slot] = d[u];
+              gdist[slot] = sqrt(d[u]);
             } else if (slot < STAGE) {
               sid[slot] = id[u];
               sdist[slot] = d[u];
@@ -687,10 +686,12 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
           }
         }
         __syncthreads();
+        // the staged values are squared sums: the keys' square roots are taken here, on
+        // independent elements, instead of inside the scan's dependency chain
         for (int p = tid; p < n; p += T) {
           const int slot = tmp[p];
           oid[p] = sid[slot];
-          od[p] = sdist[slot];
+          od[p] = sqrt(sdist[slot]);
         }
       } else if (staged) {
         // ids bunched in a few buckets: network sort of (id, slot) keys
@@ -700,7 +701,7 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         for (int p = tid; p < n; p += T) {
           const unsigned long long k = keys[p];
           oid[p] = (int32_t)(k >> 32);
-          od[p] = sdist[(unsigned)(k & 0xffffu)];
+          od[p] = sqrt(sdist[(unsigned)(k & 0xffffu)]);
         }
       } else if (n > 0) {
         // more hits than the staging area: second pass straight into the arena
@@ -879,6 +880,66 @@ int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out) {
   return DRRT_OK;
 }
 
+// The planner's own call -- ONE query per iteration (src/drrt.cpp:213-216, src/mainloop.cpp:204-210)
+// -- answered with one kernel launch and one stream wait and NO copy call: the query is read from,
+// and the row written straight into, a page-locked host buffer mapped into the device's address
+// space (S->h_map; stores of the sorted row cross PCIe as they are issued).  Returns
+// RANGE_NOT_HANDLED when the row may not fit the mapped area (or overflowed it): the caller then
+// takes the general path.
+int range_one_mapped(Store *S, const double *q3, double radius, int64_t *total, const int32_t **ids,
+                     const double **dist) {
+  cudaStream_t st = S->stream;
+  if (S->n == 0) { *total = 0; *ids = nullptr; *dist = nullptr; return DRRT_OK; }
+  DRRT_CHECK(ensure_index(S, 1, st));
+  DRRT_CHECK(map_reserve(S));
+  double expected = (double)S->n;
+  if (S->n_indexed > 0) {
+    const GridParams &g = S->gp;
+    double vol = (g.nx / g.inv_hx) * (g.ny / g.inv_hy) * (g.nt / g.inv_ht);
+    double ball = 4.18879 * fabs(radius) * fabs(radius) * fabs(radius);
+    expected = std::min((double)S->n, (double)S->n * ball / std::max(vol, 1e-300));
+  }
+  if (!(expected == expected)) return RANGE_NOT_HANDLED;
+  const bool block_mode = expected > WARP_STAGE / 2;
+  int64_t rowcap = (int64_t)(expected * 1.25 + 8.0 * sqrt(expected) + 96.0);
+  rowcap = std::min<int64_t>(rowcap, S->n);
+  // rows beyond the kernels' staging areas are re-scanned and sorted in place in the arena: not over PCIe
+  if (rowcap > MAP_ROW_ELEMS || rowcap > (block_mode ? CTA_STAGE : WARP_STAGE)) {
+    if (block_mode || rowcap > MAP_ROW_ELEMS) return RANGE_NOT_HANDLED;
+  }
+  MappedRow *M = reinterpret_cast<MappedRow *>(S->h_map);
+  M->q[0] = q3[0]; M->q[1] = q3[1]; M->q[2] = q3[2];
+  M->totals[0] = 0; M->totals[1] = 0;
+  RangeArgs A{};
+  A.V = make_view(S);
+  A.q = M->q; A.radius = nullptr; A.radius_all = radius; A.nq = 1;
+  A.offsets = M->offsets; A.counts = M->counts; A.ticket = S->d_ticket;
+  A.chunk_len = 1; A.nchunks = 1; A.chunk_cap = rowcap; A.chunk_base = nullptr;
+  A.chunk_total = M->chunk_total; A.totals = M->totals;
+  A.ids = M->ids; A.dist = M->dist;
+  int grid = 0;
+  DRRT_CHECK(kernel_grid(S, block_mode, &grid));  // (sets the shared-memory opt-in of this device)
+  DRRT_CUDA(cudaMemsetAsync(S->d_ticket, 0, sizeof(int32_t), st));
+  if (block_mode) {
+    if (S->metric == DRRT_METRIC_EUCLID) range_cta_kernel<DRRT_METRIC_EUCLID><<<1, CTA_T, CTA_SMEM, st>>>(A);
+    else range_cta_kernel<DRRT_METRIC_R2S1_WRAP><<<1, CTA_T, CTA_SMEM, st>>>(A);
+  } else {
+    if (S->metric == DRRT_METRIC_EUCLID)
+      range_warp_kernel<DRRT_METRIC_EUCLID><<<1, WARP_MODE_WARPS * 32, WARP_SMEM, st>>>(A);
+    else
+      range_warp_kernel<DRRT_METRIC_R2S1_WRAP><<<1, WARP_MODE_WARPS * 32, WARP_SMEM, st>>>(A);
+  }
+  DRRT_LAUNCHED();
+  DRRT_CUDA(cudaGetLastError());
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  S->last_nq = -1;  // nothing to fetch or pack afterwards
+  if (M->totals[1] != 0 || (int64_t)M->totals[0] > rowcap) return RANGE_NOT_HANDLED;
+  *total = (int64_t)M->totals[0];
+  *ids = M->ids;
+  *dist = M->dist;
+  return DRRT_OK;
+}
+
 int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *radius_dev,
                     double radius_all, cudaStream_t st, drrt_range_result *out) {
   if (nq < 0) return set_error(DRRT_ERR_INVALID, "range: nq < 0");
@@ -952,8 +1013,7 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
     DRRT_CHECK(S->r_ids.reserve(extent + 1, st));
     DRRT_CHECK(S->r_dist.reserve(extent + 1, st));
     A.ids = S->r_ids.p; A.dist = S->r_dist.p;
-    DRRT_CUDA(cudaMemsetAsync(S->d_ticket, 0, sizeof(int32_t), st));
-    DRRT_CUDA(cudaMemsetAsync(S->d_totals, 0, 2 * sizeof(unsigned long long), st));
+    DRRT_CUDA(cudaMemsetAsync(S->d_ticket, 0, 32, st));  // the ticket (+0) and both totals (+16, +24)
     if (block_mode) {
       if (S->metric == DRRT_METRIC_EUCLID)
         range_cta_kernel<DRRT_METRIC_EUCLID><<<grid, CTA_T, CTA_SMEM, st>>>(A);

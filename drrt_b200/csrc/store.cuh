@@ -92,6 +92,7 @@ struct Store {
   bool last_packed = true;          // the primary arena is a plain CSR
   bool last_packed_in_alt = false;  // a packed copy exists in r_*2
   int64_t *h_scalar = nullptr;  // pinned scratch (8 x i64)
+  void *h_map = nullptr;        // MappedRow + MappedSmall (pinned, mapped; map_reserve)
 
   // generic staging for host entry points
   DevBuf<int32_t> i_stage, i_stage2;
@@ -162,6 +163,34 @@ int range_pack_dev(Store *S, cudaStream_t st, drrt_range_result *out);
 enum { DIST_F64 = 0, DIST_F32 = 1, DIST_NONE = 2 };
 int range_pack_to(Store *S, cudaStream_t st, int64_t *off_out, int32_t *ids_out, void *dist_out,
                   int dist_kind, int64_t base);
+// Page-locked host memory mapped into the device's address space (cudaHostAllocMapped): the
+// small-call fast paths read their inputs from it and write their results into it, so that the
+// planner's one-query / one-edge calls cost a kernel launch and a stream wait, no copy calls.
+static constexpr int64_t MAP_ROW_ELEMS = 8192;   // hits of the mapped single-query row
+static constexpr int64_t MAP_SMALL = 1024;       // items of the other mapped small calls
+struct MappedRow {
+  double q[4];
+  unsigned long long totals[2];
+  int64_t offsets[2];
+  int64_t chunk_total[2];
+  int32_t counts[4];
+  int32_t ids[MAP_ROW_ELEMS];
+  double dist[MAP_ROW_ELEMS];
+};
+struct MappedSmall {           // after the MappedRow in the same allocation
+  double a[3 * MAP_SMALL];     // queries / start poses / points
+  double b[3 * MAP_SMALL];     // end poses
+  double out_d[MAP_SMALL];     // distances / lengths
+  int32_t ia[MAP_SMALL], ib[MAP_SMALL];  // edge end ids
+  int32_t out_i[MAP_SMALL];    // ids
+  uint8_t out_b[MAP_SMALL];    // verdicts
+  int32_t flag;                // set by validation kernels (e.g. an edge end id outside the store)
+};
+static constexpr int RANGE_NOT_HANDLED = -1;
+int map_reserve(Store *S);
+int range_one_mapped(Store *S, const double *q3, double radius, int64_t *total, const int32_t **ids,
+                     const double **dist);
+
 // capi.cu: host-buffer legs; the caller holds S->mu and has the store's device current
 int range_into(Store *S, int64_t nq, const double *q, const double *radius, double radius_all,
                int64_t cap, int64_t *offsets, int32_t *ids, void *dist, int dist_kind, int64_t *total);

@@ -262,3 +262,25 @@ def test_dubins_edges_poses_at_the_robot_radius(drrt, po):
     assert 0.2 < rv.mean() < 0.9 and 0.1 < rv[2 * n:].mean() < 0.8
     # poses a full 2e-6 or more outside every boundary are never decided by the shortcut alone:
     # whatever the device answers for them already matched the oracle's walk above
+
+
+def test_edge_ids_out_of_range_are_refused(drrt):
+    """edge end ids are validated on the device, where they are consumed: an id outside the store
+    fails the call with ERR_INVALID (small mapped call, one-shot batch and pipelined batch alike)
+    instead of reading out of bounds"""
+    t = drrt.KDTree()
+    t.KDInsert(synth.box_points(5000, 87))
+    t.SetObstacles(**synth.obstacles(32, 88))
+    for n in (1, 700, 50_000, 2_300_000):
+        a = np.random.default_rng(n).integers(0, 5000, n).astype(np.int32)
+        b = np.random.default_rng(n + 1).integers(0, 5000, n).astype(np.int32)
+        v, ln = t.ExplicitEdgeCheckIds(a, b)                 # all ids valid
+        assert len(v) == n
+        for bad in (5000, -1):
+            a2 = a.copy()
+            a2[n // 2] = bad
+            with pytest.raises(drrt.DrrtError) as ei:
+                t.ExplicitEdgeCheckIds(a2, b)
+            assert ei.value.code == drrt.capi.ERR_INVALID
+    v2, _ = t.ExplicitEdgeCheckIds(a, b)                      # the handle still works afterwards
+    assert np.array_equal(v, v2)
