@@ -112,6 +112,14 @@ SIGNATURES = {
                                                   C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                                   C.c_double, c_u8p, C.c_int32, C.c_void_p,
                                                   C.c_void_p, C.c_void_p]),
+    "drrt_obstacles_move": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_dp, C.c_int]),
+    "drrt_obstacles_update": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_u8p, c_dp]),
+    "drrt_edges_append": (C.c_int, [C.c_void_p, C.c_int64, c_ip, c_ip, c_i64p]),
+    "drrt_edges_count": (C.c_int, [C.c_void_p, c_i64p]),
+    "drrt_edges_clear": (C.c_int, [C.c_void_p]),
+    "drrt_obstacle_sweep": (C.c_int, [C.c_void_p, C.c_int32, c_u8p, C.c_int32, C.c_int, C.c_double,
+                                      C.c_double, c_i64p, c_i64p, c_i64p]),
+    "drrt_obstacle_sweep_fetch": (C.c_int, [C.c_void_p, c_i64p, c_u8p]),
     "drrt_obstacle_conflict_batch": (C.c_int, [C.c_void_p, C.c_int32, c_ip, C.c_double, c_ip, c_i64p]),
     "drrt_extend_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_double,
                                     C.c_double, C.c_int, c_dp, c_ip, c_i64p, c_ip, c_dp]),

@@ -402,6 +402,9 @@ int drrt_store_destroy(drrt_store *h) {
     S->x_unsafe.release(); S->x_len.release(); S->x_lmc.release(); S->x_best.release(); S->x_row.release(); S->x_best_cost.release();
     S->edge_paths.release(); S->edge_masks.release(); S->edge_perm.release(); S->edge_bins.release(); S->og_off.release(); S->og_idx.release(); S->og_eobs.release();
     S->og_ball.release(); S->og_erec.release();
+    S->e_u.release(); S->e_v.release(); S->node_mark.release(); S->sw_v1.release(); S->sw_v2.release();
+    S->sw_out_flag.release(); S->sw_cnt.release(); S->sw_sel.release(); S->sw_u.release(); S->sw_v.release();
+    S->sw_pick.release(); S->scan_tmp2.release(); S->sw_out_edge.release();
     if (S->d_bounds) cudaFree(S->d_bounds);
     if (S->h_pending) cudaFreeHost(S->h_pending);
     if (S->h_bounds) cudaFreeHost(S->h_bounds);
@@ -736,44 +739,38 @@ int drrt_knn_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, int k, in
 
 // ---- obstacles ------------------------------------------------------------
 
-int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const uint8_t *used,
-                       const double *life_span, const double *origin_xy, const double *radius,
-                       const int32_t *vert_off, const double *verts_xy) {
-  ENTER(h);
-  if (n_obs < 0) return set_error(DRRT_ERR_INVALID, "obstacles: n_obs < 0");
-  if (n_obs > 0 && (!kind || !used || !life_span || !origin_xy || !radius || !vert_off))
-    return set_error(DRRT_ERR_INVALID, "obstacles: null array");
-  for (int i = 0; i < n_obs; i++) {
-    if (kind[i] == 6 || kind[i] == 7)
-      return set_error(DRRT_ERR_UNSUPPORTED,
-                       "obstacles: kind %d (time-parametrised) needs a time dimension", kind[i]);
-    if (vert_off[i + 1] < vert_off[i]) return set_error(DRRT_ERR_INVALID, "obstacles: vert_off");
-  }
+}  // extern "C"
+
+namespace drrt {
+
+// Derives the device tables from the host copy of the caller's obstacle table (S->t_*): the
+// "active" list (live balls and polygons, the only obstacles that can ever answer true,
+// obstacle.cpp:761, 781-804), the whole table for the point checks and the sweeps, and the
+// per-obstacle `covers` flag; marks the broadphase grid stale.
+int obstacles_apply(Store *S) {
+  const int n_obs = (int)S->t_kind.size();
+  const std::vector<int32_t> &kind = S->t_kind, &vert_off = S->t_voff;
   const int nv_all = n_obs ? vert_off[n_obs] : 0;
-  if (nv_all > 0 && !verts_xy) return set_error(DRRT_ERR_INVALID, "obstacles: verts");
-  std::vector<int32_t> k_all(kind, kind + n_obs), vo_all(n_obs + 1, 0), k_act, vo_act(1, 0);
-  std::vector<uint8_t> live(n_obs);
-  std::vector<double> ox(n_obs), oy(n_obs), rad(radius, radius + n_obs), vx(nv_all), vy(nv_all);
+  std::vector<int32_t> k_act, vo_act(1, 0), src_act;
+  std::vector<uint8_t> live(n_obs), covers_act;
+  std::vector<double> ox(n_obs), oy(n_obs), vx(nv_all), vy(nv_all);
   std::vector<double> aox, aoy, arad, avx, avy;
-  std::vector<int32_t> src_act;
-  std::vector<uint8_t> covers_act;
-  for (int i = 0; i <= n_obs; i++) vo_all[i] = n_obs ? vert_off[i] : 0;
-  for (int v = 0; v < nv_all; v++) { vx[v] = verts_xy[2 * v]; vy[v] = verts_xy[2 * v + 1]; }
+  for (int v = 0; v < nv_all; v++) { vx[v] = S->t_verts[2 * v]; vy[v] = S->t_verts[2 * v + 1]; }
   for (int i = 0; i < n_obs; i++) {
-    ox[i] = origin_xy[2 * i];
-    oy[i] = origin_xy[2 * i + 1];
-    live[i] = (used[i] && !(life_span[i] <= 0)) ? 1 : 0;  // obstacle.cpp:761
+    ox[i] = S->t_origin[2 * i];
+    oy[i] = S->t_origin[2 * i + 1];
+    live[i] = (S->t_used[i] && !(S->t_life[i] <= 0)) ? 1 : 0;  // obstacle.cpp:761
     // only a live ball or polygon can ever answer true (obstacle.cpp:781-804)
     if (live[i] && (kind[i] == 1 || kind[i] == 3)) {
       src_act.push_back(i);
       k_act.push_back(kind[i]);
-      aox.push_back(ox[i]); aoy.push_back(oy[i]); arad.push_back(rad[i]);
+      aox.push_back(ox[i]); aoy.push_back(oy[i]); arad.push_back(S->t_radius[i]);
       for (int v = vert_off[i]; v < vert_off[i + 1]; v++) { avx.push_back(vx[v]); avy.push_back(vy[v]); }
       vo_act.push_back((int32_t)avx.size());
       double far = 0.0;  // obstacle.h:134-141 sets radius_ to this; a caller may not
       for (int v = vert_off[i]; v < vert_off[i + 1]; v++)
         far = std::max(far, sqrt((vx[v] - ox[i]) * (vx[v] - ox[i]) + (vy[v] - oy[i]) * (vy[v] - oy[i])));
-      covers_act.push_back(rad[i] * (1.0 + 1e-12) >= far ? 1 : 0);
+      covers_act.push_back(S->t_radius[i] * (1.0 + 1e-12) >= far ? 1 : 0);
     }
   }
   cudaStream_t st = S->stream;
@@ -783,10 +780,10 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
   DRRT_CHECK(put(S->o_rad, arad, st)); DRRT_CHECK(put(S->o_vx, avx, st));
   DRRT_CHECK(put(S->o_vy, avy, st));
   DRRT_CHECK(put(S->o_covers, covers_act, st));
-  DRRT_CHECK(put(S->oa_kind, k_all, st)); DRRT_CHECK(put(S->oa_voff, vo_all, st));
+  DRRT_CHECK(put(S->oa_kind, S->t_kind, st)); DRRT_CHECK(put(S->oa_voff, S->t_voff, st));
   DRRT_CHECK(put(S->oa_live, live, st));
   DRRT_CHECK(put(S->oa_ox, ox, st)); DRRT_CHECK(put(S->oa_oy, oy, st));
-  DRRT_CHECK(put(S->oa_rad, rad, st)); DRRT_CHECK(put(S->oa_vx, vx, st));
+  DRRT_CHECK(put(S->oa_rad, S->t_radius, st)); DRRT_CHECK(put(S->oa_vx, vx, st));
   DRRT_CHECK(put(S->oa_vy, vy, st));
   DRRT_CUDA(cudaStreamSynchronize(st));  // host vectors die at return
   ObstacleTable &T = S->obs;
@@ -799,10 +796,95 @@ int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const 
   T.a_rad = S->oa_rad.p; T.a_vert_off = S->oa_voff.p; T.a_vx = S->oa_vx.p; T.a_vy = S->oa_vy.p;
   S->h_o_ox = aox; S->h_o_oy = aoy; S->h_o_rad = arad; S->h_o_vx = avx; S->h_o_vy = avy;
   S->h_o_kind = k_act; S->h_o_voff = vo_act; S->h_o_src = src_act;
-  S->h_all_ox = ox; S->h_all_oy = oy; S->h_all_rad = rad; S->h_all_kind = k_all;
+  S->h_all_ox = ox; S->h_all_oy = oy; S->h_all_rad = S->t_radius; S->h_all_kind = S->t_kind;
   S->ogrid_radius = -1.0;  // broadphase grid is stale
   S->has_obstacles = true;
   return DRRT_OK;
+}
+
+}  // namespace drrt
+
+extern "C" {
+
+int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const uint8_t *used,
+                       const double *life_span, const double *origin_xy, const double *radius,
+                       const int32_t *vert_off, const double *verts_xy) {
+  ENTER(h);
+  if (n_obs < 0) return set_error(DRRT_ERR_INVALID, "obstacles: n_obs < 0");
+  if (n_obs > 0 && (!kind || !used || !life_span || !origin_xy || !radius || !vert_off))
+    return set_error(DRRT_ERR_INVALID, "obstacles: null array");
+  for (int i = 0; i < n_obs; i++) {
+    if (kind[i] == 6 || kind[i] == 7)
+      return set_error(DRRT_ERR_UNSUPPORTED,
+                       "obstacles: kind %d (time-parametrised) belongs in drrt_timed_obstacles_set", kind[i]);
+    if (vert_off[i + 1] < vert_off[i]) return set_error(DRRT_ERR_INVALID, "obstacles: vert_off");
+  }
+  const int nv_all = n_obs ? vert_off[n_obs] : 0;
+  if (nv_all > 0 && !verts_xy) return set_error(DRRT_ERR_INVALID, "obstacles: verts");
+  // the host copy of the caller's table: drrt_obstacles_move / drrt_obstacles_update patch it
+  S->t_kind.assign(kind, kind + n_obs);
+  S->t_used.assign(used, used + n_obs);
+  S->t_life.assign(life_span, life_span + n_obs);
+  S->t_origin.assign(origin_xy, origin_xy + 2 * (size_t)n_obs);
+  S->t_radius.assign(radius, radius + n_obs);
+  S->t_voff.assign(n_obs + 1, 0);
+  for (int i = 0; i <= n_obs; i++) S->t_voff[i] = n_obs ? vert_off[i] : 0;
+  S->t_verts.assign(verts_xy, verts_xy + 2 * (size_t)nv_all);
+  return obstacles_apply(S);
+}
+
+// Obstacle::UpdateObstacles -> NextOrigin (src/obstacle.cpp:12-22, 182-195): a moving obstacle's
+// origin_ jumps to the next point of its path.  Only the listed entries cross the boundary.
+//   translate_polygon == 0: origin_ alone moves -- exactly what the analytic checker then sees
+//     (it reads shape_.GetPolygon() as world coordinates, obstacle.cpp:785-794): the
+//     bounding reject (:765-779) follows the new origin, the polygon stays;
+//   translate_polygon != 0: the vertices move with the origin (the frame GetPosition(),
+//     obstacle.cpp:9-10, the Bullet hull and the visualiser use).
+int drrt_obstacles_move(drrt_store *h, int32_t n_sel, const int32_t *obstacle_index,
+                        const double *new_origin_xy, int translate_polygon) {
+  ENTER(h);
+  if (n_sel < 0 || (n_sel > 0 && (!obstacle_index || !new_origin_xy)))
+    return set_error(DRRT_ERR_INVALID, "obstacles_move: arguments");
+  if (!S->has_obstacles) return set_error(DRRT_ERR_STATE, "obstacles_move: no obstacle table");
+  const int n_obs = (int)S->t_kind.size();
+  for (int i = 0; i < n_sel; i++)
+    if (obstacle_index[i] < 0 || obstacle_index[i] >= n_obs)
+      return set_error(DRRT_ERR_INVALID, "obstacles_move: obstacle %d", obstacle_index[i]);
+  for (int i = 0; i < n_sel; i++) {
+    const int o = obstacle_index[i];
+    const double nx = new_origin_xy[2 * i], ny = new_origin_xy[2 * i + 1];
+    if (!(nx - nx == 0.0) || !(ny - ny == 0.0))
+      return set_error(DRRT_ERR_UNSUPPORTED, "obstacles_move: non-finite origin");
+    if (translate_polygon) {
+      const double dx = nx - S->t_origin[2 * o], dy = ny - S->t_origin[2 * o + 1];
+      for (int v = S->t_voff[o]; v < S->t_voff[o + 1]; v++) {
+        S->t_verts[2 * v] += dx;
+        S->t_verts[2 * v + 1] += dy;
+      }
+    }
+    S->t_origin[2 * o] = nx;
+    S->t_origin[2 * o + 1] = ny;
+  }
+  return n_sel ? obstacles_apply(S) : DRRT_OK;
+}
+
+// obstacle_used_ / life_span_ of listed obstacles (the obstacle thread switches obstacles on and
+// off, obstacle.cpp:454-499; RemoveObstacle ends with obstacle_used_ = false, :753)
+int drrt_obstacles_update(drrt_store *h, int32_t n_sel, const int32_t *obstacle_index,
+                          const uint8_t *used, const double *life_span) {
+  ENTER(h);
+  if (n_sel < 0 || (n_sel > 0 && (!obstacle_index || (!used && !life_span))))
+    return set_error(DRRT_ERR_INVALID, "obstacles_update: arguments");
+  if (!S->has_obstacles) return set_error(DRRT_ERR_STATE, "obstacles_update: no obstacle table");
+  const int n_obs = (int)S->t_kind.size();
+  for (int i = 0; i < n_sel; i++)
+    if (obstacle_index[i] < 0 || obstacle_index[i] >= n_obs)
+      return set_error(DRRT_ERR_INVALID, "obstacles_update: obstacle %d", obstacle_index[i]);
+  for (int i = 0; i < n_sel; i++) {
+    if (used) S->t_used[obstacle_index[i]] = used[i];
+    if (life_span) S->t_life[obstacle_index[i]] = life_span[i];
+  }
+  return n_sel ? obstacles_apply(S) : DRRT_OK;
 }
 
 // ---- edge checks ----------------------------------------------------------

@@ -114,6 +114,11 @@ struct Store {
   // the whole table (obstacle sweeps: conflict queries, subset checks)
   std::vector<double> h_all_ox, h_all_oy, h_all_rad;
   std::vector<int32_t> h_all_kind;
+  // host copy of the caller's table as given to drrt_obstacles_set, patched by drrt_obstacles_move /
+  // drrt_obstacles_update (only the changed entries cross the C boundary)
+  std::vector<int32_t> t_kind, t_voff;
+  std::vector<uint8_t> t_used;
+  std::vector<double> t_life, t_origin, t_radius, t_verts;
   DevBuf<uint8_t> o_mask;                // per ACTIVE obstacle: taking part in a subset check
   DevBuf<uint8_t> o_covers;              // per ACTIVE obstacle: radius_ covers every polygon vertex
   const uint8_t *edge_mask = nullptr;    // set for the duration of a subset check
@@ -133,6 +138,13 @@ struct Store {
   int64_t csr_nq = 0;
   int64_t last_extend_total = -1;
   int64_t lmc_n = 0;  // entries of x_lmc that are current (the rest of the store reads INF once covered)
+  // stored neighbour edges of the planner (drrt_edges_append) and the scratch of the obstacle sweeps
+  DevBuf<int32_t> e_u, e_v;
+  int64_t n_stored_edges = 0;
+  DevBuf<uint8_t> node_mark, sw_v1, sw_v2, sw_out_flag;
+  DevBuf<int32_t> sw_cnt, sw_sel, sw_u, sw_v, sw_pick, scan_tmp2;
+  DevBuf<int64_t> sw_out_edge;
+  int64_t sweep_out = -1;
   // solved Dubins paths handed from the solve kernel to the walk kernel
   DevBuf<unsigned char> edge_paths;
   // ranked solve: candidate list per edge, edges permuted by list, bin counters
@@ -199,6 +211,7 @@ int edge_host(Store *S, int64_t n, const double *start, const double *end, const
               uint8_t *verdict, double *length);
 int knn_host(Store *S, int64_t nq, const double *q, int k, int32_t *ids, double *dist, bool nearest);
 int lmc_mirror_cover(Store *S, cudaStream_t st);
+int obstacles_apply(Store *S);
 // knn.cu
 int knn_batch_dev(Store *S, int64_t nq, const double *q_dev, int k, int32_t *ids_dev,
                   double *dist_dev, cudaStream_t st, bool nearest = false);

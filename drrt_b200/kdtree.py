@@ -369,6 +369,59 @@ class KDTree:
         np.cumsum(counts, out=off[1:])
         return off, ids, dist
 
+    # -- Obstacle::UpdateObstacles / NextOrigin obstacle.cpp:12-22, 182-195: only the moved entries
+    def MoveObstacles(self, obstacle_indices, new_origins, translate_polygon=False):
+        idx = np.ascontiguousarray(obstacle_indices, dtype=np.int32)
+        org = _f64(new_origins, (-1, 2))
+        assert len(idx) == len(org)
+        check(self._lib.drrt_obstacles_move(self._h, len(idx), _ptr(idx, c_ip), _ptr(org, c_dp),
+                                            int(bool(translate_polygon))))
+
+    def UpdateObstacles(self, obstacle_indices, used=None, life_span=None):
+        idx = np.ascontiguousarray(obstacle_indices, dtype=np.int32)
+        u = np.ascontiguousarray(used, dtype=np.uint8) if used is not None else None
+        l = _f64(life_span) if life_span is not None else None
+        check(self._lib.drrt_obstacles_update(self._h, len(idx), _ptr(idx, c_ip),
+                                              _ptr(u, c_u8p) if u is not None else None,
+                                              _ptr(l, c_dp) if l is not None else None))
+
+    # -- the planner's stored neighbour edges on the device + AddObstacle / RemoveObstacle sweeps
+    #    (obstacle.cpp:612-754) in one call each
+    def AppendEdges(self, start_ids, end_ids):
+        a = np.ascontiguousarray(start_ids, dtype=np.int32)
+        b = np.ascontiguousarray(end_ids, dtype=np.int32)
+        assert a.size == b.size
+        first = C.c_int64()
+        check(self._lib.drrt_edges_append(self._h, a.size, _ptr(a, c_ip), _ptr(b, c_ip), C.byref(first)))
+        return first.value
+
+    @property
+    def stored_edges_(self):
+        n = C.c_int64()
+        check(self._lib.drrt_edges_count(self._h, C.byref(n)))
+        return n.value
+
+    def ClearEdges(self):
+        check(self._lib.drrt_edges_clear(self._h))
+
+    def ObstacleSweep(self, obstacle_index, other_mask=None, robot_radius=0.5, r_min=1.0,
+                      edge_kind=EDGE_DUBINS):
+        """-> dict(conflict_nodes, edges_checked, edge_index int64[n], flags uint8[n]): the stored
+        edges starting in a node in conflict with the obstacle that collide with it (bit 0), and
+        whether they also collide with another obstacle of other_mask (bit 1; RemoveObstacle)."""
+        m = np.ascontiguousarray(other_mask, dtype=np.uint8) if other_mask is not None else None
+        nc, ne, no = C.c_int64(), C.c_int64(), C.c_int64()
+        with self._lock:
+            check(self._lib.drrt_obstacle_sweep(self._h, int(obstacle_index),
+                                                _ptr(m, c_u8p) if m is not None else None,
+                                                len(m) if m is not None else 0, edge_kind,
+                                                float(robot_radius), float(r_min), C.byref(nc), C.byref(ne),
+                                                C.byref(no)))
+            idx = np.empty(no.value, dtype=np.int64)
+            fl = np.empty(no.value, dtype=np.uint8)
+            check(self._lib.drrt_obstacle_sweep_fetch(self._h, _ptr(idx, c_i64p), _ptr(fl, c_u8p)))
+        return dict(conflict_nodes=nc.value, edges_checked=ne.value, edge_index=idx, flags=fl)
+
     def ExplicitEdgeCheck_dev(self, verdict_out, start=None, end=None, start_ids=None,
                               end_ids=None, robot_radius=0.5, r_min=1.0, edge_kind=EDGE_DUBINS,
                               length_out=None):

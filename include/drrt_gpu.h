@@ -246,6 +246,44 @@ DRRT_API int drrt_obstacle_conflict_batch(drrt_store *h, int32_t n_sel,
                              const int32_t *obstacle_index, double robot_radius,
                              int32_t *counts, int64_t *total);
 
+/* Obstacle::UpdateObstacles -> NextOrigin (src/obstacle.cpp:12-22, 182-195): a moving obstacle's
+ * origin_ jumps to the next point of its path.  Only the listed entries cross the boundary; the
+ * device table and its broadphase follow.  translate_polygon == 0: origin_ alone moves, which is
+ * exactly what the analytic checker then sees (it reads shape_.GetPolygon() as world coordinates,
+ * obstacle.cpp:785-794, SURVEY F10: the bounding reject :765-779 follows the new origin, the
+ * polygon stays); != 0: the vertices move with the origin (the frame of GetPosition(),
+ * obstacle.cpp:9-10).  drrt_obstacles_update switches listed obstacles on / off
+ * (obstacle_used_, life_span_; either array may be NULL), as the obstacle thread does
+ * (obstacle.cpp:454-499) and as RemoveObstacle ends (:753). */
+DRRT_API int drrt_obstacles_move(drrt_store *h, int32_t n_sel, const int32_t *obstacle_index,
+                        const double *new_origin_xy, int translate_polygon);
+DRRT_API int drrt_obstacles_update(drrt_store *h, int32_t n_sel, const int32_t *obstacle_index,
+                          const uint8_t *used, const double *life_span);
+
+/* The sweeps on a DEVICE-RESIDENT list of the planner's stored neighbour edges.
+ * drrt_edges_append: the directed edges the planner keeps in its neighbour lists and as parent
+ * edges (linked in Extend, src/drrt.cpp:256-354; walked by RrtNodeNeighborIterator in
+ * AddObstacle / RemoveObstacle), named by node id; *first_edge receives the index of the first
+ * appended edge (edge indices are append order).
+ * drrt_obstacle_sweep does AddObstacle's (other_mask == NULL) or RemoveObstacle's work for one
+ * obstacle in one call: the conflict query (obstacle.cpp:540-610) stays on the device, every
+ * stored edge that STARTS in a node it finds is checked against obstacle_index alone
+ * (edge->ExplicitEdgeCheck(O), :643, :651, :712) and, with other_mask (n_obstacles bytes, the
+ * obstacles that are used and inside their life window, :717-734; the entry of obstacle_index is
+ * ignored), against those others.  n_out = the edges that collide with O;
+ * drrt_obstacle_sweep_fetch returns their indices in ascending order and a flag byte each
+ * (bit 0: collides with O; bit 1: also collides with another obstacle of the mask, i.e.
+ * RemoveObstacle must leave it blocked).  What the planner does with them (dist_ = INF, parent
+ * unlinking, RecalculateLMC) stays host code. */
+DRRT_API int drrt_edges_append(drrt_store *h, int64_t n, const int32_t *start_id,
+                      const int32_t *end_id, int64_t *first_edge);
+DRRT_API int drrt_edges_count(drrt_store *h, int64_t *n);
+DRRT_API int drrt_edges_clear(drrt_store *h);
+DRRT_API int drrt_obstacle_sweep(drrt_store *h, int32_t obstacle_index, const uint8_t *other_mask,
+                        int32_t n_obstacles, int edge_kind, double robot_radius, double r_min,
+                        int64_t *n_conflict_nodes, int64_t *n_edges_checked, int64_t *n_out);
+DRRT_API int drrt_obstacle_sweep_fetch(drrt_store *h, int64_t *edge_index, uint8_t *flags);
+
 /* ---- fused Extend step (the step after the edge check) ----------
  * What Extend does around the hot path for one new node (src/drrt.cpp:194-362):
  * KDFindWithinRange (:213-216), then for every neighbour the new->near edge

@@ -108,3 +108,123 @@ def test_subset_mask_must_match_table(drrt, po):
         t.ExplicitEdgeCheckSubset(np.ones(15, dtype=np.uint8), start=s, end=e)
     with pytest.raises(drrt.capi.DrrtError):
         t.FindPointsInConflictWithObstacle([16])
+
+
+def _stored_edges(t, pos, radius, n_src, seed):
+    """the planner's neighbour lists as a stored-edge list: every node of a sample links to its
+    neighbours within `radius` (drrt.cpp:256-354), both directions"""
+    rng = np.random.default_rng(seed)
+    src = np.sort(rng.choice(len(pos), n_src, replace=False)).astype(np.int32)
+    off, ids, _ = t.KDFindWithinRange(radius, pos[src])
+    a = np.repeat(src, np.diff(off)).astype(np.int32)
+    b = ids.astype(np.int32)
+    keep = a != b
+    a, b = a[keep], b[keep]
+    return np.concatenate([a, b]), np.concatenate([b, a])     # out-edges, then the reverse edges
+
+
+def test_device_resident_edge_list_sweeps(drrt, po):
+    """AddObstacle / RemoveObstacle (obstacle.cpp:612-754) in one call each over the device-resident
+    edge list: conflict query, selection of the stored edges starting in a conflict node,
+    edge->ExplicitEdgeCheck(O) and the other-obstacles re-check, against the oracle doing the same
+    steps on the host."""
+    pos = synth.box_points(120_000, 541)
+    o = synth.obstacles(96, 542)
+    o["kind"] = np.array(o["kind"]).copy()
+    o["kind"][20:24] = 1
+    o["used"] = np.array(o["used"]).copy()
+    o["used"][::9] = 0
+    t = drrt.KDTree()
+    t.KDInsert(pos)
+    t.SetObstacles(**o)
+    r = po.RefTree()
+    r.insert(pos)
+    eu, ev = _stored_edges(t, pos, 0.9, 30_000, 543)
+    half = len(eu) // 3
+    assert t.AppendEdges(eu[:half], ev[:half]) == 0           # appended as the tree grows
+    assert t.AppendEdges(eu[half:], ev[half:]) == half
+    assert t.stored_edges_ == len(eu) > 200_000
+    in_window = np.random.default_rng(544).random(96) < 0.85
+    for ob in (2, 22, 50):
+        # the oracle's version of the sweep
+        centre = np.array([[o["origin"][ob][0], o["origin"][ob][1], PI]])
+        _, conflict, _ = r.range_batch(centre, 0.5 + o["radius"][ob] + PI)
+        marked = np.zeros(len(pos), dtype=bool)
+        marked[conflict] = True
+        sel = np.nonzero(marked[eu])[0]
+        only = np.zeros(96, dtype=np.uint8)
+        only[ob] = 1
+        rv1, _, clr1 = _subset(po, o, only).edge_check_batch(pos[eu[sel]], pos[ev[sel]], want_clearance=True)
+        others = ((np.asarray(o["used"]) != 0) & in_window).astype(np.uint8)
+        others[ob] = 0
+        rv2, _, clr2 = _subset(po, o, others).edge_check_batch(pos[eu[sel]], pos[ev[sel]], want_clearance=True)
+        # AddObstacle
+        add = t.ObstacleSweep(ob)
+        assert add["conflict_nodes"] == len(conflict) and add["edges_checked"] == len(sel)
+        got = np.zeros(len(eu), dtype=np.uint8)
+        got[add["edge_index"]] = 1
+        assert (np.diff(add["edge_index"]) > 0).all() and (add["flags"] == 1).all()
+        _agree(got[sel], rv1, clr1)
+        assert not got[~marked[eu]].any()                     # only edges starting in a conflict node
+        # RemoveObstacle: the same edges, flagged when another live obstacle still blocks them
+        mask_in = others.copy()
+        mask_in[ob] = 1                                        # the entry of O itself is ignored
+        rem = t.ObstacleSweep(ob, other_mask=mask_in)
+        assert np.array_equal(rem["edge_index"], add["edge_index"])
+        blocked = np.zeros(len(eu), dtype=np.uint8)
+        blocked[rem["edge_index"]] = (rem["flags"] >> 1) & 1
+        hit = got[sel] == 1
+        _agree(blocked[sel][hit], rv2[hit], clr2[hit])
+        if o["used"][ob]:
+            assert 0 < len(add["edge_index"]) < len(sel)
+        else:
+            assert len(add["edge_index"]) == 0                # an unused obstacle never collides (:761)
+    # straight stored edges (Theta*'s LineCheck graph) take the same path
+    add = t.ObstacleSweep(50, edge_kind=drrt.EDGE_STRAIGHT)
+    assert add["edges_checked"] > 0
+    t.ClearEdges()
+    assert t.stored_edges_ == 0 and t.ObstacleSweep(2)["edges_checked"] == 0
+    with pytest.raises(drrt.DrrtError):
+        t.AppendEdges([0], [len(pos)])                        # an end outside the store
+
+
+def test_moving_obstacles_update_the_device_table(drrt, po):
+    """Obstacle::UpdateObstacles -> NextOrigin (obstacle.cpp:12-22, 182-195): origin_ of a moving
+    obstacle jumps along its path.  drrt_obstacles_move patches the listed entries; the verdicts
+    then equal a fresh table's -- both when the origin alone moves (what the analytic checker sees,
+    SURVEY F10) and when the polygon moves with it -- and drrt_obstacles_update switches obstacles
+    off and on as the obstacle thread does."""
+    o = synth.obstacles(64, 551)
+    t = drrt.KDTree()
+    t.SetObstacles(**o)
+    s, e = synth.random_edges(60_000, 552, max_len=1.5)
+    pts = synth.box_points(20_000, 553)
+    rng = np.random.default_rng(554)
+    for step in range(3):
+        idx = rng.choice(64, 9, replace=False).astype(np.int32)
+        shift = rng.choice([-1.0, 1.0], (9, 2))
+        translate = step != 1
+        o = {k: np.array(v).copy() for k, v in o.items()}
+        if translate:
+            for i, d in zip(idx, shift):
+                o["verts"][o["vert_off"][i]:o["vert_off"][i + 1]] += d
+        o["origin"][idx] += shift
+        t.MoveObstacles(idx, o["origin"][idx], translate_polygon=translate)
+        ro = po.RefObstacles(**o)
+        v, ln = t.ExplicitEdgeCheck(s, e)
+        rv, rln, clr = ro.edge_check_batch(s, e, want_clearance=True)
+        _agree(v, rv, clr)
+        fresh = drrt.KDTree()
+        fresh.SetObstacles(**o)
+        assert np.array_equal(v, fresh.ExplicitEdgeCheck(s, e)[0])
+        assert np.array_equal(t.ExplicitNodeCheck(pts), ro.point_check_batch(pts))
+        assert np.array_equal(t.LineCheck(s[:20_000], e[:20_000]), fresh.LineCheck(s[:20_000], e[:20_000]))
+    # obstacle_used_ / life_span_ of a few entries
+    off_idx = np.array([3, 30, 31], dtype=np.int32)
+    t.UpdateObstacles(off_idx, used=[0, 1, 1], life_span=[1e12, 0.0, 1e12])
+    o["used"][3] = 0
+    o["life_span"][30] = 0.0
+    rv, _, clr = po.RefObstacles(**o).edge_check_batch(s, e, want_clearance=True)
+    _agree(t.ExplicitEdgeCheck(s, e)[0], rv, clr)
+    with pytest.raises(drrt.DrrtError):
+        t.MoveObstacles([64], [[0.0, 0.0]])
