@@ -694,7 +694,8 @@ def main():
 
         # ---- config 4: replanning scenario (2 M nodes grown by 4096-node batches), one store per rank
         from benchmarks import replanning
-        extra["config4_replanning"] = replanning.run(2_000_000, 4096, device=local)
+        extra["config4_replanning"] = replanning.run(2_000_000, 4096, device=local,
+                                                      parity=(rank == 0 and world == 1 and not args.no_cpu))
 
         # ---- N > 1: strong scaling of the ONE-PROCESS multi-GPU C ABI (drrt_comm_*): rank 0's process
         # drives all N GPUs (the reference planner is one process); the other ranks wait at the barrier

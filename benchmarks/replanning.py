@@ -25,8 +25,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(nodes=2_000_000, batch=4096, device=0):
-    """grows one store on `device`; returns the result dict (torch's current stream is used)"""
+def run(nodes=2_000_000, batch=4096, device=0, parity=False):
+    """grows one store on `device`; returns the result dict (torch's current stream is used).
+    parity: at the final size, a 64-node sample of the last batch is answered by the CPU oracle
+    too (its tree over the same nodes, the obstacle table after all moves): rows bit-equal,
+    verdicts equal outside the 1e-6 band; the oracle's time on that sample is the CPU leg."""
     class args:  # noqa: N801
         pass
     args.nodes, args.batch = nodes, batch
@@ -94,7 +97,8 @@ def run(nodes=2_000_000, batch=4096, device=0):
             for k, o in enumerate(which):
                 obs["origin"][o] += step[k]
                 obs["verts"][obs["vert_off"][o]:obs["vert_off"][o + 1]] += step[k]
-            tree.SetObstacles(**obs)
+            # Obstacle::UpdateObstacles (obstacle.cpp:182-195): only the 16 moved entries cross the boundary
+            tree.MoveObstacles(which, obs["origin"][which], translate_polygon=True)
             centres = np.concatenate([obs["origin"][which], np.full((16, 1), synth.PI)], 1)
             radii = synth.ROBOT_RADIUS + obs["radius"][which] + synth.PI
             c0, c1 = ev(), ev()
@@ -117,8 +121,46 @@ def run(nodes=2_000_000, batch=4096, device=0):
             "collision_rate": tot_coll / max(tot_edges, 1),
             "conflict_queries": tot_conf_q, "conflict_hits_per_query": tot_conf_hits / max(tot_conf_q, 1),
             "gpu_launches": capi.launches() - l0}
+    if parity:
+        line["parity_sample"], line["cpu_baseline"] = parity_sample(tree, pos, obs, n_batches * args.batch,
+                                                                    synth.shrinking_radius(n_batches * args.batch, gamma, delta))
     tree.close()
     return line
+
+
+def parity_sample(tree, pos, obs, n, radius, nq=64):
+    """the last batch's first nq nodes against the CPU oracle at the final store size"""
+    from oracle import pyoracle as po
+    from drrt_b200 import synth
+    ref = po.RefTree()
+    t0 = time.perf_counter()
+    ref.insert(pos[:n])
+    t_build = time.perf_counter() - t0
+    q = pos[n - nq:n]
+    off, ids, dist = tree.KDFindWithinRange(radius, q)
+    t0 = time.perf_counter()
+    roff, rids, rdist = ref.range_batch(q, radius)
+    t_range = time.perf_counter() - t0
+    rows_equal = bool(np.array_equal(off, roff) and np.array_equal(ids, rids) and np.array_equal(dist, rdist))
+    src = np.repeat(np.arange(n - nq, n), np.diff(off))
+    s = np.concatenate([pos[src], pos[ids]])
+    e = np.concatenate([pos[ids], pos[src]])
+    v, ln = tree.ExplicitEdgeCheck(s, e, robot_radius=synth.ROBOT_RADIUS, r_min=synth.R_MIN)
+    robs = po.RefObstacles(**obs)
+    t0 = time.perf_counter()
+    rv, rln = robs.edge_check_batch(s, e, robot_radius=synth.ROBOT_RADIUS, r_min=synth.R_MIN)
+    t_edge = time.perf_counter() - t0
+    diff = np.nonzero(v != rv)[0]
+    _, _, clr = robs.edge_check_batch(s[diff], e[diff], robot_radius=synth.ROBOT_RADIUS, r_min=synth.R_MIN,
+                                      want_clearance=True)
+    ok = rln < 1e11
+    return ({"nodes": n, "queries": nq, "hits": int(len(ids)), "rows_bit_equal": rows_equal, "edges": int(len(v)),
+             "verdicts_differ": int(len(diff)), "all_differences_within_1e-6_band": bool((clr < 1e-6).all()),
+             "lengths_within_1e-9": bool(np.allclose(ln[ok], rln[ok], rtol=1e-9, atol=1e-9))},
+            {"kind": "port", "cores": po.num_threads(), "range_queries_per_s": nq / t_range,
+             "edge_checks_per_s": len(v) / t_edge,
+             "sample": "%d queries + their %d Dubins edges at %d nodes (oracle tree build %.1f s not counted)"
+                       % (nq, len(v), n, t_build)})
 
 
 def main():

@@ -124,6 +124,8 @@ SIGNATURES = {
     "drrt_extend_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, C.c_double,
                                     C.c_double, C.c_int, c_dp, c_ip, c_i64p, c_ip, c_dp]),
     "drrt_extend_fetch": (C.c_int, [C.c_void_p, c_ip, c_dp, c_u8p, c_dp]),
+    "drrt_extend_rewire": (C.c_int, [C.c_void_p, C.c_double, c_i64p]),
+    "drrt_extend_rewire_fetch": (C.c_int, [C.c_void_p, c_ip, c_ip, c_dp]),
     "drrt_extend_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                         C.POINTER(RangeResult), C.POINTER(C.c_void_p),

@@ -404,7 +404,7 @@ int drrt_store_destroy(drrt_store *h) {
     S->og_ball.release(); S->og_erec.release();
     S->e_u.release(); S->e_v.release(); S->node_mark.release(); S->sw_v1.release(); S->sw_v2.release();
     S->sw_out_flag.release(); S->sw_cnt.release(); S->sw_sel.release(); S->sw_u.release(); S->sw_v.release();
-    S->sw_pick.release(); S->scan_tmp2.release(); S->sw_out_edge.release();
+    S->sw_pick.release(); S->scan_tmp2.release(); S->sw_out_edge.release(); S->rw_lmc.release();
     if (S->d_bounds) cudaFree(S->d_bounds);
     if (S->h_pending) cudaFreeHost(S->h_pending);
     if (S->h_bounds) cudaFreeHost(S->h_bounds);
@@ -1078,6 +1078,7 @@ int drrt_extend_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, const 
                               pick(S, stream), rows, &u, &l, best_parent_dev, best_cost_dev));
   if (unsafe_dev) *unsafe_dev = u;
   if (length_dev) *length_dev = l;
+  S->last_extend_total = rows->total;  // rows stay valid until the next range / extend call
   return DRRT_OK;
 }
 

@@ -1025,8 +1025,10 @@ int extend_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *ra
     S->csr_q = nullptr;
     DRRT_CHECK(rc);
   }
+  S->ext_lmc = nullptr; S->ext_best = nullptr; S->ext_cost = nullptr; S->rewire_out = -1;
   if (best_dev && nq > 0) {
     if (!lmc_dev) return set_error(DRRT_ERR_INVALID, "extend: best parent needs the lmc array");
+    S->ext_lmc = lmc_dev; S->ext_best = best_dev; S->ext_cost = best_cost_dev;  // for drrt_extend_rewire
     best_parent_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, st>>>(nq, rr->offsets_dev, rr->ids_dev,
                                                                  S->x_unsafe.p, S->x_len.p, lmc_dev,
                                                                  best_dev, best_cost_dev);

@@ -145,6 +145,11 @@ struct Store {
   DevBuf<int32_t> sw_cnt, sw_sel, sw_u, sw_v, sw_pick, scan_tmp2;
   DevBuf<int64_t> sw_out_edge;
   int64_t sweep_out = -1;
+  // rewiring candidates of the last fused Extend (drrt_extend_rewire)
+  DevBuf<double> rw_lmc;
+  int64_t rewire_out = -1;
+  const double *ext_lmc = nullptr, *ext_cost = nullptr;  // the lmc array / best_cost of that Extend (device)
+  const int32_t *ext_best = nullptr;
   // solved Dubins paths handed from the solve kernel to the walk kernel
   DevBuf<unsigned char> edge_paths;
   // ranked solve: candidate list per edge, edges permuted by list, bin counters

@@ -135,6 +135,32 @@ static int select_indices(Store *S, int64_t n, const int32_t *e_u, const uint8_t
   return DRRT_OK;
 }
 
+// Extend's rewiring test for every (new node, neighbour) pair of the last fused Extend
+// (src/drrt.cpp:330-333): the near -> new edge is safe, and
+//   near.rrt_LMC_ > new.rrt_LMC_ + edge.dist_  &&  new's parent != near  &&
+//   new.rrt_LMC_ + edge.dist_ < move_goal.rrt_LMC_
+// with new.rrt_LMC_ / new's parent as FindBestParent left them (best_cost / best_parent).
+__global__ void rewire_flag_kernel(int64_t total, const int32_t *row, const int32_t *ids, const uint8_t *unsafe,
+                                   const double *len, const double *lmc, const int32_t *best,
+                                   const double *best_cost, double goal_lmc, uint8_t *flag) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t q = row[t], near = ids[t];
+    const double via = best_cost[q] + len[2 * t + 1];   // new_node->rrt_LMC_ + this_edge->dist_
+    flag[t] = (!unsafe[2 * t + 1] && lmc[near] > via && best[q] != near && via < goal_lmc) ? 1 : 0;
+  }
+}
+
+__global__ void rewire_out_kernel(int64_t n, const int32_t *pick, const int32_t *row, const int32_t *ids,
+                                  const double *len, const double *best_cost, int32_t *out_q, int32_t *out_near,
+                                  double *out_lmc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t t = pick[i];
+    out_q[i] = row[t];
+    out_near[i] = ids[t];
+    out_lmc[i] = best_cost[row[t]] + len[2 * (int64_t)t + 1];
+  }
+}
+
 static int stage_mask(Store *S, const uint8_t *mask_over_table, cudaStream_t st) {
   std::vector<uint8_t> act(S->h_o_src.size() + 1, 0);
   for (size_t a = 0; a < S->h_o_src.size(); a++) act[a] = mask_over_table[S->h_o_src[a]] ? 1 : 0;
@@ -203,6 +229,7 @@ int drrt_obstacle_sweep(drrt_store *h, int32_t obstacle_index, const uint8_t *ot
                         int64_t *n_conflict_nodes, int64_t *n_edges_checked, int64_t *n_out) {
   ENTER(h);
   S->sweep_out = -1;
+  S->rewire_out = -1;  // shares the selection scratch
   if (!S->has_obstacles) return set_error(DRRT_ERR_STATE, "sweep: no obstacle table");
   const int o = obstacle_index;
   if (o < 0 || o >= S->obs.n_all) return set_error(DRRT_ERR_INVALID, "sweep: obstacle %d", o);
@@ -289,6 +316,58 @@ int drrt_obstacle_sweep_fetch(drrt_store *h, int64_t *edge_index, uint8_t *flags
     if (edge_index)
       DRRT_CUDA(cudaMemcpyAsync(edge_index, S->sw_out_edge.p, S->sweep_out * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (flags) DRRT_CUDA(cudaMemcpyAsync(flags, S->sw_out_flag.p, S->sweep_out, cudaMemcpyDeviceToHost, st));
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  return DRRT_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int drrt_extend_rewire(drrt_store *h, double move_goal_lmc, int64_t *n_out) {
+  ENTER(h);
+  S->rewire_out = -1;
+  if (S->last_extend_total < 0 || !S->ext_best || !S->ext_cost || !S->ext_lmc)
+    return set_error(DRRT_ERR_STATE, "extend_rewire: no fused Extend with a parent reduction on this handle");
+  const int64_t total = S->last_extend_total;
+  if (n_out) *n_out = 0;
+  S->rewire_out = 0;
+  if (total == 0) return DRRT_OK;
+  if (total > 0x7ffffff0) return set_error(DRRT_ERR_UNSUPPORTED, "extend_rewire: more than 2^31 pairs");
+  cudaStream_t st = S->stream;
+  DRRT_CHECK(S->sw_v1.reserve((size_t)total, st));
+  rewire_flag_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+      total, S->x_row.p, S->csr_ids, S->x_unsafe.p, S->x_len.p, S->ext_lmc, S->ext_best, S->ext_cost,
+      move_goal_lmc, S->sw_v1.p);
+  DRRT_LAUNCHED();
+  int64_t n = 0;
+  DRRT_CHECK(select_indices<1>(S, total, nullptr, nullptr, S->sw_v1.p, S->sw_pick, &n, st));
+  if (n > 0) {
+    DRRT_CHECK(S->sw_u.reserve((size_t)n, st));
+    DRRT_CHECK(S->sw_v.reserve((size_t)n, st));
+    DRRT_CHECK(S->rw_lmc.reserve((size_t)n, st));
+    rewire_out_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(
+        n, S->sw_pick.p, S->x_row.p, S->csr_ids, S->x_len.p, S->ext_cost, S->sw_u.p, S->sw_v.p, S->rw_lmc.p);
+    DRRT_LAUNCHED();
+    DRRT_CUDA(cudaGetLastError());
+  }
+  DRRT_CUDA(cudaStreamSynchronize(st));
+  S->rewire_out = n;
+  S->sweep_out = -1;  // the sweep's scratch was reused
+  if (n_out) *n_out = n;
+  return DRRT_OK;
+}
+
+int drrt_extend_rewire_fetch(drrt_store *h, int32_t *query_index, int32_t *near_id, double *new_lmc) {
+  ENTER(h);
+  if (S->rewire_out < 0) return set_error(DRRT_ERR_STATE, "extend_rewire_fetch: no drrt_extend_rewire on this handle");
+  cudaStream_t st = S->stream;
+  const int64_t n = S->rewire_out;
+  if (n > 0) {
+    if (query_index) DRRT_CUDA(cudaMemcpyAsync(query_index, S->sw_u.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (near_id) DRRT_CUDA(cudaMemcpyAsync(near_id, S->sw_v.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (new_lmc) DRRT_CUDA(cudaMemcpyAsync(new_lmc, S->rw_lmc.p, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
   DRRT_CUDA(cudaStreamSynchronize(st));
   return DRRT_OK;

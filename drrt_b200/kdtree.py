@@ -510,6 +510,18 @@ class KDTree:
                                               _ptr(cost, c_dp)))
         return counts, best, cost, total.value
 
+    def ExtendRewire(self, move_goal_lmc):
+        """Extend's rewiring candidates (drrt.cpp:330-333) of the last Extend / ExtendParents call
+        -> (query_index int32[n], near_id int32[n], new_lmc f64[n]) in pair order"""
+        n = C.c_int64()
+        with self._lock:
+            check(self._lib.drrt_extend_rewire(self._h, float(move_goal_lmc), C.byref(n)))
+            qi = np.empty(n.value, dtype=np.int32)
+            ni = np.empty(n.value, dtype=np.int32)
+            lm = np.empty(n.value, dtype=np.float64)
+            check(self._lib.drrt_extend_rewire_fetch(self._h, _ptr(qi, c_ip), _ptr(ni, c_ip), _ptr(lm, c_dp)))
+        return qi, ni, lm
+
     def Extend_dev(self, range_, new_points, lmc=None, best_parent=None, best_cost=None,
                    robot_radius=0.5, r_min=1.0):
         """device-resident Extend: torch tensors in; returns (RangeResult rows, unsafe u8[2*total],

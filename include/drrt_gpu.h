@@ -315,6 +315,15 @@ DRRT_API int drrt_extend_batch(drrt_store *h, int64_t nq, const double *q, const
                       int32_t *best_parent, double *best_cost);
 DRRT_API int drrt_extend_fetch(drrt_store *h, int32_t *ids, double *dist, uint8_t *unsafe,
                       double *length);
+/* Extend's rewiring test (src/drrt.cpp:330-333) over the pairs of the last drrt_extend_batch
+ * that reduced a parent: near -> new is safe, near.rrt_LMC_ > new.rrt_LMC_ + dist_, new's parent
+ * is not near, and new.rrt_LMC_ + dist_ < move_goal.rrt_LMC_ (new.rrt_LMC_ = best_cost, new's
+ * parent = best_parent).  Only the candidates come back, in pair order: the index of the new node
+ * in the batch, the neighbour's id and the rrt_LMC_ it would get.  MakeParentOf, the queue and
+ * the change threshold (:334-346) stay host code. */
+DRRT_API int drrt_extend_rewire(drrt_store *h, double move_goal_lmc, int64_t *n_out);
+DRRT_API int drrt_extend_rewire_fetch(drrt_store *h, int32_t *query_index, int32_t *near_id,
+                             double *new_lmc);
 DRRT_API int drrt_extend_batch_dev(drrt_store *h, int64_t nq, const double *q_dev,
                           const double *radius_dev, double radius_all, double robot_radius,
                           double r_min, const double *lmc_dev, void *stream,

@@ -118,3 +118,36 @@ def test_extend_against_the_resident_lmc_mirror(drrt, po):
     tree.KDFindWithinRange(3.0, new)
     lib = capi.load()
     assert lib.drrt_extend_fetch(tree._h, None, None, None, None) == capi.ERR_STATE
+
+
+def test_extend_rewire_candidates(drrt):
+    """drrt_extend_rewire: Extend's rewiring test (drrt.cpp:330-333) evaluated on the device over
+    the pairs of the last fused Extend; only the candidates cross PCIe.  Against the same predicate
+    in numpy over the rows / verdicts / lengths the Extend returned."""
+    pos = synth.box_points(60_000, 421)
+    tree = drrt.KDTree()
+    tree.KDInsert(pos)
+    tree.SetObstacles(**synth.obstacles(64, 422))
+    rng = np.random.default_rng(423)
+    lmc = rng.uniform(0.0, 70.0, len(pos))
+    lmc[rng.integers(0, len(pos), 300)] = 1e12
+    new = synth.box_points(400, 424)
+    for goal_lmc in (1e12, 45.0):
+        out = tree.Extend(1.4, new, lmc=lmc)
+        qi, ni, lm = tree.ExtendRewire(goal_lmc)
+        off, ids = out["offsets"], out["ids"]
+        row = np.repeat(np.arange(len(new)), np.diff(off))
+        via = out["best_cost"][row] + out["length"][:, 1]
+        want = (out["unsafe"][:, 1] == 0) & (lmc[ids] > via) & (out["best_parent"][row] != ids) & (via < goal_lmc)
+        t = np.nonzero(want)[0]
+        assert np.array_equal(qi, row[t]) and np.array_equal(ni, ids[t]) and np.array_equal(lm, via[t])
+        assert 0 < len(t) < len(ids)
+    # the mirror path gives the same candidates
+    tree.WriteLMC(0, lmc)
+    tree.ExtendParents(1.4, new)
+    q2, n2, l2 = tree.ExtendRewire(45.0)
+    assert np.array_equal(q2, qi) and np.array_equal(n2, ni) and np.array_equal(l2, lm)
+    # without a parent reduction there is nothing to rewire from
+    tree.Extend(1.4, new)
+    with pytest.raises(drrt.DrrtError):
+        tree.ExtendRewire(45.0)
