@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdrrt_b200.so")
 OBJDIR = os.path.join(HERE, "build")
 
-SOURCES = ["capi.cu", "store.cu", "scan.cu", "range.cu", "knn.cu", "edgecheck.cu", "comm.cu", "sweep.cu"]
+SOURCES = ["capi.cu", "store.cu", "scan.cu", "range.cu", "knn.cu", "edgecheck.cu", "comm.cu", "sweep.cu", "timed.cu"]
 HEADERS = ["common.cuh", "store.cuh", "gridscan.cuh", "geom.cuh", os.path.join("..", "..", "include", "drrt_gpu.h")]
 
 NVCC_FLAGS = [

@@ -112,6 +112,10 @@ SIGNATURES = {
                                                   C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                                   C.c_double, c_u8p, C.c_int32, C.c_void_p,
                                                   C.c_void_p, C.c_void_p]),
+    "drrt_timed_obstacles_set": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_u8p, c_dp, c_dp, c_dp, c_ip, c_dp]),
+    "drrt_edgecheck2d_timed_batch": (C.c_int, [C.c_void_p, C.c_int64, c_dp, c_dp, C.c_double, c_u8p]),
+    "drrt_edgecheck2d_timed_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
+                                                   C.c_void_p, C.c_void_p]),
     "drrt_obstacles_move": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_dp, C.c_int]),
     "drrt_obstacles_update": (C.c_int, [C.c_void_p, C.c_int32, c_ip, c_u8p, c_dp]),
     "drrt_edges_append": (C.c_int, [C.c_void_p, C.c_int64, c_ip, c_ip, c_i64p]),

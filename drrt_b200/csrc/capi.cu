@@ -405,6 +405,7 @@ int drrt_store_destroy(drrt_store *h) {
     S->e_u.release(); S->e_v.release(); S->node_mark.release(); S->sw_v1.release(); S->sw_v2.release();
     S->sw_out_flag.release(); S->sw_cnt.release(); S->sw_sel.release(); S->sw_u.release(); S->sw_v.release();
     S->sw_pick.release(); S->scan_tmp2.release(); S->sw_out_edge.release(); S->rw_lmc.release();
+    S->tm_ox.release(); S->tm_oy.release(); S->tm_rad.release(); S->tm_path.release(); S->tm_poff.release();
     if (S->d_bounds) cudaFree(S->d_bounds);
     if (S->h_pending) cudaFreeHost(S->h_pending);
     if (S->h_bounds) cudaFreeHost(S->h_bounds);

@@ -145,6 +145,10 @@ struct Store {
   DevBuf<int32_t> sw_cnt, sw_sel, sw_u, sw_v, sw_pick, scan_tmp2;
   DevBuf<int64_t> sw_out_edge;
   int64_t sweep_out = -1;
+  // time-parametrised obstacles (kinds 6 / 7, drrt_timed_obstacles_set): the live ones
+  DevBuf<double> tm_ox, tm_oy, tm_rad, tm_path;
+  DevBuf<int32_t> tm_poff;
+  int timed_n = 0;
   // rewiring candidates of the last fused Extend (drrt_extend_rewire)
   DevBuf<double> rw_lmc;
   int64_t rewire_out = -1;

@@ -369,6 +369,27 @@ class KDTree:
         np.cumsum(counts, out=off[1:])
         return off, ids, dist
 
+    # -- ExplicitEdgeCheck2D kinds 6 / 7 (obstacle.cpp:805-875): discs moving along (dx, dy, time) paths
+    def SetTimedObstacles(self, kind, used, life_span, origin, radius, path_off, path):
+        kind = np.ascontiguousarray(kind, dtype=np.int32)
+        used = np.ascontiguousarray(used, dtype=np.uint8)
+        life = _f64(life_span)
+        origin = _f64(origin, (-1, 2))
+        radius = _f64(radius)
+        poff = np.ascontiguousarray(path_off, dtype=np.int32)
+        path = _f64(path, (-1, 3))
+        check(self._lib.drrt_timed_obstacles_set(self._h, len(kind), _ptr(kind, c_ip), _ptr(used, c_u8p),
+                                                 _ptr(life, c_dp), _ptr(origin, c_dp), _ptr(radius, c_dp),
+                                                 _ptr(poff, c_ip), _ptr(path, c_dp)))
+
+    def ExplicitEdgeCheck2DTimed(self, start_xyt, end_xyt, radius=0.5):
+        s = _f64(start_xyt, (-1, 3))
+        e = _f64(end_xyt, (-1, 3))
+        verdict = np.zeros(s.shape[0], dtype=np.uint8)
+        check(self._lib.drrt_edgecheck2d_timed_batch(self._h, s.shape[0], _ptr(s, c_dp), _ptr(e, c_dp),
+                                                     float(radius), _ptr(verdict, c_u8p)))
+        return verdict
+
     # -- Obstacle::UpdateObstacles / NextOrigin obstacle.cpp:12-22, 182-195: only the moved entries
     def MoveObstacles(self, obstacle_indices, new_origins, translate_polygon=False):
         idx = np.ascontiguousarray(obstacle_indices, dtype=np.int32)

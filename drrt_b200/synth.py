@@ -126,3 +126,34 @@ def write_obstacle_file(path, table):
             fh.write("%d\n" % (v1 - v0))
             for v in range(v0, v1):
                 fh.write("%.17g,%.17g\n" % (table["verts"][v][0], table["verts"][v][1]))
+
+
+def timed_obstacles(m=32, seed=0xD2270006, lo=5.0, hi=45.0):
+    """m time-parametrised obstacles (kinds 6 / 7, obstacle.cpp:805-875): a disc of radius_ whose
+    centre moves along path rows (dx, dy, time) relative to origin_."""
+    rng = np.random.default_rng(seed)
+    origin = rng.uniform(lo, hi, (m, 2))
+    radius = rng.uniform(0.5, 2.0, m)
+    rows = rng.integers(2, 9, m)
+    path_off = np.zeros(m + 1, dtype=np.int32)
+    np.cumsum(rows, out=path_off[1:])
+    path = np.empty((int(path_off[-1]), 3), dtype=np.float64)
+    for i in range(m):
+        t = np.cumsum(rng.uniform(0.5, 4.0, rows[i])) + rng.uniform(0.0, 5.0)
+        xy = np.cumsum(rng.uniform(-3.0, 3.0, (rows[i], 2)), axis=0)
+        path[path_off[i]:path_off[i + 1], :2] = xy
+        path[path_off[i]:path_off[i + 1], 2] = t
+    kind = np.where(rng.random(m) < 0.5, 6, 7).astype(np.int32)
+    return dict(kind=kind, used=np.ones(m, dtype=np.uint8), life_span=np.full(m, 1000000000000.0),
+                origin=origin, radius=radius, path_off=path_off, path=path)
+
+
+def timed_segments(n, seed, lo=0.0, hi=50.0, t_max=30.0):
+    """n robot moves (x, y, time) -> (x, y, time), a few units long, either time order"""
+    rng = np.random.default_rng(seed)
+    s = np.empty((n, 3))
+    s[:, 0] = rng.uniform(lo, hi, n)
+    s[:, 1] = rng.uniform(lo, hi, n)
+    s[:, 2] = rng.uniform(0.0, t_max, n)
+    e = s + np.stack([rng.uniform(-4, 4, n), rng.uniform(-4, 4, n), rng.uniform(-6, 6, n)], 1)
+    return s, e

@@ -185,7 +185,8 @@ DRRT_API int drrt_knn_batch_dev(drrt_store *h, int64_t nq, const double *q_dev, 
  * include/DRRT/obstacle.h:16-211) with the fields the analytic checker reads:
  * kind_, obstacle_used_, life_span_, origin_(0..1), radius_,
  * shape_.GetPolygon() rows -- all in the WORLD frame.
- * Kinds 6/7 (time-parametrised) -> DRRT_ERR_UNSUPPORTED. */
+ * Kinds 6/7 (time-parametrised) are refused here: they have their own table,
+ * drrt_timed_obstacles_set below. */
 DRRT_API int drrt_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind,
                        const uint8_t *used, const double *life_span,
                        const double *origin_xy, const double *radius,
@@ -214,6 +215,24 @@ DRRT_API int drrt_edgecheck_batch_dev(drrt_store *h, int64_t n, const double *st
                              double robot_radius, double r_min,
                              uint8_t *verdict_dev, double *length_dev,
                              void *stream);
+
+/* ---- time-parametrised obstacles: ExplicitEdgeCheck2D kinds 6 / 7 -------------------
+ * src/obstacle.cpp:805-875 (FindIndexBeforeTime src/drrt.cpp:178-189).  A disc of radius_ whose
+ * centre moves along path rows (dx, dy, time) relative to origin_; a segment is a robot move
+ * (x, y, TIME) -> (x, y, TIME).  verdict[i] = OR over the obstacles of ExplicitEdgeCheck2D(O,
+ * start_i, end_i, radius): for every path piece that overlaps the move in time, the centres at
+ * their (clamped) time of closest approach are closer than radius_ + radius.  The reference's
+ * planner never reaches this branch (space_has_time_ == false, src/smalltest.cpp:200); it is
+ * offered as the per-segment test it is.  path_off: n_obs + 1 row offsets into path_xyt. */
+DRRT_API int drrt_timed_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind,
+                             const uint8_t *used, const double *life_span,
+                             const double *origin_xy, const double *radius,
+                             const int32_t *path_off, const double *path_xyt);
+DRRT_API int drrt_edgecheck2d_timed_batch(drrt_store *h, int64_t n, const double *start_xyt,
+                                 const double *end_xyt, double radius, uint8_t *verdict);
+DRRT_API int drrt_edgecheck2d_timed_batch_dev(drrt_store *h, int64_t n, const double *start_dev,
+                                     const double *end_dev, double radius,
+                                     uint8_t *verdict_dev, void *stream);
 
 /* ---- obstacle add / remove sweeps ------------------------
  * AddObstacle src/obstacle.cpp:612-667 and RemoveObstacle :669-754 re-check the

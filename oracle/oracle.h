@@ -119,6 +119,22 @@ typedef struct {
 /* ExplicitEdgeCheck2D src/obstacle.cpp:756-804 (kinds 0-5), one obstacle.
  * If clearance!=NULL it is lowered to the smallest |margin| seen:
  *   |sqrt(dist_sqrd)-(radius+O.radius)| and |sqrt(seg_dist_sqrd)-radius|   */
+/* time-parametrised obstacles (kinds 6 / 7): path rows (dx, dy, time) relative to origin */
+typedef struct {
+  int n;
+  const int *kind;
+  const unsigned char *used;
+  const double *life_span;
+  const double *origin; /* n x 2 */
+  const double *radius;
+  const int *path_off;  /* n + 1 */
+  const double *path;   /* path_off[n] x 3 */
+} ref_timed_obstacles;
+int ref_edge_check_2d_timed(const ref_timed_obstacles *O, int o, const double *start, const double *end,
+                            double radius, double *clearance);
+void ref_edge_check_timed_batch(const ref_timed_obstacles *O, long n, const double *start, const double *end,
+                                double radius, unsigned char *verdict, double *clearance);
+
 int ref_edge_check_2d(const ref_obstacles *O, int o, const double *p0,
                       const double *p1, double radius, double *clearance);
 

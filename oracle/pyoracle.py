@@ -39,6 +39,11 @@ class _Obstacles(C.Structure):
                 ("vert_off", c_ip), ("verts", c_dp)]
 
 
+class _TimedObstacles(C.Structure):
+    _fields_ = [("n", C.c_int), ("kind", c_ip), ("used", c_u8p), ("life_span", c_dp), ("origin", c_dp),
+                ("radius", c_dp), ("path_off", c_ip), ("path", c_dp)]
+
+
 class _Traj(C.Structure):
     _fields_ = [("type", C.c_char * 4), ("dist", C.c_double), ("npts", C.c_int),
                 ("x", C.c_double * TRAJ_MAX), ("y", C.c_double * TRAJ_MAX)]
@@ -87,6 +92,8 @@ def lib():
                                            c_u8p, c_dp, c_dp, C.c_int]
         L.ref_point_check_batch.argtypes = [C.POINTER(_Obstacles), C.c_long, c_dp,
                                             C.c_double, C.c_double, C.c_int, c_u8p, C.c_int]
+        L.ref_edge_check_timed_batch.argtypes = [C.POINTER(_TimedObstacles), C.c_long, c_dp, c_dp,
+                                                 C.c_double, c_u8p, c_dp]
         L.ref_num_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -249,6 +256,32 @@ class RefObstacles:
                                     float(robot_radius), float(collision_distance), metric,
                                     verdict.ctypes.data_as(c_u8p), nthreads)
         return verdict
+
+
+class RefTimedObstacles:
+    """kinds 6 / 7 of ExplicitEdgeCheck2D (obstacle.cpp:805-875): obstacles moving along a path of
+    (dx, dy, time) rows relative to origin_; segments are (x, y, time) -> (x, y, time)"""
+
+    def __init__(self, kind, used, life_span, origin, radius, path_off, path):
+        self.kind = np.ascontiguousarray(kind, dtype=np.int32)
+        self.used = np.ascontiguousarray(used, dtype=np.uint8)
+        self.life_span = _f64(life_span)
+        self.origin = _f64(origin, (-1, 2))
+        self.radius = _f64(radius)
+        self.path_off = np.ascontiguousarray(path_off, dtype=np.int32)
+        self.path = _f64(path, (-1, 3))
+        self._s = _TimedObstacles(len(self.kind), _i(self.kind), self.used.ctypes.data_as(c_u8p),
+                                  _d(self.life_span), _d(self.origin), _d(self.radius), _i(self.path_off),
+                                  _d(self.path))
+
+    def edge_check_batch(self, start, end, radius=0.5, want_clearance=False):
+        start = _f64(start, (-1, 3)); end = _f64(end, (-1, 3))
+        n = start.shape[0]
+        verdict = np.zeros(n, dtype=np.uint8)
+        clr = np.zeros(n, dtype=np.float64) if want_clearance else None
+        lib().ref_edge_check_timed_batch(C.byref(self._s), n, _d(start), _d(end), float(radius),
+                                         verdict.ctypes.data_as(c_u8p), _d(clr) if clr is not None else None)
+        return (verdict, clr) if want_clearance else verdict
 
 
 def dubins_trajectory(start, end, r_min=1.0, metric=METRIC_R2S1):

@@ -213,3 +213,17 @@ def loop_time(obstacles, iters, mode=0, seed=0xD2270011, delta=5.0, gamma=100.0,
         BIN = old
     v = struct.unpack_from("<qqqqqqdd", raw, 0)
     return dict(zip(("nodes", "hits", "edges", "collisions", "blocked", "key_sum", "len_sum", "seconds"), v))
+
+
+def timed(obstacles, start, end, radius=0.5):
+    """ExplicitEdgeCheck2D with kind 6 / 7 obstacles (obstacle.cpp:805-875): verdict per (x, y, time) segment,
+    OR over the obstacles.  obstacles: dict(kind, used, life_span, origin, radius, path_off, path)"""
+    o = obstacles
+    kind = np.ascontiguousarray(o["kind"], dtype=np.int32)
+    s = np.ascontiguousarray(start, dtype=np.float64).reshape(-1, 3)
+    e = np.ascontiguousarray(end, dtype=np.float64).reshape(-1, 3)
+    payload = (struct.pack("<di", radius, len(kind)) + kind.tobytes()
+               + np.ascontiguousarray(o["used"], dtype=np.uint8).tobytes() + _f64(o["life_span"]) + _f64(o["origin"])
+               + _f64(o["radius"]) + np.ascontiguousarray(o["path_off"], dtype=np.int32).tobytes() + _f64(o["path"])
+               + struct.pack("<q", len(s)) + _f64(s) + _f64(e))
+    return np.frombuffer(_run("timed", payload), dtype=np.uint8, count=len(s)).copy()

@@ -8,8 +8,8 @@
  *       (DetectBulletCollision), absent from the reference tree and
  *       unpinned; SURVEY 8c fixes the oracle to the in-tree analytic test.
  *   QuickCheck2D / ExplicitPointCheck2D / ExplicitPointCheck :925-1090
- * Kinds 6/7 (time-parametrised, :805-875) need a time dimension the path never
- * has (space_has_time_ == false, smalltest.cpp:200) and are rejected upstream.
+ * Kinds 6/7 (time-parametrised, :805-875): ref_edge_check_2d_timed below -- the
+ * planner itself never reaches them (space_has_time_ == false, smalltest.cpp:200).
  */
 #include "oracle.h"
 
@@ -165,5 +165,72 @@ void ref_point_check_batch(const ref_obstacles *O, long n, const double *pts,
     for (int o = 0; o < O->n && !hit; o++)
       hit = explicit_point_check_2d(O, o, pt, robot_radius, collision_distance, metric);
     verdict[i] = (unsigned char)hit;
+  }
+}
+
+
+/* ---- ExplicitEdgeCheck2D, kinds 6 / 7 (obstacle.cpp:805-875) ------------------------------
+ * start / end are (x, y, TIME); the obstacle moves along path rows (dx, dy, time) relative to
+ * origin_.  FindIndexBeforeTime: src/drrt.cpp:178-189. */
+static int find_index_before_time(const double *path, int rows, double t) {
+  if (rows < 1) return -1;
+  int i = -1;
+  while (i + 1 < rows && path[3 * (i + 1) + 2] < t) i += 1;
+  return i;
+}
+
+int ref_edge_check_2d_timed(const ref_timed_obstacles *O, int o, const double *start, const double *end,
+                            double radius, double *clearance) {
+  if (!O->used[o] || O->life_span[o] <= 0) return 0; /* :761 */
+  if (O->kind[o] != 6 && O->kind[o] != 7) return 0;
+  const double *path = O->path + 3 * (size_t)O->path_off[o];
+  const int rows = O->path_off[o + 1] - O->path_off[o];
+  const double *early = start, *late = end; /* :813-819 */
+  if (!(start[2] < end[2])) { early = end; late = start; }
+  int first = find_index_before_time(path, rows, early[2]);
+  if (first < 0) first = 0;
+  int last = find_index_before_time(path, rows, late[2]);
+  if (last > rows - 1) last = rows - 1;
+  if (last <= first) return 0; /* :825 */
+  int hit = 0;
+  for (int i_start = first; i_start < last; i_start++) {
+    const int i_end = i_start + 1;
+    double x_1 = early[0], y_1 = early[1], t_1 = early[2];
+    double x_2 = path[3 * i_start] + O->origin[2 * o];
+    double y_2 = path[3 * i_start + 1] + O->origin[2 * o + 1];
+    double t_2 = path[3 * i_start + 2];
+    double m_x1 = (late[0] - x_1) / (late[2] - t_1);
+    double m_y1 = (late[1] - y_1) / (late[2] - t_1);
+    double m_x2 = (path[3 * i_end] + O->origin[2 * o] - x_2) / (path[3 * i_end + 2] - t_2);
+    double m_y2 = (path[3 * i_end + 1] + O->origin[2 * o + 1] - y_2) / (path[3 * i_end + 2] - t_2);
+    double t_c = (m_x1 * m_x1 * t_1 + m_x2 * (m_x2 * t_2 + x_1 - x_2) - m_x1 * (m_x2 * (t_1 + t_2) + x_1 - x_2) +
+                  (m_y1 - m_y2) * (m_y1 * t_1 - m_y2 * t_2 - y_1 + y_2)) /
+                 ((m_x1 - m_x2) * (m_x1 - m_x2) + (m_y1 - m_y2) * (m_y1 - m_y2));
+    double lo = (t_1 < t_2) ? t_2 : t_1;                                     /* std::max */
+    double hi = (path[3 * i_end + 2] < late[2]) ? path[3 * i_end + 2] : late[2]; /* std::min */
+    if (t_c < lo) t_c = lo;
+    else if (t_c > hi) t_c = hi;
+    double r_x = m_x1 * (t_c - t_1) + x_1, r_y = m_y1 * (t_c - t_1) + y_1;
+    double o_x = m_x2 * (t_c - t_2) + x_2, o_y = m_y2 * (t_c - t_2) + y_2;
+    double d2 = (r_x - o_x) * (r_x - o_x) + (r_y - o_y) * (r_y - o_y);
+    double reach = O->radius[o] + radius;
+    if (clearance && d2 == d2) note_margin(clearance, sqrt(d2) - reach);
+    if (d2 < reach * reach) {
+      if (!clearance) return 1;
+      hit = 1;
+    }
+  }
+  return hit;
+}
+
+void ref_edge_check_timed_batch(const ref_timed_obstacles *O, long n, const double *start, const double *end,
+                                double radius, unsigned char *verdict, double *clearance) {
+  for (long i = 0; i < n; i++) {
+    int hit = 0;
+    double c = 1e300;
+    for (int o = 0; o < O->n && (!hit || clearance); o++)
+      if (ref_edge_check_2d_timed(O, o, start + 3 * i, end + 3 * i, radius, clearance ? &c : NULL)) hit = 1;
+    verdict[i] = (unsigned char)hit;
+    if (clearance) clearance[i] = c;
   }
 }

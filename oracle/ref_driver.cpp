@@ -512,6 +512,51 @@ static int cmd_loop(Reader &in, Writer &out) {
   return 0;
 }
 
+// ---- ExplicitEdgeCheck2D kinds 6 / 7 (obstacle.cpp:805-875) ---------------------------------
+// time-parametrised obstacles: origin_, path_ rows (dx, dy, time); segments (x, y, time)
+static int cmd_timed(Reader &in, Writer &out) {
+  double radius = in.get<double>();
+  int32_t n_obs = in.get<int32_t>();
+  std::vector<int32_t> kind = in.arr<int32_t>(n_obs);
+  std::vector<uint8_t> used = in.arr<uint8_t>(n_obs);
+  std::vector<double> life = in.arr<double>(n_obs), origin = in.arr<double>(2 * n_obs), rad = in.arr<double>(n_obs);
+  std::vector<int32_t> poff = in.arr<int32_t>(n_obs + 1);
+  std::vector<double> path = in.arr<double>(3 * (size_t)(n_obs ? poff[n_obs] : 0));
+  shared_ptr<ConfigSpace> C = make_cspace(0, 1.0, radius, 0.1);
+  std::vector<shared_ptr<Obstacle>> obs;
+  for (int i = 0; i < n_obs; i++) {
+    Eigen::MatrixX2d poly;
+    poly.resize(0, 2);
+    Eigen::VectorXd o(3);
+    o(0) = origin[2 * i]; o(1) = origin[2 * i + 1]; o(2) = 0.0;
+    const int rows = poff[i + 1] - poff[i];
+    Eigen::MatrixXd p;
+    p.resize(rows, 3);
+    for (int r = 0; r < rows; r++)
+      for (int k = 0; k < 3; k++) p(r, k) = path[3 * (size_t)(poff[i] + r) + k];
+    Eigen::VectorXd times;
+    shared_ptr<Obstacle> O = make_shared<Obstacle>(3, poly, true, o, p, times);
+    O->kind_ = kind[i];
+    O->obstacle_used_ = used[i] != 0;
+    O->life_span_ = life[i];
+    O->radius_ = rad[i];
+    O->path_ = p;
+    O->cspace = C;
+    obs.push_back(O);
+  }
+  int64_t n = in.get<int64_t>();
+  std::vector<double> s = in.arr<double>(3 * n), e = in.arr<double>(3 * n);
+  std::vector<uint8_t> verdict(n, 0);
+  for (int64_t i = 0; i < n; i++) {
+    bool hit = false;
+    for (size_t o = 0; o < obs.size() && !hit; o++)
+      hit = ExplicitEdgeCheck2D(obs[o], vec3(&s[3 * i]), vec3(&e[3 * i]), radius);
+    verdict[i] = hit ? 1 : 0;
+  }
+  out.arr(verdict);
+  return 0;
+}
+
 // ---- node validity ------------------------------------------------------------
 static int cmd_points(Reader &in, Writer &out) {
   int metric = in.get<int32_t>();
@@ -562,6 +607,7 @@ int main(int argc, char **argv) {
     return cmd_edges(cmd, in, out);
   if (!strcmp(cmd, "points")) return cmd_points(in, out);
   if (!strcmp(cmd, "loop_time")) return cmd_loop(in, out);
+  if (!strcmp(cmd, "timed")) return cmd_timed(in, out);
   if (!strcmp(cmd, "obsfile")) return cmd_obsfile(cmd, in, out);
   if (!strcmp(cmd, "geom")) return cmd_geom(in, out);
   fprintf(stderr, "unknown command %s\n", cmd);

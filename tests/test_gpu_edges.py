@@ -284,3 +284,41 @@ def test_edge_ids_out_of_range_are_refused(drrt):
             assert ei.value.code == drrt.capi.ERR_INVALID
     v2, _ = t.ExplicitEdgeCheckIds(a, b)                      # the handle still works afterwards
     assert np.array_equal(v, v2)
+
+
+def test_timed_obstacles_kinds_6_7(drrt, po):
+    """ExplicitEdgeCheck2D kinds 6 / 7 (obstacle.cpp:805-875) on the device against the oracle and
+    the committed verdicts of the compiled reference; verdicts may differ only where the centres'
+    closest approach is within 1e-6 of radius_ + radius"""
+    import importlib.util
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_ref_timed_golden",
+                                                  os.path.join(here, "golden", "make_ref_timed_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    I = gen.inputs()
+    with open(os.path.join(here, "golden", "ref_timed_v1.json")) as fh:
+        gold = json.load(fh)
+    t = drrt.KDTree()
+    t.SetTimedObstacles(**I["o"])
+    for r in I["radii"]:
+        v = t.ExplicitEdgeCheck2DTimed(I["s"], I["e"], r)
+        want = np.array(gold["verdict"][str(r)], dtype=np.uint8)
+        _, clr = po.RefTimedObstacles(**I["o"]).edge_check_batch(I["s"], I["e"], r, want_clearance=True)
+        diff = np.nonzero(v != want)[0]
+        assert (clr[diff] < BAND).all() and len(diff) <= 1
+    o = synth.timed_obstacles(64, 0xC9)
+    s, e = synth.timed_segments(300_000, 0xCA)
+    t.SetTimedObstacles(**o)
+    v = t.ExplicitEdgeCheck2DTimed(s, e, 0.5)
+    rv, clr = po.RefTimedObstacles(**o).edge_check_batch(s, e, 0.5, want_clearance=True)
+    diff = np.nonzero(v != rv)[0]
+    assert (clr[diff] < BAND).all() and len(diff) <= 3
+    assert 0.05 < v.mean() < 0.6
+    # the two tables are separate: kinds 6 / 7 are refused by the static table and vice versa
+    with pytest.raises(drrt.DrrtError):
+        t.SetTimedObstacles(**dict(o, kind=np.full(64, 3)))
+    t.SetTimedObstacles(**dict(o, used=np.zeros(64, dtype=np.uint8)))
+    assert not t.ExplicitEdgeCheck2DTimed(s[:1000], e[:1000], 0.5).any()

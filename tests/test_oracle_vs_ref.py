@@ -167,3 +167,29 @@ def test_timing_commands_of_the_reference_driver(po):
     v, _ = po.RefObstacles(**o).edge_check_batch(s, e)
     hits, secs = pyref.edge_time(s, e, o)
     assert hits == int(v.sum()) and secs > 0.0
+
+
+def _timed_gen():
+    spec2 = importlib.util.spec_from_file_location("make_ref_timed_golden",
+                                                   os.path.join(HERE, "golden", "make_ref_timed_golden.py"))
+    m = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(m)
+    return m
+
+
+def test_timed_obstacles_match_reference(po):
+    """ExplicitEdgeCheck2D kinds 6 / 7 (obstacle.cpp:805-875): the oracle's restatement against the
+    committed verdicts of the compiled reference, and live against the binary when it is here"""
+    I = _timed_gen().inputs()
+    with open(os.path.join(HERE, "golden", "ref_timed_v1.json")) as fh:
+        gold = json.load(fh)
+    ro = po.RefTimedObstacles(**I["o"])
+    for r in I["radii"]:
+        v = ro.edge_check_batch(I["s"], I["e"], r)
+        assert v.tolist() == gold["verdict"][str(r)]
+        assert 0.02 < v.mean() < 0.6
+    from oracle import pyref
+    if pyref.available():
+        o = synth.timed_obstacles(40, 0xC7)
+        s, e = synth.timed_segments(6000, 0xC8)
+        assert np.array_equal(pyref.timed(o, s, e, 0.8), po.RefTimedObstacles(**o).edge_check_batch(s, e, 0.8))
