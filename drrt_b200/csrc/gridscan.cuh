@@ -147,14 +147,18 @@ __device__ __forceinline__ void sqrt_thresholds(double r, double &t_lt, double &
 
 // Fills the probe (ghost) and the candidate cell ranges of a query of radius r:
 // every node n with metric(p,n) <= r for a probe p lies in the selected cells.
-template <int METRIC>
+// THRESH: whether the exact sqrt thresholds are computed here (the range kernels decide on them;
+// the CTA kernel computes them for a whole slice of queries at once and passes them in, the
+// k-nearest kernels never look at them)
+template <int METRIC, bool THRESH = true>
 __device__ __forceinline__ void setup_query(const GridView &A, double qx, double qy, double qt,
                                             double r, Query &Q) {
   Q.x = qx;
   Q.y = qy;
   Q.t = qt;
   Q.r = r;
-  sqrt_thresholds(Q.r, Q.t_lt, Q.t_le);
+  if (THRESH) sqrt_thresholds(Q.r, Q.t_lt, Q.t_le);
+  else { Q.t_lt = 0.0; Q.t_le = 0.0; }
   Q.has_ghost = false;
   Q.gt = 0.0;
   if (A.has_wrap) Q.has_ghost = ghost_of<METRIC>(Q.x, Q.y, Q.t, A.wrap_point, Q.r, &Q.gt);
@@ -339,8 +343,10 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
         for (int u = 0; u < UNR; u++) {
           const int i = base + u * 32 + lane;
           valid[u] = i < c1;
+#ifndef DRRT_SCAN_NOPRED
           nx[u] = ny[u] = nt[u] = 0.0;
           id[u] = 0;
+#endif
           const int2 e = runs[min(jl + lane, nent)];  // runs[nent] is the sentinel
           // bit b of `ends`: some run of the window ends (exclusively) at candidate i0 + b.  Run jl
           // holds i0, so b >= 1, and runs are never empty, so the bits are distinct.
@@ -349,7 +355,13 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
           const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
           const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
           const int ey = __shfl_sync(0xffffffffu, e.y, k);
+#ifdef DRRT_SCAN_NOPRED
+          // padding lanes load SOME record (index clamped into the array) instead of being
+          // predicated off: no zero-fill, no predicated copies around the load; `valid` gates the hit
+          load_rec(A.rec + min(max(i + ey, 0), (int)A.n_indexed - 1), nx[u], ny[u], nt[u], id[u]);
+#else
           if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u]);
+#endif
           jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
         }
         f(valid, nx, ny, nt, id);

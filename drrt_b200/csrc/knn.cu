@@ -118,7 +118,7 @@ knn_kernel(KnnArgs A) {
       Query Q;
       bool all = true;
       if (V.n_indexed > 0) {
-        setup_query<METRIC>(V, px, py, pt, r, Q);
+        setup_query<METRIC, false>(V, px, py, pt, r, Q);
         Q.has_ghost = false;
         all = covers_all(V, Q);
         scan_columns(V, Q, 0, 1, s_runs[w], s_pref[w], lane, visit);
@@ -232,7 +232,7 @@ knn_select_kernel(KnnArgs A, int32_t *fallback) {
     all = true;
     if (V.n_indexed > 0) {
       Query Q;
-      setup_query<METRIC>(V, qx, qy, qt, r, Q);
+      setup_query<METRIC, false>(V, qx, qy, qt, r, Q);
       Q.has_ghost = false;
       all = covers_all(V, Q);
       scan_columns(V, Q, 0, 1, s_runs[w], s_pref[w], lane, visit);

@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
   __shared__ long long s_tmp[WARPS];
   __shared__ int s_wsum[WARPS];
   __shared__ Query s_query;
-  __shared__ double s_q[CTA_CHUNK][4];
+  __shared__ double s_q[CTA_CHUNK][6];  // x y theta radius + the exact sqrt thresholds of the radius
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const GridView &V = A.V;
@@ -530,6 +530,8 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
       double v = 0.0;
       if (qk < q1) v = c < 3 ? A.q[3 * qk + c] : (A.radius ? A.radius[qk] : A.radius_all);
       s_q[k][c] = v;
+      // the thresholds of all the slice's radii at once, off the per-query critical path
+      if (c == 3) sqrt_thresholds(v, s_q[k][4], s_q[k][5]);
     }
     __syncthreads();
 
@@ -539,7 +541,9 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
       if (w == 0) {
         Query Q0;
         const double *sq = s_q[qi - q0];
-        setup_query<METRIC>(V, sq[0], sq[1], sq[2], sq[3], Q0);
+        setup_query<METRIC, false>(V, sq[0], sq[1], sq[2], sq[3], Q0);
+        Q0.t_lt = sq[4];
+        Q0.t_le = sq[5];
         if (lane == 0) s_query = Q0;
       }
       __syncthreads();
