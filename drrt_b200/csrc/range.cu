@@ -493,12 +493,14 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
   int2 *runs = reinterpret_cast<int2 *>(smem_raw + CTA_OFF_RUNS);
   unsigned *clist = reinterpret_cast<unsigned *>(smem_raw + CTA_OFF_RUNS);  // after the scan
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + CTA_OFF_HIST);
-  __shared__ long long s_chunk;
+  __shared__ long long s_chunk, s_chunk_next;
   __shared__ int s_count, s_crowded, s_nlist;
   __shared__ long long s_tmp[WARPS];
   __shared__ int s_wsum[WARPS];
   __shared__ Query s_query;
-  __shared__ double s_q[CTA_CHUNK][6];  // x y theta radius + the exact sqrt thresholds of the radius
+  // the probes of a whole slice, set up by CTA_CHUNK threads at once at the top of the slice (ghost,
+  // cell ranges, the exact sqrt thresholds of the radius): nothing of it sits on a query's critical path
+  __shared__ Query s_slice[CTA_CHUNK];
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const GridView &V = A.V;
@@ -511,9 +513,10 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
     shift = max(0, bits - 14);
   }
 
+  if (tid == 0) s_chunk_next = (long long)atomicAdd(A.ticket, 1);
   for (;;) {
     __syncthreads();  // everyone is done with the previous chunk (and its s_chunk)
-    if (tid == 0) s_chunk = (long long)atomicAdd(A.ticket, 1);
+    if (tid == 0) s_chunk = s_chunk_next;  // taken while the previous slice's last query was answered
     __syncthreads();
     const int64_t ck = s_chunk;
     if (ck >= A.nchunks) break;
@@ -524,27 +527,25 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
     bool over = false;  // some row did not fit the slice
     // the slice's queries in one round of loads (the barrier at the top of the loop ordered the
     // previous slice's reads of s_q)
-    if (tid < 4 * CTA_CHUNK) {
-      const int k = tid >> 2, c = tid & 3;
-      const int64_t qk = q0 + k;
-      double v = 0.0;
-      if (qk < q1) v = c < 3 ? A.q[3 * qk + c] : (A.radius ? A.radius[qk] : A.radius_all);
-      s_q[k][c] = v;
-      // the thresholds of all the slice's radii at once, off the per-query critical path
-      if (c == 3) sqrt_thresholds(v, s_q[k][4], s_q[k][5]);
+    if (tid < CTA_CHUNK && q0 + tid < q1) {
+      const int64_t qk = q0 + tid;
+      Query Qk;
+      setup_query<METRIC, true>(V, A.q[3 * qk], A.q[3 * qk + 1], A.q[3 * qk + 2],
+                                A.radius ? A.radius[qk] : A.radius_all, Qk);
+      s_slice[tid] = Qk;
     }
     __syncthreads();
 
     for (int64_t qi = q0; qi < q1; qi++) {
       if (tid == 0) { s_count = 0; s_crowded = 0; s_nlist = 0; }
+      // the next slice's ticket is requested one query ahead: the round trip of the global atomic
+      // is off the slice boundary, and a CTA never holds more than one query's worth of work back
+      if (tid == 32 && qi == q1 - 1) s_chunk_next = (long long)atomicAdd(A.ticket, 1);
       for (int i = tid; i < CTA_NW / 4; i += T) reinterpret_cast<uint4 *>(hist)[i] = make_uint4(0, 0, 0, 0);
-      if (w == 0) {
-        Query Q0;
-        const double *sq = s_q[qi - q0];
-        setup_query<METRIC, false>(V, sq[0], sq[1], sq[2], sq[3], Q0);
-        Q0.t_lt = sq[4];
-        Q0.t_le = sq[5];
-        if (lane == 0) s_query = Q0;
+      if (w == 0) {  // the query's probe to its fixed place (a word per lane; no indexed reads in the scan)
+        static_assert(sizeof(Query) % 4 == 0 && sizeof(Query) <= 128, "one 32-bit word per lane");
+        if (lane < (int)(sizeof(Query) / 4))
+          reinterpret_cast<unsigned *>(&s_query)[lane] = reinterpret_cast<const unsigned *>(&s_slice[qi - q0])[lane];
       }
       __syncthreads();
       const Query Q = s_query;
