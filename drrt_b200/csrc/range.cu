@@ -693,10 +693,23 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         __syncthreads();
         // the staged values are squared sums: the keys' square roots are taken here, on
         // independent elements, instead of inside the scan's dependency chain
-        for (int p = tid; p < n; p += T) {
-          const int slot = tmp[p];
-          oid[p] = sid[slot];
-          od[p] = sqrt(sdist[slot]);
+        // (four elements per thread in flight: the two dependent shared-memory reads and the square
+        // root of one element overlap with its neighbours')
+        for (int p0 = tid; p0 < n; p0 += 4 * T) {
+          int slot[4], rid[4];
+          double rs[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) slot[k] = tmp[min(p0 + k * T, n - 1)];
+#pragma unroll
+          for (int k = 0; k < 4; k++) { rid[k] = sid[slot[k]]; rs[k] = sdist[slot[k]]; }
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int p = p0 + k * T;
+            if (p < n) {
+              oid[p] = rid[k];
+              od[p] = sqrt(rs[k]);
+            }
+          }
         }
       } else if (staged) {
         // ids bunched in a few buckets: network sort of (id, slot) keys
