@@ -232,7 +232,7 @@ def run_reference(args):
                                        "per step" % (radius, ref["queries_per_pass"])},
                 "cpu_baseline": {k: ref[k] for k in ("value", "unit", "cores", "kind", "sample", "hits_per_query")},
                 "e2e": {"value": ref["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     # (b) the oracle port (plain-C restatement, bit-identical results), all host threads
     from oracle import pyoracle as po
@@ -262,7 +262,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d config-2a queries per step x %d steps" % (sample, args.steps)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def ncu_traffic(kernel_prefix):
@@ -309,8 +309,31 @@ def rows_checksum(torch, tree, res):
                         torch.tensor(t, device=ids.device, dtype=torch.int64)])
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: whatever libraries print to file descriptor 1 (NCCL's
+    version banner, for one) is sent to stderr; emit() writes to the saved descriptor"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     global N_NODES
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -781,7 +804,7 @@ def main():
                 "data": "synthetic", "config": config, "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "extra": extra}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -852,10 +875,14 @@ def comm_strong_scaling(n_gpus, nodes_h, q_h, radius, hits, s_h, e_h):
     ne = len(s_h)
     v, k4 = pinned_empty(ne, np.uint8)
     ln, k5 = pinned_empty(ne, np.float64)
-    sec = wall(lambda: c.ExplicitEdgeCheck(s_h, e_h, robot_radius=synth.ROBOT_RADIUS, r_min=synth.R_MIN,
-                                           verdict=v, length=ln), 2)
+    sp, k6 = pinned_empty(3 * ne, np.float64)
+    ep, k7 = pinned_empty(3 * ne, np.float64)
+    sp[:] = s_h.reshape(-1)
+    ep[:] = e_h.reshape(-1)
+    sec = wall(lambda: c.ExplicitEdgeCheck(sp.reshape(-1, 3), ep.reshape(-1, 3), robot_radius=synth.ROBOT_RADIUS,
+                                           r_min=synth.R_MIN, verdict=v, length=ln), 2)
     out["edge_check"] = {"edges_per_s": ne / sec, "ms_per_step": 1e3 * sec, "collision_rate": float(v.mean()),
-                         "note": "poses in pageable numpy memory (48 B per edge up)"}
+                         "h2d_bytes_per_step": 48 * ne, "d2h_bytes_per_step": 9 * ne}
     c.close()
     return out
 
