@@ -192,15 +192,13 @@ __device__ __forceinline__ bool covers_all(const GridView &A, const Query &Q) {
   return Q.all;
 }
 
-// The cell_start INDICES that bound the one or two contiguous record runs of candidate column
-// `col`: run a = records [cell_start[a0], cell_start[a1]), run b likewise (b0 < 0: none);
-// a0 < 0: the column's footprint cannot come within the query radius.  Pure arithmetic -- the
-// CTA kernel computes it for the NEXT query while it scans the current one.
-__device__ __forceinline__ void column_cells(const GridView &A, const Query &Q, int col, int ncol,
-                                             int ncy, double cull, int &a0, int &a1, int &b0,
-                                             int &b1) {
+// the one or two contiguous record runs of candidate column `col` (empty when
+// the column's footprint cannot come within the query radius)
+__device__ __forceinline__ void column_runs(const GridView &A, const Query &Q, int col, int ncol,
+                                            int ncy, double cull, int &s0, int &l0, int &s1,
+                                            int &l1) {
   const GridParams &g = A.gp;
-  a0 = a1 = b0 = b1 = -1;
+  s0 = l0 = s1 = l1 = 0;
   if (col >= ncol) return;
   int ix = Q.ix0 + col / ncy, iy = Q.iy0 + col % ncy;
   // closest approach of the column's footprint (edge columns are open-ended)
@@ -221,28 +219,11 @@ __device__ __forceinline__ void column_cells(const GridView &A, const Query &Q, 
     theta_runs(g, Q.key, half, ta0, ta1, tb0, tb1);
   }
   int cbase = (ix * g.ny + iy) * g.nt;
-  a0 = cbase + ta0;
-  a1 = cbase + ta1 + 1;
+  s0 = A.cell_start[cbase + ta0];
+  l0 = A.cell_start[cbase + ta1 + 1] - s0;
   if (tb0 <= tb1) {
-    b0 = cbase + tb0;
-    b1 = cbase + tb1 + 1;
-  }
-}
-
-// the one or two contiguous record runs of candidate column `col` (empty when
-// the column's footprint cannot come within the query radius)
-__device__ __forceinline__ void column_runs(const GridView &A, const Query &Q, int col, int ncol,
-                                            int ncy, double cull, int &s0, int &l0, int &s1,
-                                            int &l1) {
-  int a0, a1, b0, b1;
-  column_cells(A, Q, col, ncol, ncy, cull, a0, a1, b0, b1);
-  s0 = l0 = s1 = l1 = 0;
-  if (a0 < 0) return;
-  s0 = A.cell_start[a0];
-  l0 = A.cell_start[a1] - s0;
-  if (b0 >= 0) {
-    s1 = A.cell_start[b0];
-    l1 = A.cell_start[b1] - s1;
+    s1 = A.cell_start[cbase + tb0];
+    l1 = A.cell_start[cbase + tb1 + 1] - s1;
   }
 }
 
@@ -303,104 +284,89 @@ __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, 
 // 32-run window held in the warp's registers (one REDUX.OR + POPC).  runs holds 2*T+1
 // entries, tmp64 NWARPS words.
 // f(valid[UNR], x[UNR], y[UNR], theta[UNR], id[UNR]) is called converged.
-// CTA-wide prefix over the columns' runs (one column per thread: record start / length of its run
-// and wrapped run) -> the compact list of non-empty runs in `runs` (+ sentinel).  One barrier
-// inside (tmp64); the caller orders the runs[] writes before their first read.  Returns the
-// candidate total and the number of runs (CTA-uniform).
-template <int NWARPS>
-__device__ __forceinline__ void runs_from_columns_cta(int s0, int l0, int s1, int l1, int2 *runs, int cap,
-                                                      long long *tmp64, int &total, int &nent) {
-  constexpr int T = NWARPS * 32;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int nrun = (l0 > 0) + (l1 > 0);
-  const long long mine = ((long long)nrun << 32) | (unsigned)(l0 + l1);
-  long long inc = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    long long t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) tmp64[w] = inc;
-  __syncthreads();
-  // every warp scans the NWARPS warp totals with its first lanes
-  static_assert(NWARPS <= 32, "one lane per warp total");
-  long long wt = (lane < NWARPS) ? tmp64[lane] : 0, winc = wt;
-#pragma unroll
-  for (int o = 1; o < NWARPS; o <<= 1) {
-    long long t = __shfl_up_sync(0xffffffffu, winc, o);
-    if (lane >= o) winc += t;
-  }
-  const long long all = __shfl_sync(0xffffffffu, winc, NWARPS - 1);
-  const long long wbase = __shfl_sync(0xffffffffu, winc - wt, w);
-  const long long excl64 = wbase + inc - mine;
-  const int excl = (int)(excl64 & 0xffffffffll), slot = (int)(excl64 >> 32);
-  total = (int)(all & 0xffffffffll);
-  nent = (int)(all >> 32);
-  // (`cap` entries, sentinel included: a list that does not fit is cut -- the caller sees nent >= cap)
-  if (l0 > 0 && slot < cap) runs[slot] = make_int2(excl + l0, s0 - excl);
-  if (l1 > 0 && slot + (l0 > 0) < cap) runs[slot + (l0 > 0)] = make_int2(excl + l0 + l1, s1 - (excl + l0));
-  if (tid == T - 1 && nent < cap) runs[nent] = make_int2(0x7fffffff, 0);
-}
-
-// The scan proper over a finished run list: each warp takes an equal contiguous slice of the
-// candidate numbers [0, total), every lane UNR candidates per trip.  No barrier inside.
-template <int NWARPS, int UNR, class F>
-__device__ __forceinline__ void scan_runs_cta(const GridView &A, const int2 *runs, int total, int nent, F f) {
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;
-  const int c0 = w * per, c1 = min(total, c0 + per);
-  if (c0 < c1) {
-    int lo = -1, hi = nent;  // smallest j with runs[j].x > c0
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (runs[mid].x > c0) hi = mid; else lo = mid;
-    }
-    int jl = hi;
-    // jl is warp-uniform: the run holding the first candidate of the next 32.  Runs are never
-    // empty, so those 32 candidates lie in runs jl .. jl+31: every lane fetches one of them, one
-    // warp-wide OR marks where runs end, and a lane's run is a population count away (no
-    // divergent walk, no chain of dependent shared-memory loads or shuffles).
-    for (int base = c0; base < c1; base += 32 * UNR) {
-      bool valid[UNR];
-      double nx[UNR], ny[UNR], nt[UNR];
-      int32_t id[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; u++) {
-        const int i = base + u * 32 + lane;
-        valid[u] = i < c1;
-        nx[u] = ny[u] = nt[u] = 0.0;
-        id[u] = 0;
-        const int2 e = runs[min(jl + lane, nent)];  // runs[nent] is the sentinel
-        // bit b of `ends`: some run of the window ends (exclusively) at candidate i0 + b.  Run jl
-        // holds i0, so b >= 1, and runs are never empty, so the bits are distinct.
-        const int i0 = base + u * 32;
-        const unsigned rel = (unsigned)(e.x - i0);
-        const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
-        const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
-        const int ey = __shfl_sync(0xffffffffu, e.y, k);
-        if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u]);
-        jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
-      }
-      f(valid, nx, ny, nt, id);
-    }
-  }
-}
-
-// A whole CTA of NWARPS warps visits ALL candidate columns of query Q, a batch of T columns at a
-// time: columns -> run list -> scan (the general form: any number of columns).
 template <int NWARPS, int UNR, class F>
 __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query &Q, int2 *runs,
                                                  long long *tmp64, F f) {
   constexpr int T = NWARPS * 32;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int ncy = Q.iy1 - Q.iy0 + 1;
   const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
   const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
   for (int cb = 0; cb < ncol; cb += T) {
-    int s0, l0, s1, l1, total, nent;
-    column_runs(A, Q, cb + (int)threadIdx.x, ncol, ncy, cull, s0, l0, s1, l1);
-    runs_from_columns_cta<NWARPS>(s0, l0, s1, l1, runs, 2 * T + 1, tmp64, total, nent);
+    int s0, l0, s1, l1;
+    column_runs(A, Q, cb + tid, ncol, ncy, cull, s0, l0, s1, l1);
+    const int nrun = (l0 > 0) + (l1 > 0);
+    const long long mine = ((long long)nrun << 32) | (unsigned)(l0 + l1);
+    long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) tmp64[w] = inc;
     __syncthreads();
-    scan_runs_cta<NWARPS, UNR>(A, runs, total, nent, f);
+    // every warp scans the NWARPS warp totals with its first lanes
+    static_assert(NWARPS <= 32, "one lane per warp total");
+    long long wt = (lane < NWARPS) ? tmp64[lane] : 0, winc = wt;
+#pragma unroll
+    for (int o = 1; o < NWARPS; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    const long long all = __shfl_sync(0xffffffffu, winc, NWARPS - 1);
+    const long long wbase = __shfl_sync(0xffffffffu, winc - wt, w);
+    const long long excl64 = wbase + inc - mine;
+    const int excl = (int)(excl64 & 0xffffffffll), slot = (int)(excl64 >> 32);
+    const int total = (int)(all & 0xffffffffll), nent = (int)(all >> 32);
+    if (l0 > 0) runs[slot] = make_int2(excl + l0, s0 - excl);
+    if (l1 > 0) runs[slot + (l0 > 0)] = make_int2(excl + l0 + l1, s1 - (excl + l0));
+    if (tid == T - 1) runs[nent] = make_int2(0x7fffffff, 0);
+    __syncthreads();
+    const int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;
+    const int c0 = w * per, c1 = min(total, c0 + per);
+    if (c0 < c1) {
+      int lo = -1, hi = nent;  // smallest j with runs[j].x > c0
+      while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (runs[mid].x > c0) hi = mid; else lo = mid;
+      }
+      int jl = hi;
+      // jl is warp-uniform: the run holding the first candidate of the next 32.  Runs are never
+      // empty, so those 32 candidates lie in runs jl .. jl+31: every lane fetches one of them, one
+      // warp-wide OR marks where runs end, and a lane's run is a population count away (no
+      // divergent walk, no chain of dependent shared-memory loads or shuffles).
+      for (int base = c0; base < c1; base += 32 * UNR) {
+        bool valid[UNR];
+        double nx[UNR], ny[UNR], nt[UNR];
+        int32_t id[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+          const int i = base + u * 32 + lane;
+          valid[u] = i < c1;
+#ifndef DRRT_SCAN_NOPRED
+          nx[u] = ny[u] = nt[u] = 0.0;
+          id[u] = 0;
+#endif
+          const int2 e = runs[min(jl + lane, nent)];  // runs[nent] is the sentinel
+          // bit b of `ends`: some run of the window ends (exclusively) at candidate i0 + b.  Run jl
+          // holds i0, so b >= 1, and runs are never empty, so the bits are distinct.
+          const int i0 = base + u * 32;
+          const unsigned rel = (unsigned)(e.x - i0);
+          const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+          const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
+          const int ey = __shfl_sync(0xffffffffu, e.y, k);
+#ifdef DRRT_SCAN_NOPRED
+          // padding lanes load SOME record (index clamped into the array) instead of being
+          // predicated off: no zero-fill, no predicated copies around the load; `valid` gates the hit
+          load_rec(A.rec + min(max(i + ey, 0), (int)A.n_indexed - 1), nx[u], ny[u], nt[u], id[u]);
+#else
+          if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u]);
+#endif
+          jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
+        }
+        f(valid, nx, ny, nt, id);
+      }
+    }
     __syncthreads();
   }
 }

@@ -490,17 +490,10 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
   uint16_t *wstart = reinterpret_cast<uint16_t *>(smem_raw + CTA_OFF_WSTART);
   uint16_t *tmp = reinterpret_cast<uint16_t *>(smem_raw + CTA_OFF_TMP);
   uint8_t *srank = reinterpret_cast<uint8_t *>(smem_raw + CTA_OFF_RANK);
-  // The run list of a query lives in `runs`.  While a query is scanned, the columns of the NEXT
-  // query of the slice are resolved (column_cells + 4-byte cp.async of their cell_start entries into
-  // `ccs`, which aliases tmp) and, right after the scan, turned into the next query's run list in
-  // the other HALF of `runs`: the column phase -- FP64 sqrt chain, dependent L2 loads, two
-  // barriers with half the warps idle -- leaves the per-query critical path.
-  constexpr int HALF = CTA_T;  // run-list entries per half (sentinel included)
   int2 *runs = reinterpret_cast<int2 *>(smem_raw + CTA_OFF_RUNS);
-  int *ccs = reinterpret_cast<int *>(smem_raw + CTA_OFF_TMP);
+  unsigned *clist = reinterpret_cast<unsigned *>(smem_raw + CTA_OFF_RUNS);  // after the scan
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + CTA_OFF_HIST);
   __shared__ long long s_chunk, s_chunk_next;
-  __shared__ int s_info[2][2];  // candidate total / number of runs of the run list in each half of `runs`
   __shared__ int s_count, s_crowded, s_nlist;
   __shared__ long long s_tmp[WARPS];
   __shared__ int s_wsum[WARPS];
@@ -532,8 +525,6 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
     const int64_t q0 = ck * A.chunk_len, q1 = min(A.nq, q0 + (int64_t)A.chunk_len);
     int64_t run = 0;    // hits of the chunk's earlier rows
     bool over = false;  // some row did not fit the slice
-    bool prepared = false;  // this query's run list was built ahead, in half `cur`
-    int cur = 0;
     // the slice's queries in one round of loads (the barrier at the top of the loop ordered the
     // previous slice's reads of s_q)
     if (tid < CTA_CHUNK && q0 + tid < q1) {
@@ -607,70 +598,9 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         visit_impl(std::true_type{}, valid, nx, ny, nt, id);
       };
 
-      bool issued = false;  // the next query's columns are on their way (CTA-uniform)
-      if (V.n_indexed > 0) {
-        const int ncy = Q.iy1 - Q.iy0 + 1, ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
-        int total = 0, nent = 0;
-        const int2 *rl = nullptr;
-        if (prepared) {
-          rl = runs + cur * HALF;
-          total = s_info[cur][0];
-          nent = s_info[cur][1];
-        } else if (ncol <= T) {  // one batch of columns: build the list here (first query of a slice)
-          int s0, l0, s1, l1;
-          cur = 0;
-          column_runs(V, Q, tid, ncol, ncy, Q.rr * Q.rr * (1.0 + 1e-9), s0, l0, s1, l1);
-          runs_from_columns_cta<WARPS>(s0, l0, s1, l1, runs, 2 * T + 1, s_tmp, total, nent);
-          __syncthreads();
-          rl = runs;
-        } else {
-          scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit);  // several batches: the general form
-        }
-        if (rl) {
-          if (qi + 1 < q1 && nent < HALF) {  // (this list stays inside its half)
-            const Query &Qn = s_slice[qi + 1 - q0];
-            const int ncyn = Qn.iy1 - Qn.iy0 + 1, ncoln = (Qn.ix1 - Qn.ix0 + 1) * ncyn;
-            if (ncoln <= T) {
-              int a0, a1, b0, b1;
-              column_cells(V, Qn, tid, ncoln, ncyn, Qn.rr * Qn.rr * (1.0 + 1e-9), a0, a1, b0, b1);
-              int *dst = ccs + 4 * tid;
-              const unsigned d32 = (unsigned)__cvta_generic_to_shared(dst);
-              if (a0 >= 0) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32), "l"(V.cell_start + a0) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32 + 4), "l"(V.cell_start + a1) : "memory");
-              } else {
-                dst[0] = 0; dst[1] = 0;
-              }
-              if (b0 >= 0) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32 + 8), "l"(V.cell_start + b0) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d32 + 12), "l"(V.cell_start + b1) : "memory");
-              } else {
-                dst[2] = 0; dst[3] = 0;
-              }
-              asm volatile("cp.async.commit_group;" ::: "memory");
-              issued = true;
-            }
-          }
-          scan_runs_cta<WARPS, UNR>(V, rl, total, nent, visit);
-        }
-      }
+      if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit);
       scan_tail_cta<WARPS, UNR>(V, visit);
       __syncthreads();
-      bool prepared_next = false;
-      if (issued) {
-        // the next query's run list, into the other half (one barrier inside; the sort phases'
-        // barriers below order its writes before the next scan)
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        const int4 c = *reinterpret_cast<const int4 *>(ccs + 4 * tid);
-        int tn, nn;
-        runs_from_columns_cta<WARPS>(c.x, c.y - c.x, c.z, c.w - c.z, runs + (cur ^ 1) * HALF, HALF, s_tmp, tn, nn);
-        if (tid == 0) { s_info[cur ^ 1][0] = tn; s_info[cur ^ 1][1] = nn; }
-        prepared_next = nn < HALF;
-      }
-      // shared-bucket list of the id sort: in the consumed half of `runs` (the whole area when no
-      // list was built ahead)
-      unsigned *clist = reinterpret_cast<unsigned *>(prepared_next ? runs + cur * HALF : runs);
-      const int clist_cap = prepared_next ? 2 * HALF : CTA_STAGE / 2;
 
       const int n = s_count;
       const bool staged = n > 0 && n <= STAGE;
@@ -739,27 +669,11 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
             int lb = 0;
             if (lane == 0) lb = atomicAdd(&s_nlist, __popc(lm));
             lb = __shfl_sync(0xffffffffu, lb, 0);
-            const int at = lb + __popc(lm & ltmask);
-            if (listed) {
-              if (at < clist_cap) clist[at] = ent;
-              else s_crowded = 1;  // more shared buckets than the list holds: network sort below
-            }
+            if (listed) clist[lb + __popc(lm & ltmask)] = ent;
           }
         }
         __syncthreads();
         const int nl = s_nlist;
-        if (s_crowded) {
-          // (uniform) the bucket list overflowed: order the staged hits with the network instead
-          __syncthreads();
-          for (int i = tid; i < n; i += T) keys[i] = ((unsigned long long)(unsigned)sid[i] << 32) | (unsigned)i;
-          __syncthreads();
-          sort_keys_shared<true>(keys, n, tid, T);
-          for (int p = tid; p < n; p += T) {
-            const unsigned long long k = keys[p];
-            oid[p] = (int32_t)(k >> 32);
-            od[p] = sqrt(sdist[(unsigned)(k & 0xffffu)]);
-          }
-        } else {
         for (int e = tid; e < nl; e += T) {
           const unsigned ent = clist[e];
           const int s0 = (int)(ent & 0xffffu), c = (int)(ent >> 16);
@@ -779,25 +693,11 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         __syncthreads();
         // the staged values are squared sums: the keys' square roots are taken here, on
         // independent elements, instead of inside the scan's dependency chain
-        // (four elements per thread in flight: the two dependent shared-memory reads and the square
-        // root of one element overlap with its neighbours')
-        for (int p0 = tid; p0 < n; p0 += 4 * T) {
-          int slot[4], rid[4];
-          double rs[4];
-#pragma unroll
-          for (int k = 0; k < 4; k++) slot[k] = tmp[min(p0 + k * T, n - 1)];
-#pragma unroll
-          for (int k = 0; k < 4; k++) { rid[k] = sid[slot[k]]; rs[k] = sdist[slot[k]]; }
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int p = p0 + k * T;
-            if (p < n) {
-              oid[p] = rid[k];
-              od[p] = sqrt(rs[k]);
-            }
-          }
+        for (int p = tid; p < n; p += T) {
+          const int slot = tmp[p];
+          oid[p] = sid[slot];
+          od[p] = sqrt(sdist[slot]);
         }
-        }  // !s_crowded
       } else if (staged) {
         // ids bunched in a few buckets: network sort of (id, slot) keys
         for (int i = tid; i < n; i += T) keys[i] = ((unsigned long long)(unsigned)sid[i] << 32) | (unsigned)i;
@@ -815,15 +715,12 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         __syncthreads();
         gids = oid;
         gdist = od;
-        prepared_next = false;  // the rescan rebuilds the run list over the whole area
         if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit_direct);
         scan_tail_cta<WARPS, UNR>(V, visit_direct);
         __syncthreads();
         sort_pairs_global<true>(oid, od, n, tid, T);
       }
       run += n;
-      prepared = prepared_next;
-      if (prepared) cur ^= 1;
       __syncthreads();  // staging and scratch are free for the next query
     }
     if (tid == 0) {
