@@ -75,7 +75,7 @@ __device__ __forceinline__ bool segment_hits(const ObsView &O, int o, double p0x
   const double rr = radius * radius;
   for (int v = v0; v < v1; v++) {  // :788-804
     double bx = O.vx[v], by = O.vy[v];
-    if (!point_segment_farther(p0x, p0y, ax, ay, bx, by, far2)) {
+    if (!(dist_sqrd_point_segment(p0x, p0y, ax, ay, bx, by) > far2)) {
       if (segment_dist_sqrd(p0x, p0y, p1x, p1y, ax, ay, bx, by) < rr) return true;
     }
     ax = bx;
@@ -127,7 +127,7 @@ __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const Obs
           double ax, ay, bx, by;
           load_edge(G, j, ax, ay, bx, by);
           // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
-          if (point_segment_farther(p0x, p0y, ax, ay, bx, by, far2)) continue;
+          if (dist_sqrd_point_segment(p0x, p0y, ax, ay, bx, by) > far2) continue;
           if (segment_dist_sqrd(p0x, p0y, p1x, p1y, ax, ay, bx, by) < rr &&   // :796-803
               within_reach(O, G.eobs[j], p0x, p0y, p1x, p1y, radius))          // :765-779
             return true;
@@ -162,7 +162,7 @@ __device__ __forceinline__ bool entry_hits(const ObsView &O, const ObstacleGrid 
   double ax, ay, bx, by;
   load_edge(G, j, ax, ay, bx, by);
   // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
-  if (point_segment_farther(sg[0], sg[1], ax, ay, bx, by, sg[4])) return false;
+  if (dist_sqrd_point_segment(sg[0], sg[1], ax, ay, bx, by) > sg[4]) return false;
   return segment_dist_sqrd(sg[0], sg[1], sg[2], sg[3], ax, ay, bx, by) < radius * radius &&  // :796-803
          within_reach(O, G.eobs[j], sg[0], sg[1], sg[2], sg[3], radius);                     // :765-779
 }

@@ -23,23 +23,6 @@ __device__ __forceinline__ double dist_sqrd_point_segment(double px, double py, 
   return c * c / len;
 }
 
-// DistanceSqrdPointToSegment(p, s, e) > bound2, without the division: in the interior case
-// c*c/len > bound2 is decided as c*c > bound2*len (len > 0 there).  Only for CULLS whose bound
-// carries its own margin (the callers' far2 = ((radius + |segment|)(1 + 1e-9) + 1e-9)^2): the two
-// forms can disagree only within a few ulps of the bound, nine orders of magnitude inside that
-// margin, so no verdict depends on which one is used; a NaN never culls.
-__device__ __forceinline__ bool point_segment_farther(double px, double py, double sx, double sy,
-                                                      double ex, double ey, double bound2) {
-  double vx = px - sx, vy = py - sy;
-  double ux = ex - sx, uy = ey - sy;
-  double determinate = vx * ux + vy * uy;
-  if (determinate <= 0) return vx * vx + vy * vy > bound2;
-  double len = ux * ux + uy * uy;
-  if (determinate >= len) return (ex - px) * (ex - px) + (ey - py) * (ey - py) > bound2;
-  double c = ux * vy - uy * vx;
-  return c * c > bound2 * len;
-}
-
 // SegmentDistSqrd  distancefunctions.cpp:94-164
 __device__ __forceinline__ double segment_dist_sqrd(double pax, double pay, double pbx, double pby,
                                                     double qax, double qay, double qbx, double qby) {
