@@ -327,8 +327,11 @@ __device__ void order_by_id(unsigned long long *keys, int n, int *hist, int *s_m
 // ordered allocation between warps.  Per query: columns in batches of 32 (scan_columns),
 // hits ballot-compacted into the warp's staging area, ordered by a small counting sort on id
 // buckets, written with coalesced stores.
+#ifndef DRRT_WARP_MINB
+#define DRRT_WARP_MINB 4
+#endif
 template <int METRIC>
-__global__ void __launch_bounds__(WARP_MODE_WARPS * 32, 4) range_warp_kernel(RangeArgs A) {
+__global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_warp_kernel(RangeArgs A) {
   constexpr int WARPS = WARP_MODE_WARPS, STAGE = WARP_STAGE, NB = 128;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_count[WARPS];
@@ -343,6 +346,10 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, 4) range_warp_kernel(Ran
   int *counter = &s_count[w];
   const GridView &V = A.V;
   const unsigned ltmask = (1u << lane) - 1u;
+  // one radius for the whole batch (the usual call): its exact sqrt thresholds once per warp
+  __shared__ double s_thr[2];
+  if (threadIdx.x == 0 && !A.radius) sqrt_thresholds(A.radius_all, s_thr[0], s_thr[1]);
+  __syncthreads();
 
   for (;;) {
     long long ck = 0;
@@ -356,8 +363,10 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, 4) range_warp_kernel(Ran
     bool over = false;
     for (int64_t qi = q0; qi < q1; qi++) {
       Query Q;
-      setup_query<METRIC>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
-                          A.radius ? A.radius[qi] : A.radius_all, Q);
+      setup_query<METRIC, false>(V, A.q[3 * qi], A.q[3 * qi + 1], A.q[3 * qi + 2],
+                                 A.radius ? A.radius[qi] : A.radius_all, Q);
+      if (A.radius) sqrt_thresholds(Q.r, Q.t_lt, Q.t_le);
+      else { Q.t_lt = s_thr[0]; Q.t_le = s_thr[1]; }
       const GhostBand GB = ghost_band<METRIC>(Q);
       int32_t *gids = nullptr;
       double *gdist = nullptr;
