@@ -2,7 +2,8 @@
     compute-sanitizer --tool memcheck  python benchmarks/sanitizer_pass.py
     compute-sanitizer --tool racecheck python benchmarks/sanitizer_pass.py
 (insert, both range kernels, the streamed one-call range query over several sub-batches, nearest /
-k-nearest, ranked and small-batch Dubins checks, LineCheck, the obstacle-subset check, fused Extend)."""
+k-nearest, ranked and small-batch Dubins checks, LineCheck, the obstacle-subset check, fused Extend; narrow rows,
+the mapped single-call paths, the rrt_LMC_ mirror and rewiring test, stored-edge sweeps, obstacle moves, timed obstacles)."""
 import os
 import sys
 
@@ -37,4 +38,36 @@ mask[::2] = 1
 t.ExplicitEdgeCheckSubset(mask, start=s[:17000], end=e[:17000])
 t.Extend(0.7, synth.box_points(300, 6))
 t.ExplicitNodeCheck(q[:5000])
+# ---- round 2: narrow rows, mapped single-call paths, lmc mirror + rewiring test, stored-edge sweeps,
+# obstacle moves, time-parametrised obstacles, id validation
+f32 = np.empty(len(ids), dtype=np.float32)
+assert t.KDFindWithinRangeInto(0.8, q, off2, ids2, f32) == len(ids)
+assert t.KDFindWithinRangeInto(0.8, q, off2, ids2, None) == len(ids)
+for k in range(20):
+    o1 = np.empty(2, dtype=np.int64)
+    i1 = np.empty(4096, dtype=np.int32)
+    d1 = np.empty(4096, dtype=np.float64)
+    t.KDFindWithinRangeInto(0.8 if k % 2 else 5.0, q[k:k + 1], o1, i1, d1)      # mapped row, both kernels
+    t.KDFindNearest(q[k:k + 1])
+    t.ExplicitEdgeCheck(s[k:k + 1], e[k:k + 1])
+    t.ExplicitNodeCheck(q[k:k + 1])
+n = t.tree_size_
+lmc = np.random.default_rng(7).uniform(0, 50, n)
+t.WriteLMC(0, lmc)
+t.ScatterLMC(np.arange(0, n, 5, dtype=np.int32), lmc[::5] * 0.5)
+t.ExtendParents(0.7, synth.box_points(300, 6))
+t.ExtendRewire(40.0)
+a = np.random.default_rng(8).integers(0, n, 60000).astype(np.int32)
+b = np.random.default_rng(9).integers(0, n, 60000).astype(np.int32)
+t.ExplicitEdgeCheckIds(a[:5000], b[:5000])
+offn, idn, _ = t.KDFindWithinRange(0.9, t.positions()[a[:3000]])
+t.AppendEdges(np.repeat(a[:3000], np.diff(offn)).astype(np.int32), idn)
+t.ObstacleSweep(3)
+t.ObstacleSweep(5, other_mask=np.ones(64, dtype=np.uint8))
+t.MoveObstacles([1, 2, 3], [[10.0, 10.0], [20.0, 21.0], [30.0, 5.0]], translate_polygon=True)
+t.UpdateObstacles([4], used=[0])
+t.ExplicitEdgeCheck(s[:3000], e[:3000])
+t.SetTimedObstacles(**synth.timed_obstacles(16, 10))
+ts, te = synth.timed_segments(5000, 11)
+t.ExplicitEdgeCheck2DTimed(ts, te, 0.5)
 print("sanitizer pass ok: %d range hits, %d/%d edges collide" % (len(ids), int(v.sum()), len(v)))
