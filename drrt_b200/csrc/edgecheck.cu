@@ -627,41 +627,6 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
   }
 }
 
-// K4 for a handful of edges (the unchanged planner asks for ONE edge per call, drrt.cpp:411-422,
-// 286-293): solve, walk and per-segment test in one launch, one thread per edge -- no work list,
-// no counters to clear, nothing between the launch and the caller's wait.  The same functions as
-// the solve / walk pair (six-word solve in double, PolylineWalker, segment_vs_obstacles), so the
-// verdicts and lengths are the pair's.
-static constexpr int64_t SMALL_EDGE_BATCH = 64;
-
-template <bool MASKED>
-__global__ void __launch_bounds__(64) dubins_small_kernel(EdgeArgs A) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= A.n) return;
-  double sx, sy, st, ex, ey, et;
-  load_pose(A, e, false, sx, sy, st);
-  load_pose(A, e, true, ex, ey, et);
-  DubinsPath P;
-  P.kinds = 0;
-  const double edge_dist = metric_dist(A.metric, sx, sy, st, ex, ey, et);  // NewEdge :19
-  dubins_solve(sx, sy, st, ex, ey, et, A.r_min, edge_dist, P);
-  if (A.length) A.length[e] = P.dist;
-  bool hit = false;
-  if (A.obs.n > 0 && (P.kinds & 63) != 0) {
-    PolylineWalker W;
-    W.start(&P, A.r_min);
-    double px = 0.0, py = 0.0, cx, cy;
-    bool have_prev = false, connects = false;
-    while (!hit && W.next(&cx, &cy, &connects)) {  // dubinsedge.cpp:875-893, first hit decides
-      if (have_prev && connects) hit = segment_vs_obstacles<MASKED>(A.obs, A.grid, px, py, cx, cy, A.robot_radius);
-      px = cx;
-      py = cy;
-      have_prev = true;
-    }
-  }
-  A.verdict[e] = hit ? 1 : 0;
-}
-
 // K5: LineCheck (obstacle.cpp:1098-1133), one thread per edge.
 //
 // The reference cuts the straight edge into 50 collinear pieces (repeated +-dist/50, :1108-1133)
@@ -942,11 +907,6 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
   if (edge_kind == DRRT_EDGE_STRAIGHT) {
     if (masked) linecheck_kernel<true><<<nb, EDGE_T, smem, st>>>(A);
     else linecheck_kernel<false><<<nb, EDGE_T, smem, st>>>(A);
-    DRRT_LAUNCHED();
-  } else if (n <= SMALL_EDGE_BATCH && !csr) {
-    const unsigned nb64 = (unsigned)((n + 63) / 64);
-    if (masked) dubins_small_kernel<true><<<nb64, 64, 0, st>>>(A);
-    else dubins_small_kernel<false><<<nb64, 64, 0, st>>>(A);
     DRRT_LAUNCHED();
   } else {
     if (st != S->stream) DRRT_CUDA(cudaStreamSynchronize(S->stream));
