@@ -522,6 +522,7 @@ def main():
 
     roof_edge = None
     cpu_edge = None
+    config5_summary = None
     extra = {}
     if not args.no_extra:
         sec = host_timed(e2e_two_call_step, e2e_steps)
@@ -720,6 +721,14 @@ def main():
         extra["config4_replanning"] = replanning.run(2_000_000, 4096, device=local,
                                                       parity=(rank == 0 and world == 1 and not args.no_cpu))
 
+        # ---- N > 1: BASELINE config 5 -- an 8 M-node store replicated by NCCL broadcast of 4096-node
+        # insert batches, 64 K queries per GPU at its RRTx radius; every rank's rows against rank 0's
+        # own answer (the store is twice the L2: the HBM-bound point of the range kernel)
+        if world > 1:
+            extra["config5_8m_nodes"] = config5(torch, dist, drrt_b200, synth, dev, local, rank, world, timed, state,
+                                                peak, max(2, min(args.steps, 5)))
+            config5_summary = extra["config5_8m_nodes"]
+
         # ---- N > 1: strong scaling of the ONE-PROCESS multi-GPU C ABI (drrt_comm_*): rank 0's process
         # drives all N GPUs (the reference planner is one process); the other ranks wait at the barrier
         if world > 1:
@@ -798,6 +807,9 @@ def main():
                   "store": "replicated per GPU; NCCL broadcast of the insert batch"}
         if parity is not None:
             config["parity_across_gpus"] = parity
+        if config5_summary is not None:
+            config["config5_8m_nodes"] = {k: config5_summary[k] for k in
+                                          ("queries_per_s", "ms_per_step", "roofline_frac", "ranks_equal_single_gpu")}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -807,6 +819,55 @@ def main():
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def config5(torch, dist, drrt_b200, synth, dev, local, rank, world, timed, state, peak, steps):
+    """BASELINE config 5 on this run's GPUs (called at N > 1)"""
+    n5, batch = 8_000_000, 4096
+    tree = drrt_b200.KDTree(device=local, capacity=n5)
+    src = torch.from_numpy(synth.nodes(n5, synth.SEED_NODES_8GPU)).to(dev) if rank == 0 else None
+    buf = torch.empty((batch, 3), dtype=torch.float64, device=dev)
+    t0 = time.perf_counter()
+    for lo in range(0, n5, batch):
+        m = min(batch, n5 - lo)
+        if rank == 0:
+            buf[:m].copy_(src[lo:lo + m])
+        dist.broadcast(buf, src=0)                    # the insert batch reaches every replica over NVLink
+        tree.KDInsert_dev(buf[:m].contiguous())
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    del src
+    r5 = synth.shrinking_radius(n5, synth.GAMMA_REF)
+    q_all = synth.queries(N_QUERIES * world, synth.SEED_QUERIES + 5)
+    qd = torch.from_numpy(np.ascontiguousarray(q_all[rank * N_QUERIES:(rank + 1) * N_QUERIES])).to(dev)
+
+    def f():
+        state["res5"] = tree.KDFindWithinRange_dev(r5, qd)
+
+    ms = timed(f, steps, 3) / steps
+    hits = int(state["res5"].total)
+    mine = rows_checksum(torch, tree, state["res5"])
+    allsum = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allsum, mine)
+    ok = None
+    if rank == 0:
+        ok = True
+        for r in range(world):
+            qr = torch.from_numpy(np.ascontiguousarray(q_all[r * N_QUERIES:(r + 1) * N_QUERIES])).to(dev)
+            want = rows_checksum(torch, tree, tree.KDFindWithinRange_dev(r5, qr))
+            ok = ok and bool(torch.equal(want.cpu(), allsum[r].cpu()))
+        if not ok:
+            raise SystemExit("bench.py: config 5 -- a rank's rows differ from the single-GPU answer")
+    dist.barrier()
+    out = {"nodes": n5, "insert_batches": (n5 + batch - 1) // batch, "build_s": t_build, "radius": r5,
+           "hits_per_query": hits / N_QUERIES, "ms_per_step": ms, "queries_per_s": world * N_QUERIES / (ms * 1e-3),
+           "roofline_frac": (32.0 * N_QUERIES + 36.0 * hits) / (ms * 1e-3) / 1e9 / peak,
+           "ranks_equal_single_gpu": ok,
+           "what": "8 M-node store replicated on %d GPUs by NCCL broadcast of 4096-node insert batches, 64 K "
+                   "queries per GPU; counts / ids / distance bits of every rank's shard equal rank 0's own answer" % world}
+    tree.close()
+    torch.cuda.empty_cache()
+    return out
 
 
 def config1_inloop(iters=1200):
