@@ -229,14 +229,18 @@ __device__ __forceinline__ void column_runs(const GridView &A, const Query &Q, i
 
 // One warp visits column batches first, first+stride, ... of query Q and calls
 // f(valid, x, y, theta, id) once per candidate slot with all 32 lanes converged
-// (valid == false on padding lanes).
+// (valid == false on padding lanes).  The non-empty runs of a batch are compacted (two ballots)
+// into `runs` (RUNS_PER_BATCH + 1 entries of the calling warp: run j covers candidate numbers
+// [runs[j-1].x, runs[j].x) and candidate i of it is record i + runs[j].y, sentinel last), and a
+// candidate's run comes from the same 32-run register window as in the CTA scan: one REDUX.OR
+// marks where the window's runs end, a POPC away is the lane's run -- no per-candidate search.
 template <class F>
 __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, int first,
-                                             int stride, int *run_start, int *run_pref,
-                                             int lane, F f) {
+                                             int stride, int2 *runs, int lane, F f) {
   const int ncy = Q.iy1 - Q.iy0 + 1;
   const int ncol = (Q.ix1 - Q.ix0 + 1) * ncy;
   const double cull = Q.rr * Q.rr * (1.0 + 1e-9);
+  const unsigned lt = (1u << lane) - 1u;
   for (int cb = first * 32; cb < ncol; cb += stride * 32) {
     int s0, l0, s1, l1;
     column_runs(A, Q, cb + lane, ncol, ncy, cull, s0, l0, s1, l1);
@@ -247,29 +251,29 @@ __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, 
       int t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    int excl = inc - tot;
-    int total = __shfl_sync(0xffffffffu, inc, 31);
+    const int excl = inc - tot;
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    const unsigned m0 = __ballot_sync(0xffffffffu, l0 > 0), m1 = __ballot_sync(0xffffffffu, l1 > 0);
+    const int nent = __popc(m0) + __popc(m1);
+    const int slot = __popc(m0 & lt) + __popc(m1 & lt);  // runs of the lanes before this one
     __syncwarp();
-    run_start[2 * lane] = s0;
-    run_start[2 * lane + 1] = s1;
-    run_pref[2 * lane] = excl;
-    run_pref[2 * lane + 1] = excl + l0;
-    if (lane == 31) run_pref[RUNS_PER_BATCH] = total;
+    if (l0 > 0) runs[slot] = make_int2(excl + l0, s0 - excl);
+    if (l1 > 0) runs[slot + (l0 > 0)] = make_int2(excl + l0 + l1, s1 - (excl + l0));
+    if (lane == 31) runs[nent] = make_int2(0x7fffffff, 0);
     __syncwarp();
-    for (int i = lane; i < ((total + 31) & ~31); i += 32) {
-      bool valid = i < total;
+    int jl = 0;  // warp-uniform: the run holding the first candidate of the next 32
+    for (int base = 0; base < total; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < total;
       double nx = 0.0, ny = 0.0, nt = 0.0;
       int32_t id = 0;
-      if (valid) {
-        // largest run index j with run_pref[j] <= i
-        int lo = 0, hi = RUNS_PER_BATCH;
-#pragma unroll
-        for (int step = 0; step < 6; step++) {
-          int mid = (lo + hi) >> 1;
-          if (run_pref[mid] <= i) lo = mid; else hi = mid;
-        }
-        load_rec(A.rec + (run_start[lo] + (i - run_pref[lo])), nx, ny, nt, id);
-      }
+      const int2 e = runs[min(jl + lane, nent)];
+      const unsigned rel = (unsigned)(e.x - base);
+      const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+      const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
+      const int ey = __shfl_sync(0xffffffffu, e.y, k);
+      if (valid) load_rec(A.rec + (i + ey), nx, ny, nt, id);
+      jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
       f(valid, nx, ny, nt, id);
     }
   }

@@ -77,8 +77,7 @@ template <int METRIC>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_kernel(KnnArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_runs[KNN_WARPS][RUNS_PER_BATCH];
-  __shared__ int s_pref[KNN_WARPS][RUNS_PER_BATCH + 1];
+  __shared__ int2 s_runl[KNN_WARPS][RUNS_PER_BATCH + 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   // plain mode: one query per warp; list mode: the warps share the listed queries
   const int64_t count = A.qlist ? (int64_t)A.qlist[0] : A.nq;
@@ -121,7 +120,7 @@ knn_kernel(KnnArgs A) {
         setup_query<METRIC, false>(V, px, py, pt, r, Q);
         Q.has_ghost = false;
         all = covers_all(V, Q);
-        scan_columns(V, Q, 0, 1, s_runs[w], s_pref[w], lane, visit);
+        scan_columns(V, Q, 0, 1, s_runl[w], lane, visit);
       }
       scan_tail(V, 0, 1, lane, visit);
       // every unscanned node is farther than r
@@ -197,8 +196,7 @@ __device__ void warp_sort_pairs(double *d, int32_t *id, int n, int lane) {
 template <int METRIC>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_select_kernel(KnnArgs A, int32_t *fallback) {
-  __shared__ int s_runs[KNN_WARPS][RUNS_PER_BATCH];
-  __shared__ int s_pref[KNN_WARPS][RUNS_PER_BATCH + 1];
+  __shared__ int2 s_runl[KNN_WARPS][RUNS_PER_BATCH + 1];
   __shared__ double s_d[KNN_WARPS][KSEL_CAP];
   __shared__ int32_t s_id[KNN_WARPS][KSEL_CAP];
   __shared__ int s_count[KNN_WARPS];
@@ -235,7 +233,7 @@ knn_select_kernel(KnnArgs A, int32_t *fallback) {
       setup_query<METRIC, false>(V, qx, qy, qt, r, Q);
       Q.has_ghost = false;
       all = covers_all(V, Q);
-      scan_columns(V, Q, 0, 1, s_runs[w], s_pref[w], lane, visit);
+      scan_columns(V, Q, 0, 1, s_runl[w], lane, visit);
     }
     scan_tail(V, 0, 1, lane, visit);
     __syncwarp();

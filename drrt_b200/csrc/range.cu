@@ -335,8 +335,7 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_wa
   constexpr int WARPS = WARP_MODE_WARPS, STAGE = WARP_STAGE, NB = 128;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_count[WARPS];
-  __shared__ int s_runs[WARPS * RUNS_PER_BATCH];
-  __shared__ int s_pref[WARPS * (RUNS_PER_BATCH + 1)];
+  __shared__ int2 s_runl[WARPS][RUNS_PER_BATCH + 1];
   __shared__ int s_hist[WARPS][NB + 1];
   __shared__ int s_misc[WARPS][4 + WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -394,7 +393,7 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_wa
       };
       auto scan_all = [&]() {
         if (V.n_indexed > 0)
-          scan_columns(V, Q, 0, 1, s_runs + w * RUNS_PER_BATCH, s_pref + w * (RUNS_PER_BATCH + 1), lane, visit);
+          scan_columns(V, Q, 0, 1, s_runl[w], lane, visit);
         scan_tail(V, 0, 1, lane, visit);
       };
       scan_all();
