@@ -199,7 +199,6 @@ knn_select_kernel(KnnArgs A, int32_t *fallback) {
   __shared__ int2 s_runl[KNN_WARPS][RUNS_PER_BATCH + 1];
   __shared__ double s_d[KNN_WARPS][KSEL_CAP];
   __shared__ int32_t s_id[KNN_WARPS][KSEL_CAP];
-  __shared__ int s_count[KNN_WARPS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t qi = (int64_t)blockIdx.x * KNN_WARPS + w;
   if (qi >= A.nq) return;
@@ -210,14 +209,14 @@ knn_select_kernel(KnnArgs A, int32_t *fallback) {
   int32_t *sid = s_id[w];
   double r = A.r0;
   bool all = false;
+  int cnt = 0;
   auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
     const double d = sqrt(metric_sum<METRIC>(qx, qy, qt, nx, ny, nt));
     const bool in = valid && (all || d <= r);
     const unsigned m = __ballot_sync(0xffffffffu, in);
     if (!m) return;
-    int pos = 0;
-    if (lane == 0) pos = atomicAdd(&s_count[w], __popc(m));
-    pos = __shfl_sync(0xffffffffu, pos, 0);
+    const int pos = cnt;  // warp-uniform register: every lane sees the ballot
+    cnt += __popc(m);
     if (in) {
       const int slot = pos + __popc(m & ltmask);
       if (slot < KSEL_CAP) { sd[slot] = d; sid[slot] = id; }
@@ -225,7 +224,7 @@ knn_select_kernel(KnnArgs A, int32_t *fallback) {
   };
   int n = 0;
   for (;;) {
-    if (lane == 0) s_count[w] = 0;
+    cnt = 0;
     __syncwarp();
     all = true;
     if (V.n_indexed > 0) {
@@ -237,7 +236,7 @@ knn_select_kernel(KnnArgs A, int32_t *fallback) {
     }
     scan_tail(V, 0, 1, lane, visit);
     __syncwarp();
-    n = s_count[w];
+    n = cnt;
     // every node within r is staged: k of them settle the answer (unscanned nodes are farther)
     if (n >= A.k || all || n > KSEL_CAP) break;
     r *= 2.0;

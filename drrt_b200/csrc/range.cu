@@ -334,7 +334,6 @@ template <int METRIC>
 __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_warp_kernel(RangeArgs A) {
   constexpr int WARPS = WARP_MODE_WARPS, STAGE = WARP_STAGE, NB = 128;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_count[WARPS];
   __shared__ int2 s_runl[WARPS][RUNS_PER_BATCH + 1];
   __shared__ int s_hist[WARPS][NB + 1];
   __shared__ int s_misc[WARPS][4 + WARPS];
@@ -342,7 +341,6 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_wa
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw) + w * STAGE;  // (id << 32) | slot
   double *sdist = reinterpret_cast<double *>(smem_raw + (size_t)WARPS * STAGE * 8) + w * STAGE;
   uint16_t *order = reinterpret_cast<uint16_t *>(smem_raw + (size_t)WARPS * STAGE * 16) + w * STAGE;
-  int *counter = &s_count[w];
   const GridView &V = A.V;
   const unsigned ltmask = (1u << lane) - 1u;
   // one radius for the whole batch (the usual call): its exact sqrt thresholds once per warp
@@ -369,17 +367,15 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_wa
       const GhostBand GB = ghost_band<METRIC>(Q);
       int32_t *gids = nullptr;
       double *gdist = nullptr;
-      if (lane == 0) *counter = 0;
-      __syncwarp();
+      int cnt = 0;  // hits of this query so far: warp-uniform, in a register (every lane sees the ballot)
       auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
         bool hit;
         double d;  // squared sum of the admitting probe; the key is its square root (taken at the write)
         eval_candidates<METRIC, 1>(Q, GB, &valid, &nx, &ny, &nt, &id, V.gate, &hit, &d);
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (!m) return;
-        int pos = 0;
-        if (lane == 0) pos = atomicAdd(counter, __popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, 0);
+        const int pos = cnt;
+        cnt += __popc(m);
         if (hit) {
           const int slot = pos + __popc(m & ltmask);
           if (gids) {
@@ -398,7 +394,7 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_wa
       };
       scan_all();
       __syncwarp();
-      const int n = *counter;
+      const int n = cnt;
       const bool staged = n > 0 && n <= STAGE;
       const bool fits = run + n <= cap;
       if (lane == 0) {
@@ -420,8 +416,7 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_wa
       } else if (n > 0) {
         // more hits than the staging area: second pass straight into the arena
         __syncwarp();
-        if (lane == 0) *counter = 0;
-        __syncwarp();
+        cnt = 0;
         gids = oid;
         gdist = od;
         scan_all();
