@@ -750,7 +750,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        _, cpu = cpu_range_baseline(r2a, 0)
+        cpu_tree, cpu = cpu_range_baseline(r2a, 0)
+
+        def cpu_tree_for_single_calls():
+            return cpu_tree, None
         if N_NODES == 1_000_000:
             # beside the port: the reference's own compiled sources on the same queries (what
             # `--impl reference` times at length), a short sample
@@ -774,6 +777,24 @@ def main():
             if refbin is not None:
                 cpu_edge["reference_binary"] = refbin
             cpu["edge_check"] = cpu_edge
+            # one query per call on the CPU (the oracle's tree walk, one thread), beside e2e.single_call
+            if "single_call" in e2e:
+                from oracle import pyoracle as po
+                small = po.RefTree()
+                small.insert(synth.nodes(10_000, 0xD2270031))
+                qs = synth.queries(512, 0xD2270032)
+                big, _ = cpu_tree_for_single_calls()
+                sc = {}
+                for name, tr, rad in (("nodes_10k", small, synth.shrinking_radius(10_000, synth.GAMMA_REF)),
+                                      ("nodes_1m", big, r2b)):
+                    ts = []
+                    for k in range(64, 320):
+                        t0 = time.perf_counter()
+                        tr.range_one(qs[k], rad)
+                        ts.append(time.perf_counter() - t0)
+                    sc[name] = {"us_median": 1e6 * float(np.median(ts)), "radius": rad}
+                sc["call"] = "the oracle's KDFindWithinRange, one query per call, one thread (ctypes)"
+                cpu["single_call"] = sc
             # config 1: the planner iteration over the reference's OWN objects, all-CPU reference vs
             # the same driver over the shim + this library (oracle/_ref/drrt_ref vs drrt_shim)
             inloop = config1_inloop()
