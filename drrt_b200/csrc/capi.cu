@@ -31,25 +31,6 @@ static cudaStream_t pick(Store *S, void *stream) {
   return stream ? (cudaStream_t)stream : S->stream;
 }
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
-#define ENTER(h)                                                         \
-  if (!(h)) return drrt::set_error(DRRT_ERR_INVALID, "null handle");      \
-  drrt::Store *S = reinterpret_cast<drrt::Store *>(h);                    \
-  std::lock_guard<std::mutex> lock__(S->mu);                              \
-  drrt::DeviceGuard guard__(S->device);                                   \
-  if (!guard__.ok) return drrt::set_error(DRRT_ERR_CUDA, "cudaSetDevice failed")
-
 static int upload(const void *src, void *dst, size_t bytes, cudaStream_t st) {
   if (!bytes) return DRRT_OK;
   DRRT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));

@@ -143,19 +143,12 @@ static int run_all(Comm *C, F f) {
 
 struct Locked {
   std::lock_guard<std::mutex> lock;
-  int prev = -1;
-  bool ok = true;
-  explicit Locked(Store *S) : lock(S->mu) {
-    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-    if (prev != S->device && cudaSetDevice(S->device) != cudaSuccess) ok = false;
-  }
-  ~Locked() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
+  DeviceGuard guard;
+  explicit Locked(Store *S) : lock(S->mu), guard(S->device) {}
 };
 #define LOCKED(S)                                                                  \
   drrt::Locked locked__(S);                                                        \
-  if (!locked__.ok) return drrt::set_error(DRRT_ERR_CUDA, "cudaSetDevice failed")
+  if (!locked__.guard.ok) return drrt::set_error(DRRT_ERR_CUDA, "cudaSetDevice failed")
 
 #define DRRT_NCCL(call)                                                                    \
   do {                                                                                     \

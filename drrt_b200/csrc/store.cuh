@@ -163,6 +163,27 @@ struct Store {
   unsigned long long *d_edge_counter = nullptr;
 };
 
+// Every extern "C" entry point on a handle: serialise on the handle's mutex and make its device
+// current for the duration of the call (restored on return).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+#define ENTER(h)                                                         \
+  if (!(h)) return drrt::set_error(DRRT_ERR_INVALID, "null handle");      \
+  drrt::Store *S = reinterpret_cast<drrt::Store *>(h);                    \
+  std::lock_guard<std::mutex> lock__(S->mu);                              \
+  drrt::DeviceGuard guard__(S->device);                                   \
+  if (!guard__.ok) return drrt::set_error(DRRT_ERR_CUDA, "cudaSetDevice failed")
+
 // store.cu
 int store_reserve_nodes(Store *S, int64_t need);
 int store_insert_dev(Store *S, int64_t n, const double *pos_dev, cudaStream_t st,

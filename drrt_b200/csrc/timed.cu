@@ -91,15 +91,6 @@ static int put_vec(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t st) {
 
 using namespace drrt;
 
-#define ENTER(h)                                                         \
-  if (!(h)) return drrt::set_error(DRRT_ERR_INVALID, "null handle");      \
-  drrt::Store *S = reinterpret_cast<drrt::Store *>(h);                    \
-  std::lock_guard<std::mutex> lock__(S->mu);                              \
-  int prev_dev__ = -1;                                                    \
-  if (cudaGetDevice(&prev_dev__) != cudaSuccess || (prev_dev__ != S->device && cudaSetDevice(S->device) != cudaSuccess)) \
-    return drrt::set_error(DRRT_ERR_CUDA, "cudaSetDevice failed");        \
-  struct Back__ { int d; ~Back__() { if (d >= 0) cudaSetDevice(d); } } back__{prev_dev__}
-
 extern "C" {
 
 int drrt_timed_obstacles_set(drrt_store *h, int32_t n_obs, const int32_t *kind, const uint8_t *used,
