@@ -606,12 +606,12 @@ int range_into(Store *S, int64_t nq, const double *q, const double *radius, doub
                        (long long)res.total, (long long)cap);
     return DRRT_OK;
   }
-  if (!S->copy_stream) {
-    DRRT_CUDA(cudaStreamCreateWithFlags(&S->copy_stream, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; b++) {
-      DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_packed[b], cudaEventDisableTiming));
-      DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_copied[b], cudaEventDisableTiming));
-    }
+  // (the copy stream is shared with the pipelined edge checks, which may have created it first:
+  // the events are checked on their own)
+  if (!S->copy_stream) DRRT_CUDA(cudaStreamCreateWithFlags(&S->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    if (!S->ev_packed[b]) DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_packed[b], cudaEventDisableTiming));
+    if (!S->ev_copied[b]) DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_copied[b], cudaEventDisableTiming));
   }
   cudaStream_t cs = S->copy_stream;
   const int64_t sub = INTO_SUB;

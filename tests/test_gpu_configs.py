@@ -139,3 +139,71 @@ def test_store_8m_nodes_sample(drrt, po):
         got = tree.structure(lo, 1 << 20)
         for k in ("parent", "left", "right", "split"):
             assert np.array_equal(got[k], st[k][lo:lo + (1 << 20)]), k
+
+
+def test_config2a_full_batch_properties(drrt, config3):
+    """BASELINE config 2a at FULL size (1 M nodes, 64 K queries, ~233 M hits): what can be said about
+    every row without the oracle.  Rows sorted by id with no repeats; every key is the reference's
+    metric of the query (or of its ghost) and the node, recomputed in torch in the reference's
+    operation order, bit for bit, and lies under the radius; counts / offsets / total agree; two runs
+    give identical rows; the float rows of the host call are the double rows rounded."""
+    import torch
+    from drrt_b200 import capi
+    tree, pos, q = config3["tree"], config3["pos"], config3["q"]
+    dev = torch.device("cuda", 0)
+    r = synth.shrinking_radius(len(pos), synth.GAMMA_REF)
+    qd = torch.from_numpy(q).to(dev)
+    pd = torch.from_numpy(pos).to(dev)
+
+    def run():
+        tree.KDFindWithinRange_dev(r, qd)
+        res = tree.range_pack()
+        off, ids, dist = tree.range_result_tensors(res)
+        cnt = tree.range_result_counts(res)
+        return res, off.clone(), ids[:res.total].clone(), dist[:res.total].clone(), cnt.clone()
+
+    res, off, ids, dist, cnt = run()
+    total = int(res.total)
+    assert total > 64_000 * 3000 and int(off[-1]) == total and int(cnt.to(torch.int64).sum()) == total
+    assert torch.equal(off[1:] - off[:-1], cnt.to(torch.int64))
+    # sorted by id, no repeats inside a row
+    rising = ids[1:] > ids[:-1]
+    row_start = torch.zeros(total, dtype=torch.bool, device=dev)
+    row_start[off[:-1][cnt > 0]] = True
+    assert bool((rising | row_start[1:]).all())
+    # keys: metric(q, n) or metric(ghost, n), reference operation order (smalltest.cpp:167-175)
+    row = torch.repeat_interleave(torch.arange(len(q), device=dev), cnt.to(torch.int64))
+    W = synth.TWO_PI
+
+    def metric(qt):
+        n = pd[ids.to(torch.int64)]
+        qq = qd[row]
+        t0 = qq[:, 0] - n[:, 0]
+        t1 = qq[:, 1] - n[:, 1]
+        s = t0 * t0 + t1 * t1
+        a, b = qt, n[:, 2]
+        ad = (a - b).abs()
+        wr = torch.minimum(a, b) + W - torch.maximum(a, b)
+        m = torch.minimum(ad, wr)
+        return torch.sqrt(s + m * m)
+
+    qt = qd[row, 2]
+    first = metric(qt)
+    ghost_t = torch.where(qt < W / 2.0, qt + W, qt - W)       # ghostpoint.cpp:39-52
+    ghost = metric(ghost_t)
+    ok = (dist == first) | (dist == ghost)
+    assert bool(ok.all()), int((~ok).sum())
+    assert float((dist == first).float().mean()) > 0.95       # the ghost admits only what the walk hides
+    assert bool(((dist < r) | ((ids == 0) & (dist <= r))).all())
+    del first, ghost, ghost_t, qt, row, ok, rising, row_start
+    # identical on a second run
+    res2, off2, ids2, dist2, cnt2 = run()
+    assert torch.equal(off, off2) and torch.equal(ids, ids2) and torch.equal(dist, dist2)
+    del off2, ids2, dist2, cnt2
+    # the narrow rows of the host call, full size
+    o = np.empty(len(q) + 1, dtype=np.int64)
+    i32 = np.empty(total, dtype=np.int32)
+    f32 = np.empty(total, dtype=np.float32)
+    assert tree.KDFindWithinRangeInto(r, q, o, i32, f32) == total
+    assert np.array_equal(o, off.cpu().numpy()) and np.array_equal(i32, ids.cpu().numpy())
+    assert np.array_equal(f32, dist.cpu().numpy().astype(np.float32))

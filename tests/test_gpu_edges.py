@@ -322,3 +322,28 @@ def test_timed_obstacles_kinds_6_7(drrt, po):
         t.SetTimedObstacles(**dict(o, kind=np.full(64, 3)))
     t.SetTimedObstacles(**dict(o, used=np.zeros(64, dtype=np.uint8)))
     assert not t.ExplicitEdgeCheck2DTimed(s[:1000], e[:1000], 0.5).any()
+
+
+def test_streamed_range_after_pipelined_edges_on_one_handle(drrt, po):
+    """The pipelined host edge check and the streamed host range query share the handle's copy
+    stream but own their events: either may come first (a range query after a 10 M-edge call once
+    found its events missing)."""
+    pos = synth.box_points(120_000, 91)
+    q = synth.box_points(40_000, 92)                    # > 1.5 sub-batches: the streamed path
+    s, e = synth.random_edges(4_300_000, 93)            # > 2 chunks: the pipelined path
+    for edges_first in (True, False):
+        t = drrt.KDTree()
+        t.KDInsert(pos)
+        t.SetObstacles(**synth.obstacles(64, 94))
+        want = t.KDFindWithinRange(0.9, q)              # two-call form: no streams involved
+        for step in ((0, 1) if edges_first else (1, 0)):
+            if step == 0:
+                v, ln = t.ExplicitEdgeCheck(s, e)
+                assert 0.0 < v.mean() < 1.0
+            else:
+                o = np.empty(len(q) + 1, dtype=np.int64)
+                i = np.empty(len(want[1]), dtype=np.int32)
+                d = np.empty(len(want[1]), dtype=np.float64)
+                assert t.KDFindWithinRangeInto(0.9, q, o, i, d) == len(want[1])
+                assert np.array_equal(o, want[0]) and np.array_equal(i, want[1]) and np.array_equal(d, want[2])
+        t.close()
