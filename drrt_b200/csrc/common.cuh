@@ -104,9 +104,10 @@ __host__ __device__ __forceinline__ double r2s1_sum(double ax, double ay, double
   t1 = t1 * t1;
   double s = t0 + t1;
   double ad = fabs(at - bt);
-  double mn = (bt < at) ? bt : at;
-  double mx = (at < bt) ? bt : at;
-  double wr = mn + DRRT_TWO_PI - mx;
+  // the same two roundings without materialising min and max: at < bt picks (at + 2 PI) - bt, else
+  // (bt + 2 PI) - at (bt == at gives either); at + 2 PI is loop-invariant in the scans
+  double w1 = (at + DRRT_TWO_PI) - bt, w2 = (bt + DRRT_TWO_PI) - at;
+  double wr = (at < bt) ? w1 : w2;
   double m = (wr < ad) ? wr : ad;
   return s + m * m;
 }

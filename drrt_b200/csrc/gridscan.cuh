@@ -299,14 +299,17 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
   for (int cb = 0; cb < ncol; cb += T) {
     int s0, l0, s1, l1;
     column_runs(A, Q, cb + tid, ncol, ncy, cull, s0, l0, s1, l1);
-    const int nrun = (l0 > 0) + (l1 > 0);
-    const long long mine = ((long long)nrun << 32) | (unsigned)(l0 + l1);
-    long long inc = mine;
+    // candidates before this thread's: a 32-bit shuffle scan; runs before it: two ballots
+    const unsigned ltm = (1u << lane) - 1u;
+    const unsigned m0 = __ballot_sync(0xffffffffu, l0 > 0), m1 = __ballot_sync(0xffffffffu, l1 > 0);
+    int cinc = l0 + l1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      long long t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+      int t = __shfl_up_sync(0xffffffffu, cinc, o);
+      if (lane >= o) cinc += t;
     }
+    const long long mine = ((long long)((l0 > 0) + (l1 > 0)) << 32) | (unsigned)(l0 + l1);
+    const long long inc = ((long long)(__popc(m0 & ltm) + __popc(m1 & ltm) + (l0 > 0) + (l1 > 0)) << 32) | (unsigned)cinc;
     if (lane == 31) tmp64[w] = inc;
     __syncthreads();
     // every warp scans the NWARPS warp totals with its first lanes
@@ -329,10 +332,18 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
     const int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;
     const int c0 = w * per, c1 = min(total, c0 + per);
     if (c0 < c1) {
-      int lo = -1, hi = nent;  // smallest j with runs[j].x > c0
-      while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (runs[mid].x > c0) hi = mid; else lo = mid;
+      // smallest j with runs[j].x > c0 (the sentinel runs[nent] qualifies): a 32-way search, every
+      // lane probes one entry per round -- two rounds of shared-memory latency for up to 1024 runs
+      // instead of ten dependent ones
+      int lo = 0, hi = nent;
+      for (;;) {
+        const int step = (hi - lo + 32) >> 5;  // ceil((hi - lo + 1) / 32)
+        const int pr = min(lo + (lane + 1) * step - 1, hi);
+        const unsigned above = __ballot_sync(0xffffffffu, runs[pr].x > c0);
+        const int L = __ffs(above) - 1;  // lane 31 probes hi, which qualifies
+        hi = min(lo + (L + 1) * step - 1, hi);
+        if (step == 1) break;
+        lo = lo + L * step;
       }
       int jl = hi;
       // jl is warp-uniform: the run holding the first candidate of the next 32.  Runs are never

@@ -305,6 +305,8 @@ int rebuild_index(Store *S, cudaStream_t st) {
   double Lt = gp.periodic ? S->period : std::max(b[5] - b[4], 1e-9);
   // cubic cells holding ~2 nodes on average; the metric weighs x, y and theta
   // equally, so the neighbourhood is a ball in these units
+  // (measured on config 2a / 2b, profiles/README.md: 1 or 4 nodes per cell and theta cells half,
+  // a quarter or twice as deep as wide are all slower or equal)
   const double occupancy = 2.0;
   double cells = std::max(1.0, (double)n / occupancy);
   double h = cbrt(Lx * Ly * Lt / cells);
