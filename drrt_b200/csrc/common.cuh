@@ -43,11 +43,14 @@ int set_error(int code, const char *fmt, ...);
   } while (0)
 
 // ---------------------------------------------------------------------------
-// Sorted node record: one 32-byte sector per candidate.
+// Sorted node record: one 32-byte sector per candidate.  gatef is gate[id] rounded to float: it
+// decides the signed theta prune of a candidate (walk_reaches, range.cu) without a second trip to
+// L2 unless the query's bound falls within the rounding of the copy; the insert kernels keep it
+// current when a later insert lowers the gate of an indexed node (store.cu, kd_insert_step).
 struct __align__(32) NodeRec {
   double x, y, th;
   int32_t id;
-  int32_t pad;
+  float gatef;
 };
 
 // Uniform bucket grid over (x, y, key(theta)); theta is the fastest index so a

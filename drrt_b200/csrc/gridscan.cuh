@@ -5,11 +5,34 @@
 // and, inside each column, one or two contiguous runs of records (theta is the
 // fastest cell index; the second run is the periodic wrap).  A warp flattens
 // the runs of 32 columns so every lane always has a candidate to evaluate.
+// Visitors are called as f(valid, x, y, theta, id, gatef).
 #pragma once
 
 #include "store.cuh"
 
 namespace drrt {
+
+// -DDRRT_PHASE_CLOCKS: thread 0 of every CTA adds the cycles between the marks of a query to
+// g_phase[k] (an experiment build, benchmarks/phase_clocks.py; the marks compile to nothing otherwise)
+#ifdef DRRT_PHASE_CLOCKS
+__device__ unsigned long long g_phase[24];
+#define DRRT_PHASE_DECL long long ph_last = clock64();
+#define DRRT_PHASE_ARG , ph_last
+#define DRRT_PHASE_PARAM , long long &ph_last
+#define DRRT_PHASE(k)                                                        \
+  do {                                                                       \
+    if (threadIdx.x == 0) {                                                  \
+      const long long ph_now = clock64();                                    \
+      atomicAdd(&g_phase[k], (unsigned long long)(ph_now - ph_last));        \
+      ph_last = ph_now;                                                      \
+    }                                                                        \
+  } while (0)
+#else
+#define DRRT_PHASE_DECL
+#define DRRT_PHASE_ARG
+#define DRRT_PHASE_PARAM
+#define DRRT_PHASE(k) do { } while (0)
+#endif
 
 static constexpr int RUNS_PER_BATCH = 64;  // 32 columns x (run + wrapped run)
 
@@ -33,15 +56,21 @@ inline GridView make_view(const Store *S) {
 }
 
 // One 32-byte record with a single 256-bit load (sm_100: LDG.E.256); two 128-bit loads fetch
-// the same sector twice and double the L1 requests of the scan.
-__device__ __forceinline__ void load_rec(const NodeRec *r, double &x, double &y, double &t, int32_t &id) {
+// the same sector twice and double the L1 requests of the scan.  gf = the float copy of gate[id].
+__device__ __forceinline__ void load_rec(const NodeRec *r, double &x, double &y, double &t, int32_t &id,
+                                         float &gf) {
   unsigned long long a, b, c, d;
   asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(r));
   x = __longlong_as_double((long long)a);
   y = __longlong_as_double((long long)b);
   t = __longlong_as_double((long long)c);
   id = (int32_t)(d & 0xffffffffull);
+  gf = __uint_as_float((unsigned)(d >> 32));
 }
+
+// candidates that come straight from the SoA arrays (the unsorted tail) carry no float gate: NaN
+// fails both of its comparisons and sends the candidate to the exact look-up
+#define DRRT_NO_GATEF __uint_as_float(0x7fc00000u)
 
 struct Query {
   double x, y, t, r;
@@ -267,14 +296,15 @@ __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, 
       const bool valid = i < total;
       double nx = 0.0, ny = 0.0, nt = 0.0;
       int32_t id = 0;
+      float gf = 0.0f;
       const int2 e = runs[min(jl + lane, nent)];
       const unsigned rel = (unsigned)(e.x - base);
       const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
       const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
       const int ey = __shfl_sync(0xffffffffu, e.y, k);
-      if (valid) load_rec(A.rec + (i + ey), nx, ny, nt, id);
+      if (valid) load_rec(A.rec + (i + ey), nx, ny, nt, id, gf);
       jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
-      f(valid, nx, ny, nt, id);
+      f(valid, nx, ny, nt, id, gf);
     }
   }
 }
@@ -287,10 +317,10 @@ __device__ __forceinline__ void scan_columns(const GridView &A, const Query &Q, 
 // lane handles UNR candidates per trip (i, i+32, ...); the run of a candidate is found from a
 // 32-run window held in the warp's registers (one REDUX.OR + POPC).  runs holds 2*T+1
 // entries, tmp64 NWARPS words.
-// f(valid[UNR], x[UNR], y[UNR], theta[UNR], id[UNR]) is called converged.
+// f(valid[UNR], x[UNR], y[UNR], theta[UNR], id[UNR], gatef[UNR]) is called converged.
 template <int NWARPS, int UNR, class F>
 __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query &Q, int2 *runs,
-                                                 long long *tmp64, F f) {
+                                                 long long *tmp64, F f DRRT_PHASE_PARAM) {
   constexpr int T = NWARPS * 32;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int ncy = Q.iy1 - Q.iy0 + 1;
@@ -312,6 +342,7 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
     const long long inc = ((long long)(__popc(m0 & ltm) + __popc(m1 & ltm) + (l0 > 0) + (l1 > 0)) << 32) | (unsigned)cinc;
     if (lane == 31) tmp64[w] = inc;
     __syncthreads();
+    DRRT_PHASE(1);
     // every warp scans the NWARPS warp totals with its first lanes
     static_assert(NWARPS <= 32, "one lane per warp total");
     long long wt = (lane < NWARPS) ? tmp64[lane] : 0, winc = wt;
@@ -329,8 +360,20 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
     if (l1 > 0) runs[slot + (l0 > 0)] = make_int2(excl + l0 + l1, s1 - (excl + l0));
     if (tid == T - 1) runs[nent] = make_int2(0x7fffffff, 0);
     __syncthreads();
+    DRRT_PHASE(2);
+#ifdef DRRT_SPLIT_OLD
     const int per = (((total + NWARPS - 1) / NWARPS) + 31) & ~31;
     const int c0 = w * per, c1 = min(total, c0 + per);
+#else
+    // whole trips (32 * UNR candidates) dealt out in contiguous blocks that differ by at most one trip:
+    // only the query's last trip is partly filled (equal shares rounded up to 32 candidates left every
+    // warp with a half-empty last trip -- 80 trips for the 71 that config 2a's 4 500 candidates need)
+    constexpr int TRIP = 32 * UNR;
+    const int ntrips = (total + TRIP - 1) / TRIP;
+    const int tq = ntrips / NWARPS, trem = ntrips - tq * NWARPS;
+    const int c0 = (w * tq + min(w, trem)) * TRIP;
+    const int c1 = min(total, c0 + (tq + (w < trem ? 1 : 0)) * TRIP);
+#endif
     if (c0 < c1) {
       // smallest j with runs[j].x > c0 (the sentinel runs[nent] qualifies): a 32-way search, every
       // lane probes one entry per round -- two rounds of shared-memory latency for up to 1024 runs
@@ -354,14 +397,15 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
         bool valid[UNR];
         double nx[UNR], ny[UNR], nt[UNR];
         int32_t id[UNR];
+        float gf[UNR];
+        DRRT_PHASE(3);
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
           const int i = base + u * 32 + lane;
           valid[u] = i < c1;
-#ifndef DRRT_SCAN_NOPRED
           nx[u] = ny[u] = nt[u] = 0.0;
           id[u] = 0;
-#endif
+          gf[u] = 0.0f;
           const int2 e = runs[min(jl + lane, nent)];  // runs[nent] is the sentinel
           // bit b of `ends`: some run of the window ends (exclusively) at candidate i0 + b.  Run jl
           // holds i0, so b >= 1, and runs are never empty, so the bits are distinct.
@@ -370,19 +414,29 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
           const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
           const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
           const int ey = __shfl_sync(0xffffffffu, e.y, k);
-#ifdef DRRT_SCAN_NOPRED
-          // padding lanes load SOME record (index clamped into the array) instead of being
-          // predicated off: no zero-fill, no predicated copies around the load; `valid` gates the hit
-          load_rec(A.rec + min(max(i + ey, 0), (int)A.n_indexed - 1), nx[u], ny[u], nt[u], id[u]);
-#else
-          if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u]);
+#ifdef DRRT_PHASE_CLOCKS
+          asm volatile("" ::"r"(ey));
+          DRRT_PHASE(16 + 2 * u);  // the run window of candidate u resolved
 #endif
+          if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u], gf[u]);
           jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
+#ifdef DRRT_PHASE_CLOCKS
+          asm volatile("" ::"r"(jl));
+          DRRT_PHASE(17 + 2 * u);  // load issued, window advanced
+#endif
         }
-        f(valid, nx, ny, nt, id);
+        DRRT_PHASE(11);
+#ifdef DRRT_PHASE_CLOCKS
+#pragma unroll
+        for (int u = 0; u < UNR; u++) asm volatile("" ::"d"(nt[u]), "r"(id[u]));  // the loads have landed
+        DRRT_PHASE(12);
+#endif
+        f(valid, nx, ny, nt, id, gf);
       }
     }
+    DRRT_PHASE(3);   // thread 0's own trips
     __syncthreads();
+    DRRT_PHASE(4);   // waiting for the slowest warp
   }
 }
 
@@ -394,15 +448,17 @@ __device__ __forceinline__ void scan_tail_cta(const GridView &A, F f) {
     bool valid[UNR];
     double nx[UNR], ny[UNR], nt[UNR];
     int32_t id[UNR];
+    float gf[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; u++) {
       int64_t i = b + (int64_t)u * NWARPS * 32 + tid;
       valid[u] = i < A.n;
       nx[u] = ny[u] = nt[u] = 0.0;
       id[u] = (int32_t)i;
+      gf[u] = DRRT_NO_GATEF;
       if (valid[u]) { nx[u] = A.x[i]; ny[u] = A.y[i]; nt[u] = A.th[i]; }
     }
-    f(valid, nx, ny, nt, id);
+    f(valid, nx, ny, nt, id, gf);
   }
 }
 
@@ -414,7 +470,7 @@ __device__ __forceinline__ void scan_tail(const GridView &A, int first, int stri
     bool valid = i < A.n;
     double nx = 0.0, ny = 0.0, nt = 0.0;
     if (valid) { nx = A.x[i]; ny = A.y[i]; nt = A.th[i]; }
-    f(valid, nx, ny, nt, (int32_t)i);
+    f(valid, nx, ny, nt, (int32_t)i, DRRT_NO_GATEF);
   }
 }
 

@@ -91,7 +91,7 @@ knn_kernel(KnnArgs A) {
   const double qx = A.q[3 * qi], qy = A.q[3 * qi + 1], qt = A.q[3 * qi + 2];
 
   double px = qx, py = qy, pt = qt;  // current probe
-  auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
+  auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id, float) {
     bool cand = false;
     double d = 0.0;
     if (valid) {
@@ -210,7 +210,7 @@ knn_select_kernel(KnnArgs A, int32_t *fallback) {
   double r = A.r0;
   bool all = false;
   int cnt = 0;
-  auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
+  auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id, float) {
     const double d = sqrt(metric_sum<METRIC>(qx, qy, qt, nx, ny, nt));
     const bool in = valid && (all || d <= r);
     const unsigned m = __ballot_sync(0xffffffffu, in);

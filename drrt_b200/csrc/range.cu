@@ -94,9 +94,22 @@ __device__ __forceinline__ GhostBand ghost_band(const Query &Q) {
   return B;
 }
 
+// walk_reaches' second clause, `!(pt - gate[id] > r)`, from the float copy of the gate that came
+// with the record: the copy is within 2^-24 relative of gate[id], the subtraction rounds once more,
+// so outside a band of a few float ulps around r the comparison on the copy IS the comparison on
+// the double.  Inside the band (or with no copy: NaN) the candidate asks for the exact look-up.
+__device__ __forceinline__ void gate_from_copy(double pt, double r, float gf, bool &reached, bool &unsure) {
+  const double a = pt - (double)gf;
+  // (a node without a gate holds 1e300, +inf as a float: the clamp keeps tol finite and a = -inf reached)
+  const double tol = 2.4e-7 * (double)fminf(fabsf(gf), 3.0e38f) + 1e-12 * (1.0 + fabs(pt));
+  const bool pruned = a > r + tol;
+  reached = a < r - tol;
+  unsure = !pruned && !reached;
+}
+
 // Candidate test: the reference's predicate with the ghost probe behind ghost_band, for UNR
 // candidates at once, written straight-line (selects, no per-candidate branches) so that the
-// FP64 chains of the candidates overlap; the gate[] look-up and the ghost pass stay behind
+// FP64 chains of the candidates overlap; the exact gate[] look-up and the ghost pass stay behind
 // warp-level branches because they are rare.  The decision is taken on the SQUARED sum against
 // the exact thresholds of the query (Query::t_lt / t_le, gridscan.cuh), which is the
 // reference's `sqrt(s) < range` bit for bit; sout receives the squared sum of the admitting
@@ -105,8 +118,8 @@ __device__ __forceinline__ GhostBand ghost_band(const Query &Q) {
 template <int METRIC, int UNR>
 __device__ __forceinline__ void eval_candidates(const Query &Q, const GhostBand &B, const bool *valid,
                                                 const double *nx, const double *ny, const double *nt,
-                                                const int32_t *id, const double *gate, bool *hit,
-                                                double *sout) {
+                                                const int32_t *id, const float *gf, const double *gate,
+                                                bool *hit, double *sout) {
   double s[UNR];
   bool askgate[UNR];
 #pragma unroll
@@ -123,9 +136,21 @@ __device__ __forceinline__ void eval_candidates(const Query &Q, const GhostBand 
     sout[u] = s[u];
   }
   if (METRIC != DRRT_METRIC_EUCLID && __any_sync(0xffffffffu, anygate)) {
+    // second clause from the float copy (no memory access); the exact look-up only inside its band
+    bool unsure[UNR], anyunsure = false;
 #pragma unroll
-    for (int u = 0; u < UNR; u++)
-      if (askgate[u]) hit[u] = !(Q.t - gate[id[u]] > Q.r);
+    for (int u = 0; u < UNR; u++) {
+      bool reached;
+      gate_from_copy(Q.t, Q.r, gf[u], reached, unsure[u]);
+      unsure[u] = unsure[u] && askgate[u];
+      if (askgate[u]) hit[u] = reached;
+      anyunsure |= unsure[u];
+    }
+    if (__any_sync(0xffffffffu, anyunsure)) {
+#pragma unroll
+      for (int u = 0; u < UNR; u++)
+        if (unsure[u]) hit[u] = !(Q.t - gate[id[u]] > Q.r);
+    }
   }
   if (Q.has_ghost) {  // kdtree.cpp:807-819; uniform
     bool needg[UNR], any = false;
@@ -142,7 +167,11 @@ __device__ __forceinline__ void eval_candidates(const Query &Q, const GhostBand 
       for (int u = 0; u < UNR; u++) {
         const bool in = needg[u] && s2[u] < Q.t_lt;   // the ghost walk admits with `<` only (:733, :765)
         bool ok = in;
-        if (METRIC != DRRT_METRIC_EUCLID && in && (Q.gt - nt[u] > Q.r)) ok = !(Q.gt - gate[id[u]] > Q.r);
+        if (METRIC != DRRT_METRIC_EUCLID && in && (Q.gt - nt[u] > Q.r)) {
+          bool reached, unsure;
+          gate_from_copy(Q.gt, Q.r, gf[u], reached, unsure);
+          ok = unsure ? !(Q.gt - gate[id[u]] > Q.r) : reached;
+        }
         if (ok) { hit[u] = true; sout[u] = s2[u]; }
       }
     }
@@ -368,10 +397,10 @@ __global__ void __launch_bounds__(WARP_MODE_WARPS * 32, DRRT_WARP_MINB) range_wa
       int32_t *gids = nullptr;
       double *gdist = nullptr;
       int cnt = 0;  // hits of this query so far: warp-uniform, in a register (every lane sees the ballot)
-      auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id) {
+      auto visit = [&](bool valid, double nx, double ny, double nt, int32_t id, float gf) {
         bool hit;
         double d;  // squared sum of the admitting probe; the key is its square root (taken at the write)
-        eval_candidates<METRIC, 1>(Q, GB, &valid, &nx, &ny, &nt, &id, V.gate, &hit, &d);
+        eval_candidates<METRIC, 1>(Q, GB, &valid, &nx, &ny, &nt, &id, &gf, V.gate, &hit, &d);
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (!m) return;
         const int pos = cnt;
@@ -540,6 +569,7 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
     __syncthreads();
 
     for (int64_t qi = q0; qi < q1; qi++) {
+      DRRT_PHASE_DECL
       if (tid == 0) { s_count = 0; s_crowded = 0; s_nlist = 0; }
       // the next slice's ticket is requested one query ahead: the round trip of the global atomic
       // is off the slice boundary, and a CTA never holds more than one query's worth of work back
@@ -551,28 +581,31 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
           reinterpret_cast<unsigned *>(&s_query)[lane] = reinterpret_cast<const unsigned *>(&s_slice[qi - q0])[lane];
       }
       __syncthreads();
+      DRRT_PHASE(0);
       const Query Q = s_query;
       const GhostBand GB = ghost_band<METRIC>(Q);
       int32_t *gids = nullptr;
       double *gdist = nullptr;
 
       auto visit_impl = [&](auto direct_tag, const bool *valid, const double *nx, const double *ny,
-                            const double *nt, const int32_t *id) {
+                            const double *nt, const int32_t *id, const float *gf) {
         constexpr bool DIRECT = decltype(direct_tag)::value;
         bool hit[UNR];
         double d[UNR];
         unsigned m[UNR];
         int tot = 0;
-        eval_candidates<METRIC, UNR>(Q, GB, valid, nx, ny, nt, id, V.gate, hit, d);
+        eval_candidates<METRIC, UNR>(Q, GB, valid, nx, ny, nt, id, gf, V.gate, hit, d);
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
           m[u] = __ballot_sync(0xffffffffu, hit[u]);
           tot += __popc(m[u]);
         }
+        DRRT_PHASE(13);
         if (tot == 0) return;
         int pos = 0;
         if (lane == 0) pos = atomicAdd(&s_count, tot);
         pos = __shfl_sync(0xffffffffu, pos, 0);
+        DRRT_PHASE(14);
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
           if (hit[u]) {
@@ -593,17 +626,21 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
           }
           pos += __popc(m[u]);
         }
+        DRRT_PHASE(15);
       };
       auto visit = [&](const bool *valid, const double *nx, const double *ny, const double *nt,
-                       const int32_t *id) { visit_impl(std::false_type{}, valid, nx, ny, nt, id); };
+                       const int32_t *id, const float *gf) {
+        visit_impl(std::false_type{}, valid, nx, ny, nt, id, gf);
+      };
       auto visit_direct = [&](const bool *valid, const double *nx, const double *ny,
-                              const double *nt, const int32_t *id) {
-        visit_impl(std::true_type{}, valid, nx, ny, nt, id);
+                              const double *nt, const int32_t *id, const float *gf) {
+        visit_impl(std::true_type{}, valid, nx, ny, nt, id, gf);
       };
 
-      if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit);
+      if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit DRRT_PHASE_ARG);
       scan_tail_cta<WARPS, UNR>(V, visit);
       __syncthreads();
+      DRRT_PHASE(5);
 
       const int n = s_count;
       const bool staged = n > 0 && n <= STAGE;
@@ -650,32 +687,51 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         }
         reinterpret_cast<uint4 *>(wstart)[tid] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         __syncthreads();
+        DRRT_PHASE(6);
         // position = bucket start + arrival rank; buckets holding several hits are listed
         // (by their first arrival) and put in id order below
-        for (int i0 = 0; i0 < n; i0 += T) {
-          const int i = i0 + tid;
-          bool listed = false;
-          unsigned ent = 0;
-          if (i < n) {
-            const unsigned b = (unsigned)sid[i] >> shift;
+        // four staged hits per thread and trip, straight-line: the four look-up chains (id -> counter
+        // word and word start -> position) overlap instead of running one after the other behind
+        // `if (i < n)`, and the shared buckets found in a trip are appended with ONE bump of the list
+        // counter per warp instead of one per hit row (a query's critical path held seven of those
+        // atomic round trips)
+        for (int i0 = 0; i0 < n; i0 += 4 * T) {
+          unsigned ent[4], m[4];
+          bool listed[4];
+          int tot = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int i = i0 + k * T + tid;
+            const bool ok = i < n;
+            const int ii = ok ? i : 0;  // some staged hit (n > 0): the loads need no guard
+            const unsigned b = (unsigned)sid[ii] >> shift;
             const unsigned wd = hist[b >> 2];
             const int sh = (b & 3u) * 8;
             const int s0 = wstart[b >> 2] + (int)__dp4a(wd & ((1u << sh) - 1u), 0x01010101u, 0u);
-            const unsigned r = srank[i];
-            tmp[s0 + r] = (uint16_t)i;
+            const unsigned r = srank[ii];
+            if (ok) tmp[s0 + r] = (uint16_t)i;
             const unsigned c = (wd >> sh) & 0xffu;
-            listed = c > 1 && r == 0;
-            ent = (unsigned)s0 | (c << 16);
+            ent[k] = (unsigned)s0 | (c << 16);
+            listed[k] = ok && c > 1 && r == 0;
           }
-          const unsigned lm = __ballot_sync(0xffffffffu, listed);
-          if (lm) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            m[k] = __ballot_sync(0xffffffffu, listed[k]);
+            tot += __popc(m[k]);
+          }
+          if (tot) {
             int lb = 0;
-            if (lane == 0) lb = atomicAdd(&s_nlist, __popc(lm));
+            if (lane == 0) lb = atomicAdd(&s_nlist, tot);
             lb = __shfl_sync(0xffffffffu, lb, 0);
-            if (listed) clist[lb + __popc(lm & ltmask)] = ent;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              if (listed[k]) clist[lb + __popc(m[k] & ltmask)] = ent[k];
+              lb += __popc(m[k]);
+            }
           }
         }
         __syncthreads();
+        DRRT_PHASE(7);
         const int nl = s_nlist;
         for (int e = tid; e < nl; e += T) {
           const unsigned ent = clist[e];
@@ -694,6 +750,7 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
           }
         }
         __syncthreads();
+        DRRT_PHASE(8);
         // the staged values are squared sums: the keys' square roots are taken here, on
         // independent elements, instead of inside the scan's dependency chain
         for (int p = tid; p < n; p += T) {
@@ -718,13 +775,15 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         __syncthreads();
         gids = oid;
         gdist = od;
-        if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit_direct);
+        if (V.n_indexed > 0) scan_columns_cta<WARPS, UNR>(V, Q, runs, s_tmp, visit_direct DRRT_PHASE_ARG);
         scan_tail_cta<WARPS, UNR>(V, visit_direct);
         __syncthreads();
         sort_pairs_global<true>(oid, od, n, tid, T);
       }
+      DRRT_PHASE(9);   // thread 0's own share of the row write
       run += n;
       __syncthreads();  // staging and scratch are free for the next query
+      DRRT_PHASE(10);
     }
     if (tid == 0) {
       A.chunk_total[ck] = run;
@@ -1066,3 +1125,14 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
 }
 
 }  // namespace drrt
+
+#ifdef DRRT_PHASE_CLOCKS
+extern "C" __attribute__((visibility("default"))) int drrt_debug_phases(unsigned long long *out, int reset) {
+  if (cudaMemcpyFromSymbol(out, drrt::g_phase, sizeof(unsigned long long) * 24) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[24] = {0};
+    if (cudaMemcpyToSymbol(drrt::g_phase, z, sizeof z) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+#endif

@@ -67,6 +67,13 @@ __global__ void kd_insert_init(int64_t base, int64_t n, const double *__restrict
   ins_gate[k] = g;
 }
 
+// where the sorted record of an indexed node lives (the float copy of its gate follows the gate)
+struct RecPatch {
+  NodeRec *rec;
+  const int32_t *cell_of, *rank, *cell_start;
+  int64_t n_indexed;
+};
+
 __device__ __forceinline__ double coord(const double *x, const double *y, const double *th,
                                         int64_t i, int s) {
   return s == 0 ? x[i] : (s == 1 ? y[i] : th[i]);
@@ -77,7 +84,8 @@ __device__ __forceinline__ bool kd_insert_step(int64_t base, int64_t k, const do
                                                const double *y, const double *th, double *gate,
                                                int32_t *parent, int32_t *left, int32_t *right,
                                                uint8_t *split, int32_t *ins_cur,
-                                               uint8_t *ins_split, double *ins_gate) {
+                                               uint8_t *ins_split, double *ins_gate,
+                                               const RecPatch &R) {
   int32_t c = ins_cur[k];
   if (c < 0) return false;
   const int32_t id = (int32_t)(base + k);
@@ -96,7 +104,10 @@ __device__ __forceinline__ bool kd_insert_step(int64_t base, int64_t k, const do
         // c now has a right child: the walk no longer treats c as a leaf when
         // the query lies to its right (kdtree.cpp:722-727 vs :747-756)
         double tc = th[c];
-        if (tc < gate[c]) gate[c] = tc;
+        if (tc < gate[c]) {
+          gate[c] = tc;
+          if (c < R.n_indexed) R.rec[R.cell_start[R.cell_of[c]] + R.rank[c]].gatef = (float)tc;
+        }
       }
       ins_cur[k] = -1;
       return false;
@@ -121,12 +132,12 @@ __global__ void kd_insert_round(int64_t base, int64_t n, const double *x, const 
                                 const double *th, double *gate, int32_t *parent,
                                 int32_t *left, int32_t *right, uint8_t *split,
                                 int32_t *ins_cur, uint8_t *ins_split, double *ins_gate,
-                                int32_t *pending) {
+                                int32_t *pending, RecPatch R) {
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   bool p = false;
   if (k < n)
     p = kd_insert_step(base, k, x, y, th, gate, parent, left, right, split, ins_cur, ins_split,
-                       ins_gate);
+                       ins_gate, R);
   int c = __syncthreads_count(p);
   if (threadIdx.x == 0 && c) atomicAdd(pending, c);
 }
@@ -136,13 +147,14 @@ __global__ void kd_insert_round(int64_t base, int64_t n, const double *x, const 
 __global__ void kd_insert_small(int64_t base, int64_t n, const double *x, const double *y,
                                 const double *th, double *gate, int32_t *parent,
                                 int32_t *left, int32_t *right, uint8_t *split,
-                                int32_t *ins_cur, uint8_t *ins_split, double *ins_gate) {
+                                int32_t *ins_cur, uint8_t *ins_split, double *ins_gate,
+                                RecPatch R) {
   int64_t k = threadIdx.x;
   for (;;) {
     bool p = false;
     if (k < n)
       p = kd_insert_step(base, k, x, y, th, gate, parent, left, right, split, ins_cur,
-                         ins_split, ins_gate);
+                         ins_split, ins_gate, R);
     if (__syncthreads_count(p) == 0) break;
   }
 }
@@ -179,10 +191,11 @@ int store_insert_dev(Store *S, int64_t n, const double *pos_dev, cudaStream_t st
                                   S->parent.p, S->left.p, S->right.p, S->split.p, S->ins_cur.p,
                                   S->ins_split.p, S->ins_gate.p);
   DRRT_LAUNCHED();
+  const RecPatch R{S->rec.p, S->cell_of.p, S->rank_in_cell.p, S->cell_start.p, S->n_indexed};
   if (n <= 1024) {
     kd_insert_small<<<1, 1024, 0, st>>>(base, n, S->x.p, S->y.p, S->th.p, S->gate.p,
                                         S->parent.p, S->left.p, S->right.p, S->split.p,
-                                        S->ins_cur.p, S->ins_split.p, S->ins_gate.p);
+                                        S->ins_cur.p, S->ins_split.p, S->ins_gate.p, R);
     DRRT_LAUNCHED();
   } else {
     // rounds in groups; the pending count of the LAST round of a group decides
@@ -193,7 +206,7 @@ int store_insert_dev(Store *S, int64_t n, const double *pos_dev, cudaStream_t st
         kd_insert_round<<<G, T, 0, st>>>(base, n, S->x.p, S->y.p, S->th.p, S->gate.p,
                                          S->parent.p, S->left.p, S->right.p, S->split.p,
                                          S->ins_cur.p, S->ins_split.p, S->ins_gate.p,
-                                         S->d_pending);
+                                         S->d_pending, R);
         DRRT_LAUNCHED();
       }
       DRRT_CUDA(cudaMemcpyAsync(S->h_pending, S->d_pending, sizeof(int32_t),
@@ -263,7 +276,7 @@ __global__ void cell_assign_kernel(int64_t n, const double *x, const double *y, 
 }
 
 __global__ void scatter_kernel(int64_t n, const double *x, const double *y, const double *th,
-                               const int32_t *cell_of, const int32_t *rank,
+                               const double *gate, const int32_t *cell_of, const int32_t *rank,
                                const int32_t *cell_start, NodeRec *rec) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -272,7 +285,7 @@ __global__ void scatter_kernel(int64_t n, const double *x, const double *y, cons
   r.y = y[i];
   r.th = th[i];
   r.id = (int32_t)i;
-  r.pad = 0;
+  r.gatef = (float)gate[i];
   rec[cell_start[cell_of[i]] + rank[i]] = r;
 }
 
@@ -338,8 +351,8 @@ int rebuild_index(Store *S, cudaStream_t st) {
                                        S->rank_in_cell.p, S->cell_start.p);
   DRRT_LAUNCHED();
   DRRT_CHECK(exclusive_scan_i32(S->cell_start.p, S->cell_start.p, ncell + 1, S->scan_tmp, st));
-  scatter_kernel<<<GN, T, 0, st>>>(n, S->x.p, S->y.p, S->th.p, S->cell_of.p, S->rank_in_cell.p,
-                                   S->cell_start.p, S->rec.p);
+  scatter_kernel<<<GN, T, 0, st>>>(n, S->x.p, S->y.p, S->th.p, S->gate.p, S->cell_of.p,
+                                   S->rank_in_cell.p, S->cell_start.p, S->rec.p);
   DRRT_LAUNCHED();
   DRRT_CUDA(cudaGetLastError());
   S->gp = gp;

@@ -197,6 +197,27 @@ def test_range_signed_prune_without_wrap(drrt, po):
     assert list(ids) == [3]
 
 
+def test_range_signed_prune_follows_later_inserts(drrt, po):
+    # the sorted records carry a float copy of gate[]: an insert that gives an INDEXED node its first
+    # right theta child lowers that node's gate, and the copy has to follow (no index rebuild in
+    # between: the tails stay under the rebuild threshold) -- both kernels, with and without ghost
+    pos = synth.box_points(60_000, 98)
+    rng = np.random.default_rng(99)
+    q = synth.box_points(400, 100)
+    q[:300, 2] = W - rng.uniform(0.0, 0.6, 300)
+    for wraps, wp in (((), ()), ((2,), (W,))):
+        t = drrt.KDTree(wraps=wraps, wrap_points=wp)
+        r = po.RefTree(wraps=wraps, wrap_points=wp)
+        done = 0
+        for chunk in (40_000, 1, 1, 500, 3, 1500, 1, 2000, 90, 1):
+            t.KDInsert(pos[done:done + chunk])
+            r.insert(pos[done:done + chunk])
+            done += chunk
+            _check(t, r, q, 1.2)        # warp-per-query kernel
+            _check(t, r, q[:48], 6.5)   # CTA-per-query kernel
+        t.close()
+
+
 def _rows_dev(drrt, res):
     """rows of a device-resident result as host arrays: offsets, counts, ids, dist"""
     off, ids, dist = drrt.KDTree.range_result_tensors(res)
