@@ -19,12 +19,8 @@ from drrt_b200 import capi, synth  # noqa: E402
 
 NAMES = [  # noqa: E501
          "clear + probe copy, barrier", "column runs, first scan, barrier", "run list, barrier",
-         "trips: first run search, loop", "wait for the slowest warp", "tail scan, barrier", "bucket prefix (2 barriers)",
-         "positions, barrier", "insertion sort, barrier", "thread 0's row write", "end barrier",
-         "trip: rest up to the loads issued", "trip: loads landed", "trip: distances, decision, ballots",
-         "trip: staging counter", "trip: staging + bucket counter",
-         "trip: window of candidate 0", "trip: load 0 issued, window advanced", "trip: window of candidate 1",
-         "trip: load 1 issued, window advanced"]
+         "thread 0's trips", "wait for the slowest warp", "tail scan, barrier", "bucket prefix (2 barriers)",
+         "positions, barrier", "insertion sort, barrier", "thread 0's row write", "end barrier"]
 dev = torch.device("cuda", 0)
 lib = capi.load()
 raw = C.CDLL(os.environ["DRRT_B200_LIB"])
@@ -34,7 +30,7 @@ tree = drrt_b200.KDTree(device=0, capacity=len(nodes))
 tree.KDInsert(nodes)
 qd = torch.from_numpy(q).to(dev)
 r = synth.shrinking_radius(len(nodes), synth.GAMMA_REF)
-out = (C.c_ulonglong * 24)()
+out = (C.c_ulonglong * 16)()
 for _ in range(3):
     tree.KDFindWithinRange_dev(r, qd)
 torch.cuda.synchronize()

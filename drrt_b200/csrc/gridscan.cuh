@@ -15,7 +15,7 @@ namespace drrt {
 // -DDRRT_PHASE_CLOCKS: thread 0 of every CTA adds the cycles between the marks of a query to
 // g_phase[k] (an experiment build, benchmarks/phase_clocks.py; the marks compile to nothing otherwise)
 #ifdef DRRT_PHASE_CLOCKS
-__device__ unsigned long long g_phase[24];
+__device__ unsigned long long g_phase[16];
 #define DRRT_PHASE_DECL long long ph_last = clock64();
 #define DRRT_PHASE_ARG , ph_last
 #define DRRT_PHASE_PARAM , long long &ph_last
@@ -398,7 +398,6 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
         double nx[UNR], ny[UNR], nt[UNR];
         int32_t id[UNR];
         float gf[UNR];
-        DRRT_PHASE(3);
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
           const int i = base + u * 32 + lane;
@@ -414,23 +413,9 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
           const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
           const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
           const int ey = __shfl_sync(0xffffffffu, e.y, k);
-#ifdef DRRT_PHASE_CLOCKS
-          asm volatile("" ::"r"(ey));
-          DRRT_PHASE(16 + 2 * u);  // the run window of candidate u resolved
-#endif
           if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u], gf[u]);
           jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
-#ifdef DRRT_PHASE_CLOCKS
-          asm volatile("" ::"r"(jl));
-          DRRT_PHASE(17 + 2 * u);  // load issued, window advanced
-#endif
         }
-        DRRT_PHASE(11);
-#ifdef DRRT_PHASE_CLOCKS
-#pragma unroll
-        for (int u = 0; u < UNR; u++) asm volatile("" ::"d"(nt[u]), "r"(id[u]));  // the loads have landed
-        DRRT_PHASE(12);
-#endif
         f(valid, nx, ny, nt, id, gf);
       }
     }

@@ -600,12 +600,10 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
           m[u] = __ballot_sync(0xffffffffu, hit[u]);
           tot += __popc(m[u]);
         }
-        DRRT_PHASE(13);
         if (tot == 0) return;
         int pos = 0;
         if (lane == 0) pos = atomicAdd(&s_count, tot);
         pos = __shfl_sync(0xffffffffu, pos, 0);
-        DRRT_PHASE(14);
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
           if (hit[u]) {
@@ -626,7 +624,6 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
           }
           pos += __popc(m[u]);
         }
-        DRRT_PHASE(15);
       };
       auto visit = [&](const bool *valid, const double *nx, const double *ny, const double *nt,
                        const int32_t *id, const float *gf) {
@@ -1128,9 +1125,9 @@ int range_batch_dev(Store *S, int64_t nq, const double *q_dev, const double *rad
 
 #ifdef DRRT_PHASE_CLOCKS
 extern "C" __attribute__((visibility("default"))) int drrt_debug_phases(unsigned long long *out, int reset) {
-  if (cudaMemcpyFromSymbol(out, drrt::g_phase, sizeof(unsigned long long) * 24) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(out, drrt::g_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
   if (reset) {
-    unsigned long long z[24] = {0};
+    unsigned long long z[16] = {0};
     if (cudaMemcpyToSymbol(drrt::g_phase, z, sizeof z) != cudaSuccess) return 1;
   }
   return 0;
