@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """A/B numbers of one build of the library (DRRT_B200_LIB selects it; default = the in-tree one):
 
-    python benchmarks/ab.py [range] [single] [edges] [loop]
+    python benchmarks/ab.py [range] [knn] [single] [edges] [loop]
 
+knn    : device time of k-nearest (k = 16) and nearest on the same queries, checksums
 range  : device time of the headline step (config 2a, 64 K queries, L2 flushed), 2b, hit checksum
 single : wall-clock per nq == 1 call of drrt_range_batch_into / drrt_nearest_batch / one-edge check
 edges  : config 3 -- device time and the host call (pinned poses) of 10 M Dubins edges
@@ -66,6 +67,16 @@ if "range" in what:
         off, ids, dist = tree.range_result_tensors(res)
         chk = int(ids[:res.total].to(torch.int64).sum().item()) ^ int(dist[:res.total].view(torch.int64).sum().item())
         print(tag, "range", name, "ms mean %.4f min %.4f" % (mean, mn), "hits", int(res.total), "checksum", chk, flush=True)
+
+if "knn" in what:
+    K = 16
+    kid = torch.empty((len(q), K), dtype=torch.int32, device=dev)
+    kd = torch.empty((len(q), K), dtype=torch.float64, device=dev)
+    for name, k in (("k16", K), ("nearest", 1)):
+        mean, mn = dev_time(lambda: tree.KDFindKNearest_dev(k, qd, kid, kd))
+        n = len(q) * k
+        chk = int(kid.view(-1)[:n].to(torch.int64).sum().item()) ^ int(kd.view(-1)[:n].view(torch.int64).sum().item())
+        print(tag, "knn", name, "ms mean %.4f min %.4f" % (mean, mn), "checksum", chk, flush=True)
 
 if "single" in what:
     small = drrt_b200.KDTree(device=0)

@@ -8,6 +8,8 @@
 // Visitors are called as f(valid, x, y, theta, id, gatef).
 #pragma once
 
+#include <type_traits>
+
 #include "store.cuh"
 
 namespace drrt {
@@ -393,7 +395,11 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
       // empty, so those 32 candidates lie in runs jl .. jl+31: every lane fetches one of them, one
       // warp-wide OR marks where runs end, and a lane's run is a population count away (no
       // divergent walk, no chain of dependent shared-memory loads or shuffles).
-      for (int base = c0; base < c1; base += 32 * UNR) {
+      // a trip of 32 * UNR candidates; FULL trips (all but the query's last one) load and test without
+      // guards -- no zero fill, no predicated copies of the eight record registers per candidate, no
+      // `i < c1` in the candidate test: 5.4 % fewer warp instructions, 3.495 -> 3.43 ms (config 2a)
+      auto trip = [&](auto full_tag, int base) {
+        constexpr bool FULL = decltype(full_tag)::value;
         bool valid[UNR];
         double nx[UNR], ny[UNR], nt[UNR];
         int32_t id[UNR];
@@ -401,10 +407,7 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
           const int i = base + u * 32 + lane;
-          valid[u] = i < c1;
-          nx[u] = ny[u] = nt[u] = 0.0;
-          id[u] = 0;
-          gf[u] = 0.0f;
+          valid[u] = FULL || i < c1;
           const int2 e = runs[min(jl + lane, nent)];  // runs[nent] is the sentinel
           // bit b of `ends`: some run of the window ends (exclusively) at candidate i0 + b.  Run jl
           // holds i0, so b >= 1, and runs are never empty, so the bits are distinct.
@@ -413,11 +416,21 @@ __device__ __forceinline__ void scan_columns_cta(const GridView &A, const Query 
           const unsigned ends = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
           const int k = __popc(ends & ((2u << lane) - 1u));  // runs ending at or before candidate i
           const int ey = __shfl_sync(0xffffffffu, e.y, k);
-          if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u], gf[u]);
+          if (FULL) {
+            load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u], gf[u]);
+          } else {
+            nx[u] = ny[u] = nt[u] = 0.0;
+            id[u] = 0;
+            gf[u] = 0.0f;
+            if (valid[u]) load_rec(A.rec + (i + ey), nx[u], ny[u], nt[u], id[u], gf[u]);
+          }
           jl += __popc(ends) + (__any_sync(0xffffffffu, rel == 32u) ? 1 : 0);
         }
         f(valid, nx, ny, nt, id, gf);
-      }
+      };
+      int base = c0;
+      for (; base + 32 * UNR <= c1; base += 32 * UNR) trip(std::true_type{}, base);
+      if (base < c1) trip(std::false_type{}, base);
     }
     DRRT_PHASE(3);   // thread 0's own trips
     __syncthreads();
