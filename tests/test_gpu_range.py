@@ -174,6 +174,30 @@ def test_range_clustered_ids_fall_back_to_network_sort(drrt, po):
     _check(t, r, q, 3.5)     # CTA-per-query mode, crowded buckets
 
 
+def test_range_cta_crowded_and_wrapped_bucket_counters(drrt, po):
+    # CTA-per-query mode sorts by id with BYTE counters per id bucket (id >> shift); ids bunched in one
+    # bucket must send the query to the network sort.  With 4.3 M nodes a bucket spans 512 ids: 40
+    # consecutive ids in one ball crowd a counter (>= 32), 400 make it wrap (>= 256: the carry lands in
+    # the neighbouring counter, and only the counters no longer adding up to the hit count shows it)
+    n = 4_300_000
+    pos = synth.box_points(n, 94)
+    rng = np.random.default_rng(95)
+    blob = lambda c, m: np.asarray(c) + rng.normal(0, 0.05, (m, 3))
+    pos[2_000_384:2_000_784] = blob([12.0, 30.0, 2.5], 400)      # bucket 3907, ids 2000384 .. 2000895
+    pos[3_000_320:3_000_360] = blob([35.0, 14.0, 4.0], 40)       # bucket 5860
+    t = drrt.KDTree(capacity=n)
+    t.KDInsert(pos)
+    r = po.RefTree()
+    r.insert(pos)
+    q = synth.box_points(24, 96)
+    q[:8] = blob([12.0, 30.0, 2.5], 8)
+    q[8:16] = blob([35.0, 14.0, 4.0], 8)
+    off = _check(t, r, q, 1.45)
+    counts = np.diff(off)
+    assert counts.min() > 256 and counts.max() <= 4608      # CTA mode, rows staged in shared memory
+    assert (counts[:8] > counts[16:].max()).all()           # the blobs are inside their queries' balls
+
+
 def test_range_signed_prune_without_wrap(drrt, po):
     # a tree created WITHOUT wrapped dimensions still uses the wrap-aware metric;
     # the reference's signed theta prune (kdtree.cpp:744-756) then hides some
