@@ -90,10 +90,8 @@ struct Query {
 };
 
 __device__ __forceinline__ int cell_floor(double v, double v0, double inv_h) {
-  double f = floor((v - v0) * inv_h);
-  if (f < -1.0e9) return -1000000000;
-  if (f > 1.0e9) return 1000000000;
-  return (int)f;
+  // one conversion that rounds down and saturates (NaN -> 0, as (int)floor(NaN)), then the clamp
+  return max(-1000000000, min(1000000000, __double2int_rd((v - v0) * inv_h)));
 }
 
 // Cells of the theta axis within `half` of key: run a = [ta0,ta1], and the
@@ -246,7 +244,10 @@ __device__ __forceinline__ void column_runs(const GridView &A, const Query &Q, i
   // must stay under sqrt(r^2 - rho^2) to be in range
   int ta0 = Q.ta0, ta1 = Q.ta1, tb0 = Q.tb0, tb1 = Q.tb1;
   if (!Q.all) {
-    double half = sqrt(fmax(Q.rr * Q.rr - rho2, 0.0)) * (1.0 + 1e-9) + 1e-9 * (1.0 + Q.rr);
+    // an upper bound is all the candidate cells need: single-precision square root of the argument
+    // rounded up, itself rounded up (a few instructions where the double one takes ~30)
+    double half = (double)__fsqrt_ru(__double2float_ru(fmax(Q.rr * Q.rr - rho2, 0.0))) * (1.0 + 1e-9) +
+                  1e-9 * (1.0 + Q.rr);
     theta_runs(g, Q.key, half, ta0, ta1, tb0, tb1);
   }
   int cbase = (ix * g.ny + iy) * g.nt;
