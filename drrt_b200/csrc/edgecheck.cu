@@ -145,8 +145,7 @@ struct WarpScratch {
   double seg[32][5];   // p0x p0y p1x p1y far2 of each lane's segment
   int start[32][4];    // up to four grid cells per segment: entry range start / length
   int len[32][4];
-  int pre[33];         // exclusive prefix of the lanes' entry counts
-  unsigned hit;
+  int own[32];         // the lanes that bring entries, in lane order: lane | (pairs before its own) << 5
 };
 
 // one grid entry (polygon edge or ball) against one segment: the reference's tests verbatim
@@ -179,14 +178,17 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
                                            double radius, WarpScratch *ws, int lane) {
   if (G.nx == 0)  // no grid (degenerate table): per-lane loop over all obstacles
     return test && segment_vs_obstacles<MASKED>(O, G, p0x, p0y, p1x, p1y, radius);
-  double lox = fmin(p0x, p1x), hix = fmax(p0x, p1x), loy = fmin(p0y, p1y), hiy = fmax(p0y, p1y);
   int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;  // empty
-  if (test && lox <= hix && loy <= hiy) {
-    double fx0 = floor((lox - G.x0) * G.inv_cell), fx1 = floor((hix - G.x0) * G.inv_cell);
-    double fy0 = floor((loy - G.y0) * G.inv_cell), fy1 = floor((hiy - G.y0) * G.inv_cell);
-    if (!(fx1 < 0.0 || fy1 < 0.0 || fx0 > (double)(G.nx - 1) || fy0 > (double)(G.ny - 1))) {
-      cx0 = (int)fmax(fx0, 0.0); cx1 = (int)fmin(fx1, (double)(G.nx - 1));
-      cy0 = (int)fmax(fy0, 0.0); cy1 = (int)fmin(fy1, (double)(G.ny - 1));
+  // cells of the segment's bounding box: the cell of each end point by one rounding-down, saturating
+  // conversion (floor is monotone: the box's low cell is the smaller of the two), compared and clamped as
+  // integers -- no double min / max / floor.  Points that are not numbers test nothing.
+  if (test && ((p0x + p1x) + (p0y + p1y)) - ((p0x + p1x) + (p0y + p1y)) == 0.0) {
+    const int ax = __double2int_rd((p0x - G.x0) * G.inv_cell), bx = __double2int_rd((p1x - G.x0) * G.inv_cell);
+    const int ay = __double2int_rd((p0y - G.y0) * G.inv_cell), by = __double2int_rd((p1y - G.y0) * G.inv_cell);
+    const int x0 = min(ax, bx), x1 = max(ax, bx), y0 = min(ay, by), y1 = max(ay, by);
+    if (!(x1 < 0 || y1 < 0 || x0 > G.nx - 1 || y0 > G.ny - 1)) {
+      cx0 = max(x0, 0); cx1 = min(x1, G.nx - 1);
+      cy0 = max(y0, 0); cy1 = min(y1, G.ny - 1);
     }
   }
   const int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
@@ -218,20 +220,33 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
     int t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
-  ws->pre[lane + 1] = inc;
-  if (lane == 0) { ws->pre[0] = 0; ws->hit = 0; }
+  // The owner of pair p is the first lane with entries whose inclusive prefix exceeds p.  The lanes
+  // that bring entries list themselves in lane order (`own`); one warp-wide OR marks the pair numbers
+  // at which a lane's entries END, and the owner of pair p is as many list places on as there are
+  // marks below p -- no search over the prefix array (five dependent shared-memory reads per pair),
+  // and the verdicts come back through a second warp-wide OR instead of a shared-memory atomic.
+  const unsigned ltm = (1u << lane) - 1u;
+  const unsigned bring = __ballot_sync(0xffffffffu, total > 0);
+  if (total > 0) ws->own[__popc(bring & ltm)] = lane | ((inc - total) << 5);
   __syncwarp();
-  const int all = ws->pre[32];
-  for (int p = lane; p < all; p += 32) {
-    int lo = 0, hi = 32;  // owner = last lane with pre[owner] <= p
-#pragma unroll
-    for (int step = 0; step < 5; step++) {
-      int mid = (lo + hi) >> 1;
-      if (ws->pre[mid] <= p) lo = mid; else hi = mid;
+  const int all = __shfl_sync(0xffffffffu, inc, 31);
+  unsigned hitmask = 0;
+  int jbase = 0;  // lanes whose entries end before `base`
+  for (int base = 0; base < all; base += 32) {
+    const int p = base + lane;
+    const unsigned rel = (unsigned)(inc - 1 - base);
+    const unsigned ends = __reduce_or_sync(0xffffffffu, (total > 0 && rel < 32u) ? 1u << rel : 0u);
+    bool h = false;
+    int lo = 0;
+    if (p < all) {
+      const int o = ws->own[jbase + __popc(ends & ltm)];
+      lo = o & 31;
+      int q = p - (o >> 5), k = 0;
+      while (q >= ws->len[lo][k]) { q -= ws->len[lo][k]; k++; }
+      h = entry_hits<MASKED>(O, G, G.idx[ws->start[lo][k] + q], ws->seg[lo], radius);
     }
-    int q = p - ws->pre[lo], k = 0;
-    while (q >= ws->len[lo][k]) { q -= ws->len[lo][k]; k++; }
-    if (entry_hits<MASKED>(O, G, G.idx[ws->start[lo][k] + q], ws->seg[lo], radius)) atomicOr(&ws->hit, 1u << lo);
+    hitmask |= __reduce_or_sync(0xffffffffu, h ? 1u << lo : 0u);
+    jbase += __popc(ends);
   }
   // segments spanning many cells: one at a time, the warp sweeps its cells
   unsigned wmask = __ballot_sync(0xffffffffu, wide);
@@ -245,12 +260,10 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
       int c = (wx0 + k / wny) * G.ny + (wy0 + k % wny);
       for (int e = G.off[c]; e < G.off[c + 1] && !h; e++) h = entry_hits<MASKED>(O, G, G.idx[e], ws->seg[L], radius);
     }
-    if (__any_sync(0xffffffffu, h) && lane == 0) atomicOr(&ws->hit, 1u << L);
+    if (__any_sync(0xffffffffu, h)) hitmask |= 1u << L;
   }
-  __syncwarp();
-  bool mine = (ws->hit >> lane) & 1u;
   __syncwarp();  // the scratch is reused by the next call
-  return mine;
+  return (hitmask >> lane) & 1u;
 }
 
 struct EdgeArgs {
