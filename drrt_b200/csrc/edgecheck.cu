@@ -141,8 +141,8 @@ __device__ __forceinline__ bool segment_vs_obstacles(const ObsView &O, const Obs
 }
 
 // Per-warp scratch of the cooperative segment test.
-struct WarpScratch {
-  double seg[32][5];   // p0x p0y p1x p1y far2 of each lane's segment
+struct __align__(16) WarpScratch {
+  double seg[32][6];   // p0x p0y p1x p1y far2 (+ pad: rows are read with 128-bit loads) of each lane's segment
   int start[32][4];    // up to four grid cells per segment: entry range start / length
   int len[32][4];
   int own[32];         // the lanes that bring entries, in lane order: lane | (pairs before its own) << 5
@@ -208,11 +208,12 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
   }
   // most segments run through empty cells: nothing to do for the whole warp
   if (!__any_sync(0xffffffffu, total > 0 || wide)) return false;
-#pragma unroll
-  for (int k = 0; k < 4; k++) { ws->start[lane][k] = st[k]; ws->len[lane][k] = ln[k]; }
+  *reinterpret_cast<int4 *>(ws->start[lane]) = make_int4(st[0], st[1], st[2], st[3]);
+  *reinterpret_cast<int4 *>(ws->len[lane]) = make_int4(ln[0], ln[1], ln[2], ln[3]);
   // cull distance: radius + an upper bound of the segment's length (|dx| + |dy|, no sqrt)
   double far = (radius + (fabs(p1x - p0x) + fabs(p1y - p0y))) * (1.0 + 1e-9) + 1e-9;
-  ws->seg[lane][0] = p0x; ws->seg[lane][1] = p0y; ws->seg[lane][2] = p1x; ws->seg[lane][3] = p1y;
+  *reinterpret_cast<double2 *>(&ws->seg[lane][0]) = make_double2(p0x, p0y);
+  *reinterpret_cast<double2 *>(&ws->seg[lane][2]) = make_double2(p1x, p1y);
   ws->seg[lane][4] = far * far;
   int inc = total;
 #pragma unroll
@@ -241,9 +242,15 @@ __device__ bool warp_segments_vs_obstacles(const ObsView &O, const ObstacleGrid 
     if (p < all) {
       const int o = ws->own[jbase + __popc(ends & ltm)];
       lo = o & 31;
-      int q = p - (o >> 5), k = 0;
-      while (q >= ws->len[lo][k]) { q -= ws->len[lo][k]; k++; }
-      h = entry_hits<MASKED>(O, G, G.idx[ws->start[lo][k] + q], ws->seg[lo], radius);
+      // the owner's four cell lists with two 128-bit loads, the cell of pair q by comparisons
+      const int4 l4 = *reinterpret_cast<const int4 *>(ws->len[lo]);
+      const int4 s4 = *reinterpret_cast<const int4 *>(ws->start[lo]);
+      const int q0 = p - (o >> 5), b1 = l4.x, b2 = b1 + l4.y, b3 = b2 + l4.z;
+      const int e = q0 < b1 ? s4.x + q0 : q0 < b2 ? s4.y + (q0 - b1) : q0 < b3 ? s4.z + (q0 - b2) : s4.w + (q0 - b3);
+      const double2 sa = *reinterpret_cast<const double2 *>(&ws->seg[lo][0]);
+      const double2 sb = *reinterpret_cast<const double2 *>(&ws->seg[lo][2]);
+      const double sg[5] = {sa.x, sa.y, sb.x, sb.y, ws->seg[lo][4]};
+      h = entry_hits<MASKED>(O, G, G.idx[e], sg, radius);
     }
     hitmask |= __reduce_or_sync(0xffffffffu, h ? 1u << lo : 0u);
     jbase += __popc(ends);
