@@ -161,7 +161,7 @@ __device__ __forceinline__ bool entry_hits(const ObsView &O, const ObstacleGrid 
   double ax, ay, bx, by;
   load_edge(G, j, ax, ay, bx, by);
   // an edge farther than radius + |segment| from p0 cannot come within radius of the segment
-  if (dist_sqrd_point_segment(sg[0], sg[1], ax, ay, bx, by) > sg[4]) return false;
+  if (dist_sqrd_point_segment_sel(sg[0], sg[1], ax, ay, bx, by) > sg[4]) return false;
   return segment_dist_sqrd(sg[0], sg[1], sg[2], sg[3], ax, ay, bx, by) < radius * radius &&  // :796-803
          within_reach(O, G.eobs[j], sg[0], sg[1], sg[2], sg[3], radius);                     // :765-779
 }
