@@ -580,8 +580,8 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
   unsigned long long *next_edge = &work[0];
   PolylineWalker W;
   W.part = 3;
-  long long e = -1;       // record this lane is walking
-  long long en = -1;      // record it walks next (in flight or landed in s_path[cur ^ 1])
+  bool e = false;         // this lane is walking a record (it sits in s_path[cur])
+  bool en = false;        // the record it walks next is in flight to, or has landed in, s_path[cur ^ 1]
   int cur = 0;
   bool exhausted = false; // no unclaimed edges left
   bool have_prev = false;
@@ -589,10 +589,10 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
   long long w_next = 0, w_end = 0;  // the warp's reserve of claimed edges (uniform)
   bool w_done = false;              // the global counter has run past the last edge
   for (;;) {
-    if (e < 0 && en >= 0) {
+    if (!e && en) {
       asm volatile("cp.async.wait_all;" ::: "memory");
-      e = en;
-      en = -1;
+      e = true;
+      en = false;
       cur ^= 1;
       W.start(&s_path[cur][threadIdx.x], A.r_min, true, true);
       have_prev = false;
@@ -600,7 +600,7 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
     // lanes without a next edge take one from the warp's reserve of claimed edges and start its
     // copy; the reserve is refilled WALK_CLAIM edges at a time, so the round trip of the global
     // atomic is paid once per WALK_CLAIM edges instead of in every trip
-    unsigned need = __ballot_sync(0xffffffffu, en < 0 && !exhausted);
+    unsigned need = __ballot_sync(0xffffffffu, !en && !exhausted);
     if (need) {
       if (w_next == w_end && !w_done) {
         unsigned long long base = 0;
@@ -612,10 +612,10 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
       }
       const int avail = (int)(w_end - w_next);
       const int rank = __popc(need & ((1u << lane) - 1));
-      if (en < 0 && !exhausted) {
+      if (!en && !exhausted) {
         if (rank < avail) {
-          en = w_next + rank;
-          const char *src = reinterpret_cast<const char *>(paths + en);
+          en = true;
+          const char *src = reinterpret_cast<const char *>(paths + (w_next + rank));
           const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_path[cur ^ 1][threadIdx.x]);
 #pragma unroll
           for (int k = 0; k < (int)sizeof(DubinsPath); k += 16)
@@ -627,7 +627,7 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
       }
       w_next += min(__popc(need), avail);
     }
-    if (__all_sync(0xffffffffu, e < 0 && en < 0)) break;
+    if (__all_sync(0xffffffffu, !e && !en)) break;
     // Lanes run ahead: most segments have no grid entry in their cells, so a lane steps along its
     // polyline -- next point, cells of the new segment -- until it holds a segment that has something
     // to be tested against (or its path ends, or WALK_AHEAD steps have passed); then the warp tests the
@@ -641,22 +641,22 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
     int total = 0;
     if (A.grid.nx == 0) {  // no grid (degenerate table): one point per round, per-lane loop over all obstacles
       bool test = false, hit1 = false;
-      if (e >= 0) {
+      if (e) {
         bool connects = false;
         if (!W.next(&cx, &cy, &connects)) ended = true;
         else test = have_prev && connects;
       }
       if (test) hit1 = segment_vs_obstacles<MASKED>(O, A.grid, px, py, cx, cy, A.robot_radius);
-      if (e >= 0) {
+      if (e) {
         if (ended || hit1) {
           A.verdict[__double_as_longlong(s_path[cur][threadIdx.x].dist)] = hit1 ? 1 : 0;
-          e = -1;
+          e = false;
         } else { px = cx; py = cy; have_prev = true; }
       }
       continue;
     }
     for (int step = 0; step < WALK_AHEAD; step++) {
-      const bool stepping = e >= 0 && !pending && !ended;
+      const bool stepping = e && !pending && !ended;
       if (!__any_sync(0xffffffffu, stepping)) break;
       if (stepping) {
         bool connects = false;
@@ -674,10 +674,10 @@ dubins_walk_kernel(EdgeArgs A, const DubinsPath *paths, unsigned long long *work
     bool hit = false;
     if (__any_sync(0xffffffffu, pending))
       hit = warp_pending_vs_obstacles<MASKED>(O, A.grid, pending ? total : 0, pending && wide, A.robot_radius, ws, lane);
-    if (e >= 0) {
+    if (e) {
       if (ended || hit) {  // :878-889 first hit decides the edge
         A.verdict[__double_as_longlong(s_path[cur][threadIdx.x].dist)] = hit ? 1 : 0;
-        e = -1;
+        e = false;
       } else if (pending) {
         px = cx;
         py = cy;
