@@ -534,16 +534,6 @@ struct PolylineWalker {
     P.type = packed;
   }
   bool fresh;      // the next point does not continue a tested polyline segment
-#ifdef DRRT_WALK_ROT
-  // The collision walk may take an arc's interior points by rotating the previous one (4 multiplies, 2
-  // adds) instead of a double-precision sincos each; an arc's first point, its exact end angle and
-  // the zero-filled tail keep sincos.  Up to 63 steps of ~1e-16 each: within 1e-14 of the sincos value,
-  // eight orders of magnitude inside the 1e-6 band the verdicts are compared in (the trig functions
-  // themselves differ from glibc's by an ulp or two).  Trajectories for the caller keep sincos.
-  bool rotate = false;
-  bool prev_ok = false;  // (pcs, psn) belong to the point one regular step before the next one
-  double pcs = 1.0, psn = 0.0;
-#endif
 
   __device__ __forceinline__ void begin_part() {
     while (part < 3) {
@@ -571,10 +561,6 @@ struct PolylineWalker {
   __device__ __forceinline__ void start(const DubinsPath *p, double r, bool skip = false, bool prep = false) {
     path = p; r_min = r; part = 0; i = 0; n = 0; kind = PART_NONE; fresh = true; skip_idle = skip;
     prepared = prep;
-#ifdef DRRT_WALK_ROT
-    rotate = skip;  // the collision walk (the only caller that skips idle parts)
-    prev_ok = false;
-#endif
     begin_part();
   }
   __device__ __forceinline__ bool done() const { return part >= 3; }
@@ -587,32 +573,17 @@ struct PolylineWalker {
       if (i == 0) { *x = cx; *y = cy; } else { *x = a; *y = b; }
     } else {
       double phi;
-      bool regular = false;  // phi is the previous regular phi -+ 0.1
       if (equal) {
         phi = (i == 0) ? a : 0.0;
       } else if (!ended) {
         bool in = (kind == PART_ARC_R) ? (val >= phi_end) : (val <= phi_end);
-        if (in) { phi = val; regular = true; if (kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
+        if (in) { phi = val; if (kind == PART_ARC_R) val -= 0.1; else val += 0.1; }
         else { phi = phi_end; ended = true; }
       } else {
         phi = 0.0;  // entries the reference's loop never reaches stay Zero()
       }
       double sn, cs;
-#ifdef DRRT_WALK_ROT
-      if (rotate && regular && prev_ok) {
-        // interior point of an arc: the previous point's (cos, sin) turned by -+0.1 rad
-        const double C = 0.99500416527802576610, S = 0.09983341664682815230;  // cos 0.1, sin 0.1
-        const double sg = (kind == PART_ARC_R) ? -S : S;
-        cs = pcs * C - psn * sg;
-        sn = psn * C + pcs * sg;
-      } else {
-        sincos(phi, &sn, &cs);
-      }
-      pcs = cs; psn = sn;
-      prev_ok = regular;
-#else
       sincos(phi, &sn, &cs);
-#endif
       *x = cx + r_min * cs;
       *y = cy + r_min * sn;
     }
@@ -642,17 +613,8 @@ struct PolylineWalker {
         }
       }
       fresh = true;
-#ifdef DRRT_WALK_ROT
-      prev_ok = false;
-#endif
     }
-    if (i >= n) {
-      part++;
-      begin_part();
-#ifdef DRRT_WALK_ROT
-      prev_ok = false;
-#endif
-    }
+    if (i >= n) { part++; begin_part(); }
     return true;
   }
 };
