@@ -398,9 +398,12 @@ int drrt_store_destroy(drrt_store *h) {
       if (S->ev_copied[b]) cudaEventDestroy(S->ev_copied[b]);
     }
     for (int b = 0; b < 2; b++) {
+      if (S->ev_join[b]) cudaEventDestroy(S->ev_join[b]);
+      if (S->side_stream[b]) cudaStreamDestroy(S->side_stream[b]);
       if (S->ev_up[b]) cudaEventDestroy(S->ev_up[b]);
       if (S->ev_done[b]) cudaEventDestroy(S->ev_done[b]);
     }
+    if (S->ev_fork) cudaEventDestroy(S->ev_fork);
     if (S->down_stream) cudaStreamDestroy(S->down_stream);
     if (S->copy_stream) cudaStreamDestroy(S->copy_stream);
     if (S->stream) cudaStreamDestroy(S->stream);

@@ -993,13 +993,32 @@ int edgecheck_batch_dev(Store *S, int64_t n, const double *start_dev, const doub
       int sms = 148;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, S->device);
       const unsigned g = (unsigned)std::min<int64_t>(nb, (int64_t)sms * 12);
-      dubins_solve_bin_kernel<CAND_RSL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 0, work);
+      // Two words (RSR, LSL) hold nine edges in ten of a planner's batch and take ~0.7 ms each; the
+      // other five bins are small and, launched one after the other, spend most of their ~0.4 ms
+      // filling and draining the machine.  They run beside the large ones on two side streams (the
+      // bins write disjoint path records and append to the work list atomically).
+      if (!S->side_stream[0]) {
+        for (int b = 0; b < 2; b++) {
+          DRRT_CUDA(cudaStreamCreateWithFlags(&S->side_stream[b], cudaStreamNonBlocking));
+          DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_join[b], cudaEventDisableTiming));
+        }
+        DRRT_CUDA(cudaEventCreateWithFlags(&S->ev_fork, cudaEventDisableTiming));
+      }
+      cudaStream_t s0 = S->side_stream[0], s1 = S->side_stream[1];
+      DRRT_CUDA(cudaEventRecord(S->ev_fork, st));
+      DRRT_CUDA(cudaStreamWaitEvent(s0, S->ev_fork, 0));
+      DRRT_CUDA(cudaStreamWaitEvent(s1, S->ev_fork, 0));
       dubins_solve_bin_kernel<CAND_RSR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 1, work);
-      dubins_solve_bin_kernel<CAND_RLR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 2, work);
-      dubins_solve_bin_kernel<CAND_LSR><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 3, work);
+      dubins_solve_bin_kernel<CAND_LSR><<<g, EDGE_T, 0, s0>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 3, work);
+      dubins_solve_bin_kernel<0><<<g, EDGE_T, 0, s1>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 6, work);
+      dubins_solve_bin_kernel<CAND_RSL><<<g, EDGE_T, 0, s0>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 0, work);
+      dubins_solve_bin_kernel<CAND_LRL><<<g, EDGE_T, 0, s1>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 5, work);
       dubins_solve_bin_kernel<CAND_LSL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 4, work);
-      dubins_solve_bin_kernel<CAND_LRL><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 5, work);
-      dubins_solve_bin_kernel<0><<<g, EDGE_T, 0, st>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 6, work);
+      dubins_solve_bin_kernel<CAND_RLR><<<g, EDGE_T, 0, s1>>>(A, paths, S->edge_perm.p, S->edge_masks.p, bins, 2, work);
+      DRRT_CUDA(cudaEventRecord(S->ev_join[0], s0));
+      DRRT_CUDA(cudaEventRecord(S->ev_join[1], s1));
+      DRRT_CUDA(cudaStreamWaitEvent(st, S->ev_join[0], 0));
+      DRRT_CUDA(cudaStreamWaitEvent(st, S->ev_join[1], 0));
       for (int k = 0; k < 10; k++) DRRT_LAUNCHED();
     }
     if (A.obs.n == 0) {

@@ -675,12 +675,16 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
         // `if (i < n)`, and the shared buckets found in a trip are appended with ONE bump of the list
         // counter per warp instead of one per hit row (a query's critical path held seven of those
         // atomic round trips)
-        for (int i0 = 0; i0 < n; i0 += 4 * T) {
-          unsigned ent[4], m[4];
-          bool listed[4];
+        // rows of 32 hits a warp has in a batch (i0 + k T + its 32 lanes, k < 4): the batches are
+        // instantiated for one to four live rows, so a warp never runs a row that lies wholly beyond n
+        // (128 rows for config 2a's 111 in the fixed four-row form)
+        auto batch = [&](auto nk_tag, int i0) {
+          constexpr int NK = decltype(nk_tag)::value;
+          unsigned ent[NK], m[NK];
+          bool listed[NK];
           int tot = 0;
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
+          for (int k = 0; k < NK; k++) {
             const int i = i0 + k * T + tid;
             const bool ok = i < n;
             const int ii = ok ? i : 0;  // some staged hit (n > 0): the loads need no guard
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
             listed[k] = ok && c > 1 && r == 0;
           }
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
+          for (int k = 0; k < NK; k++) {
             m[k] = __ballot_sync(0xffffffffu, listed[k]);
             tot += __popc(m[k]);
           }
@@ -704,11 +708,18 @@ __global__ void __launch_bounds__(CTA_T, 2) range_cta_kernel(RangeArgs A) {
             if (lane == 0) lb = atomicAdd(&s_nlist, tot);
             lb = __shfl_sync(0xffffffffu, lb, 0);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < NK; k++) {
               if (listed[k]) clist[lb + __popc(m[k] & ltmask)] = ent[k];
               lb += __popc(m[k]);
             }
           }
+        };
+        for (int i0 = 0; i0 + w * 32 < n; i0 += 4 * T) {
+          const int live = (n - i0 - w * 32 + T - 1) / T;  // rows of this warp that hold a hit (>= 1)
+          if (live >= 4) batch(std::integral_constant<int, 4>{}, i0);
+          else if (live == 3) batch(std::integral_constant<int, 3>{}, i0);
+          else if (live == 2) batch(std::integral_constant<int, 2>{}, i0);
+          else batch(std::integral_constant<int, 1>{}, i0);
         }
         __syncthreads();
         DRRT_PHASE(7);

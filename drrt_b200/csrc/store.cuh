@@ -85,6 +85,9 @@ struct Store {
   // pipelined host edge checks: poses up on copy_stream, kernels on stream, verdicts down on down_stream
   cudaStream_t down_stream = nullptr;
   cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  // ranked Dubins solve: the small single-word bins run beside the two large ones
+  cudaStream_t side_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   int32_t *d_ticket = nullptr;
   unsigned long long *d_totals = nullptr;  // inside the d_ticket allocation
   int range_grid[2] = {0, 0};  // resident grid of range_warp_kernel / range_cta_kernel on THIS device
