@@ -179,7 +179,12 @@ __device__ __forceinline__ int lane_segment_cells(const ObstacleGrid &G, double 
                                                   double p1y, double radius, WarpScratch *ws, int lane,
                                                   bool &wide) {
   int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;  // empty
-  if (((p0x + p1x) + (p0y + p1y)) - ((p0x + p1x) + (p0y + p1y)) == 0.0) {
+  // Points that are not finite numbers test nothing -- decided BESIDE the conversions (they saturate,
+  // not-a-number gives cell 0) and applied to their result, not in front of them as a branch on a chain
+  // of four dependent additions (7.34 -> 7.26 ms per 10 M edges)
+  const double fsum = (p0x + p1x) + (p0y + p1y);
+  const bool finite = fsum - fsum == 0.0;
+  {
     const int ax = __double2int_rd((p0x - G.x0) * G.inv_cell), bx = __double2int_rd((p1x - G.x0) * G.inv_cell);
     const int ay = __double2int_rd((p0y - G.y0) * G.inv_cell), by = __double2int_rd((p1y - G.y0) * G.inv_cell);
     const int x0 = min(ax, bx), x1 = max(ax, bx), y0 = min(ay, by), y1 = max(ay, by);
@@ -189,7 +194,7 @@ __device__ __forceinline__ int lane_segment_cells(const ObstacleGrid &G, double 
     }
   }
   const int ncx = cx1 - cx0 + 1, ncy = cy1 - cy0 + 1;
-  const int ncells = (ncx > 0 && ncy > 0) ? ncx * ncy : 0;
+  const int ncells = (ncx > 0 && ncy > 0 && finite) ? ncx * ncy : 0;
   wide = ncells > 4;
   int total = 0, st[4], ln[4];
 #pragma unroll
