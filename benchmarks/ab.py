@@ -123,6 +123,9 @@ if "edges" in what:
     mean, mn = dev_time(lambda: tree.ExplicitEdgeCheck_dev(verdict, start=start, end=end, robot_radius=0.5, r_min=1.0,
                                                            length_out=length), steps=5)
     print(tag, "edges device ms mean %.3f min %.3f" % (mean, mn), "collide", int(verdict.sum().item()), flush=True)
+    mean, mn = dev_time(lambda: tree.ExplicitEdgeCheck_dev(verdict, start=start, end=end, robot_radius=0.5, r_min=1.0,
+                                                           edge_kind=1, length_out=length), steps=5)
+    print(tag, "straight edges device ms mean %.3f min %.3f" % (mean, mn), "collide", int(verdict.sum().item()), flush=True)
     del start, end
     sp, ep = torch.from_numpy(s_h).pin_memory(), torch.from_numpy(e_h).pin_memory()
     vp, lp = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()

@@ -542,8 +542,12 @@ dubins_bin_scatter_kernel(int64_t n, const uint8_t *masks, unsigned long long *b
 }
 
 // MASK > 0: every edge of the bin has exactly that candidate list; MASK == 0: the list is read
+// Six CTAs per SM (80 registers, 48 - 80 B of spills in the single-word instances) instead of the five
+// that 92 registers allow: the solve is a long dependent FP64 chain per edge (issue slots 42 % busy at
+// 20 warps per SM), and the extra warps are worth more than the spills cost -- 10 M edges of config 3
+// 7.25 -> 6.96 ms; seven CTAs (72 registers, 170 B) 7.11, eight (64 registers, 240 B) 7.25.
 template <int MASK>
-__global__ void __launch_bounds__(EDGE_T)
+__global__ void __launch_bounds__(EDGE_T, 6)
 dubins_solve_bin_kernel(EdgeArgs A, DubinsPath *paths, const uint32_t *perm, const uint8_t *masks,
                         const unsigned long long *bin_state, int bin, unsigned long long *work) {
   const unsigned long long lo = bin_state[8 + bin], hi = bin_state[8 + bin + 1];
@@ -761,7 +765,11 @@ __device__ __forceinline__ int line_screen(const ObsView &O, const ObstacleGrid 
 }
 
 template <bool MASKED>
-__global__ void __launch_bounds__(EDGE_T)
+// eight CTAs per SM (64 registers): 0.784 -> 0.742 ms per 10 M straight edges (four 1.01, six 0.787, ten 0.80)
+#ifndef DRRT_LINE_MINB
+#define DRRT_LINE_MINB 8
+#endif
+__global__ void __launch_bounds__(EDGE_T, DRRT_LINE_MINB)
 linecheck_kernel(EdgeArgs A) {
   const ObsView &O = A.obs;
   const int64_t e = (int64_t)blockIdx.x * EDGE_T + threadIdx.x;
